@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- converged integrals/s (QAGS, rel_tol 1e-10) of the batched quadrature hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA engine via the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+One "step" = one pass of the hot path over one batch of synthetic parameterised integrands
+(workload S1 = BASELINE.json configs[1]: 1M smooth integrands exp(-p0 x) cos(p1 x) on [0,1],
+QAGS, Tolerance::Relative(1e-10), max_evals 2000).  Weak scaling: every rank owns a block-cyclic
+shard of N x batch integrals and the step ends with one NCCL gather of the results.
+
+Prints ONE JSON line on rank 0 (see DESIGN.md section 7 for every field).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT, ROOT / "gkquad-rs_b200"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+METRIC = "converged integrals/sec (QAGS, rel_tol 1e-10)"
+UNIT = "integrals/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="S1")
+    ap.add_argument("--batch", type=int, default=1 << 20, help="integrals per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def shard_params(W, batch, rank, world):
+    """Block-cyclic shard of the global batch of world*batch integrals;
+    every rank regenerates its own parameters from the counter-based generator."""
+    from gkquad_b200.workloads import block_cyclic_shard
+    idx = block_cyclic_shard(batch * world, rank, world)
+    # the generator is indexed by the global integral number: build per-block and concatenate
+    blocks = []
+    B = 4096
+    for s in range(0, len(idx), B):
+        start = int(idx[s])
+        cnt = min(B, len(idx) - s)
+        blocks.append(W.make_params(start, cnt))
+    return np.ascontiguousarray(np.concatenate(blocks, axis=1)), idx
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def tol_to_oracle(t):
+    return {0: ("abs", t.abs_tol), 1: ("rel", t.rel_tol), 2: ("abs_or_rel", t.abs_tol, t.rel_tol),
+            3: ("abs_and_rel", t.abs_tol, t.rel_tol)}[t.kind]
+
+
+def cpu_leg(W, p, n, seconds_target=6.0, nthreads=0):
+    """The reference's CPU implementation of the path = the golden-vector-pinned oracle port
+    (gkquad itself needs a Rust toolchain, absent here), all host threads, on the same batch."""
+    from oracle import oracle as O
+    algo = {"AUTO": 0, "QAGS": 1, "QAGP": 2}[W.algo]
+    kw = dict(params=p, tol=tol_to_oracle(W.tol), max_evals=W.max_evals, n=n, nthreads=nthreads)
+    if W.points and W.points != "param0":
+        kw["points"] = W.points
+    O.integrate_batch(algo, W.functor, W.a, W.b, **{**kw, "n": min(n, 65536), "params": p[:, :min(n, 65536)]})
+    reps, t0, best = 0, time.perf_counter(), 1e30
+    conv = 0
+    while True:
+        t1 = time.perf_counter()
+        r = O.integrate_batch(algo, W.functor, W.a, W.b, **kw)
+        dt = time.perf_counter() - t1
+        best = min(best, dt)
+        conv = int((r["status"] == 0).sum())
+        reps += 1
+        if reps >= 3 and time.perf_counter() - t0 > seconds_target:
+            break
+        if reps >= 50:
+            break
+    return conv / best, O.num_threads() if nthreads == 0 else nthreads, reps, r
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from gkquad_b200.workloads import WORKLOADS
+    W = WORKLOADS[args.workload]
+    n = args.batch
+    p = W.make_params(0, n)
+    from oracle import oracle as O
+    algo = {"AUTO": 0, "QAGS": 1, "QAGP": 2}[W.algo]
+    kw = dict(params=p, tol=tol_to_oracle(W.tol), max_evals=W.max_evals, n=n, nthreads=0)
+    if W.points and W.points != "param0":
+        kw["points"] = W.points
+    for _ in range(max(1, args.warmup)):
+        r = O.integrate_batch(algo, W.functor, W.a, W.b, **kw)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = O.integrate_batch(algo, W.functor, W.a, W.b, **kw)
+    dt = (time.perf_counter() - t0) / args.steps
+    conv = int((r["status"] == 0).sum())
+    val = conv / dt
+    cores = O.num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{W.name}: {W.description}; {W.algo}, {W.tol}, max_evals {W.max_evals}",
+                   "batch": n, "parallelism": f"{cores} host threads"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"the full {n}-integral batch per step (golden-vector-pinned C++ port of "
+                                   "gkquad's CPU path; gkquad itself needs a Rust toolchain, absent here)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    import gkquad_b200 as gk
+    from gkquad_b200.workloads import WORKLOADS
+
+    W = WORKLOADS[args.workload]
+    assert W.dim == 1, "bench.py times the 1-D hot path (the 2-D configs are parity-test cases)"
+    n = args.batch
+    algo = {"AUTO": 0, "QAGS": 1, "QAGP": 2}[W.algo]
+    eng = gk.Engine(local_rank)
+    p_host, idx = shard_params(W, n, rank, world)
+    p_dev = torch.as_tensor(p_host, device=dev)
+    kw = dict(algo=algo, tol=W.tol, max_evals=W.max_evals, n=n)
+    if W.points and W.points != "param0":
+        kw["points"] = W.points
+    elif W.points == "param0":
+        from gkquad_b200.workloads import csr_points_from_param0
+        off, pts = csr_points_from_param0(p_host)
+        kw["pts_offsets"] = torch.as_tensor(off, device=dev)
+        kw["pts"] = torch.as_tensor(pts, device=dev)
+
+    est = torch.empty(n, dtype=torch.float64, device=dev)
+    dlt = torch.empty(n, dtype=torch.float64, device=dev)
+    nev = torch.empty(n, dtype=torch.int32, device=dev)
+    st = torch.empty(n, dtype=torch.int32, device=dev)
+    # gather target (rank-major; un-permuted to block-cyclic positions by the consumer via `idx`)
+    if world > 1:
+        # one packed SoA buffer per rank: estimate | delta | (nevals, status) = 24 B / integral
+        packed = torch.empty(3 * n, dtype=torch.float64, device=dev)
+        gathered = torch.empty(world * 3 * n, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        eng.integrate_batch(W.functor, W.a, W.b, p_dev, out=(est, dlt, nev, st), **kw)
+        if world > 1:
+            packed[:n].copy_(est)
+            packed[n:2 * n].copy_(dlt)
+            packed[2 * n:].view(torch.int32)[:n].copy_(nev)
+            packed[2 * n:].view(torch.int32)[n:].copy_(st)
+            dist.all_gather_into_tensor(gathered, packed)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, device-timed, L2 flushed between steps (not timed) -------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng.reset_stats()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = eng.stats()["kernel_launches"] + (4 * args.steps if world > 1 else 0)
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    conv_local = torch.tensor([(st == 0).sum().item()], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(conv_local, op=dist.ReduceOp.SUM)
+    total_ms = float(t.item())
+    converged = float(conv_local.item())
+    ms_per_step = total_ms / args.steps
+    value = converged / (ms_per_step * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel profile (separate pass, events around every kernel on the launch stream) ----
+    eng.set_profiling(True)
+    prof_acc = {}
+    PR = 5
+    for _ in range(PR):
+        flush.zero_()
+        eng.integrate_batch(W.functor, W.a, W.b, p_dev, out=(est, dlt, nev, st), **kw)
+        for name, ms in eng.profile():
+            prof_acc.setdefault(name, []).append(ms)
+    eng.set_profiling(False)
+    eng.sync()
+    stats = eng.stats()
+    nev_h = nev.cpu().numpy().astype(np.int64)
+    fl_eval = eng.functor(1, W.functor)[3]
+    F_t = 6.0 if not (np.isfinite(W.a) and np.isfinite(W.b)) else 0.0
+    w_eval = fl_eval + F_t + 8.0  # W_i = nevals_i * (F_f + F_t + 8)
+    n25, nloop = stats["last_survivors_qk25"], stats["last_survivors_loop"]
+    evals_by_kernel = {}
+    if W.algo == "QAGS":
+        evals_by_kernel = {"k_qags_init<qk17>": 17 * n, "k_qags_init<qk25>": 25 * n25,
+                           "k_adaptive<QAGS>": int(nev_h.sum()) - 17 * n - 25 * n25}
+    else:
+        evals_by_kernel = {"k_adaptive<QAGP>": int(nev_h.sum())}
+    kernels = []
+    for name, v in prof_acc.items():
+        ms = float(np.mean(v))
+        fl = evals_by_kernel.get(name, 0) * w_eval
+        kernels.append({"kernel": name, "ms": ms, "evals": evals_by_kernel.get(name, 0),
+                        "tflops": fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0})
+    peak_flops, peak_ms = eng.measure_fp64_peak(5)
+    dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
+    whole_tflops = float(nev_h.sum()) * w_eval / (ms_per_step * 1e-3) / 1e12
+    roofline = None
+    if dom:
+        roofline = {
+            "bound": "fp64", "kernel": dom["kernel"], "achieved": dom["tflops"], "peak": peak_flops / 1e12,
+            "unit": "TFLOP/s", "frac": dom["tflops"] / (peak_flops / 1e12), "traffic": None,
+            "peak_source": "measured in this run: dependent-chain DFMA micro-kernel over all SMs "
+                           "(MEASURED_PEAKS.json carries no FP64 figure; BASELINE.md section 3)",
+            "flops_per_eval": w_eval, "kernels": kernels,
+            "whole_step": {"achieved": whole_tflops, "frac": whole_tflops / (peak_flops / 1e12)},
+            "hbm": {"algorithmic_bytes_per_step": int(n * (8 * p_host.shape[0] + 24)),
+                    "note": "HBM is two orders of magnitude from binding (SURVEY.md section 8d)"},
+        }
+
+    # ---- e2e: the public host entry (gkq_integrate_batch_host) with pinned host buffers ----------
+    e2e = None
+    if not args.no_e2e:
+        ph = torch.as_tensor(p_host).pin_memory()
+        oe = torch.empty(n, dtype=torch.float64).pin_memory()
+        od = torch.empty(n, dtype=torch.float64).pin_memory()
+        on = torch.empty(n, dtype=torch.int32).pin_memory()
+        os_ = torch.empty(n, dtype=torch.int32).pin_memory()
+        out = (oe.numpy(), od.numpy(), on.numpy().view(np.uint32), os_.numpy().view(np.uint32))
+        kwh = dict(algo=algo, tol=W.tol, max_evals=W.max_evals, n=n, out=out)
+        if W.points and W.points != "param0":
+            kwh["points"] = W.points
+        if W.points != "param0":
+            for _ in range(3):
+                eng.integrate_batch(W.functor, W.a, W.b, ph.numpy(), **kwh)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                eng.integrate_batch(W.functor, W.a, W.b, ph.numpy(), **kwh)
+            dt = (time.perf_counter() - t0) / args.steps
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            conv_e = float((out[3] == 0).sum())
+            ce = torch.tensor([conv_e], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ce, op=dist.ReduceOp.SUM)
+            e2e = {"value": float(ce.item()) / float(tt.item()), "unit": UNIT,
+                   "h2d_bytes_per_step": int(p_host.nbytes), "d2h_bytes_per_step": int(24 * n),
+                   "ms_per_step": float(tt.item()) * 1e3,
+                   "api": "gkq_integrate_batch_host (pinned host buffers, chunked H2D/compute/D2H pipeline)"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, reps, ref = cpu_leg(W, p_host, n)
+        g_est = est.cpu().numpy()
+        g_st = st.cpu().numpy().astype(np.uint32)
+        tol_abs = W.tol.to_abs(np.abs(ref["estimate"]))
+        okrows = ref["status"] == 0
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"the same {n}-integral batch, best of {reps} passes, all host threads "
+                         "(golden-vector-pinned C++ port of gkquad's CPU path; no Rust toolchain here)",
+               "parity_vs_cpu": {"status_mismatch": int((g_st != ref["status"]).sum()),
+                                 "nevals_mismatch": int((nev_h != ref["nevals"]).sum()),
+                                 "out_of_tolerance": int((np.abs(g_est - ref["estimate"])[okrows] > tol_abs[okrows]).sum())}}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{W.name}: {W.description}; {W.algo}, {W.tol}, max_evals {W.max_evals}",
+                       "batch_per_gpu": n, "global_batch": n * world,
+                       "parallelism": f"shard{world}" + ("+nccl_all_gather" if world > 1 else ""),
+                       "l2": "flushed (256 MB memset) between timed steps, outside the event brackets",
+                       "converged_fraction": converged / (n * world),
+                       "mean_nevals": float(nev_h.mean())},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

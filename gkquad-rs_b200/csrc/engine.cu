@@ -1,0 +1,999 @@
+// engine.cu -- handle, device scratch, dispatch and the C ABI of libgkquad_b200.so
+// (include/gkquad_b200.h).  No torch, no oracle, no CPU fallback: without a CUDA device
+// gkq_create fails and nothing can be computed.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gkquad_b200.h"
+#include "kernels_1d.cuh"
+#include "kernels_2d.cuh"
+
+namespace gkq {
+
+#define GKQ_ROW(ID, NAME, NP, FL) {NAME, NP, FL},
+static const FunctorInfo F1_TABLE[F1_COUNT] = {GKQ_F1_LIST(GKQ_ROW)};
+static const FunctorInfo F2_TABLE[F2_COUNT] = {GKQ_F2_LIST(GKQ_ROW)};
+static const FunctorInfo YR_TABLE[YR_COUNT] = {GKQ_YR_LIST(GKQ_ROW)};
+#undef GKQ_ROW
+
+static thread_local std::string g_create_error = "";
+
+// ---- small kernels that are not templated on a functor ----------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_fill_result(long long n, Outputs O, double est, double dlt,
+                                                       uint32_t nev, uint32_t st) {
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i < n) write_result(O, i, est, dlt, nev, st);
+}
+
+// AUTO over a CSR batch (auto.rs:29-33): integrals without points -> QAGS worklist, with
+// points -> QAGP worklist; also records the largest per-integral point count.
+__global__ void __launch_bounds__(BLOCK) k_split_auto(long long n, const long long* pts_offsets,
+                                                      unsigned int* listS, unsigned int* listP,
+                                                      Control* ctl, int mode) {
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    const bool valid = i < n;
+    long long cnt = 0;
+    if (valid) cnt = pts_offsets[i + 1] - pts_offsets[i];
+    // mode 0 = AUTO split, 1 = everything to QAGP (only the max count is needed)
+    if (mode == 0) {
+        list_append(valid && cnt == 0, (unsigned int)i, listS, &ctl->countS);
+        list_append(valid && cnt != 0, (unsigned int)i, listP, &ctl->countP);
+    }
+    // max points per integral -> pad[0]
+    unsigned long long m = (unsigned long long)(cnt > 0 ? cnt : 0);
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, m, o);
+        m = other > m ? other : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(&ctl->pad[0], m);
+}
+
+// FP64 pipe calibration: 8 independent dependent-DFMA chains per thread.
+__global__ void __launch_bounds__(BLOCK) k_dfma_peak(double* sink, int iters, double seed) {
+    double x0 = seed + threadIdx.x, x1 = x0 + 1., x2 = x0 + 2., x3 = x0 + 3.;
+    double x4 = x0 + 4., x5 = x0 + 5., x6 = x0 + 6., x7 = x0 + 7.;
+    const double m = 0.999999, c = 1e-9;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, m, c); x1 = fma(x1, m, c); x2 = fma(x2, m, c); x3 = fma(x3, m, c);
+        x4 = fma(x4, m, c); x5 = fma(x5, m, c); x6 = fma(x6, m, c); x7 = fma(x7, m, c);
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) sink[0] = s;  // never true: keeps the chains alive
+}
+
+}  // namespace gkq
+
+using namespace gkq;
+
+// ---- handle ----------------------------------------------------------------------------------
+struct gkq_handle_s {
+    int device = 0;
+    int sm_count = 0;
+    size_t total_mem = 0;
+    std::string err;
+    gkq_stats stats{};
+
+    Control* ctl = nullptr;       // device
+    Control* ctl_host = nullptr;  // pinned mirror for lazy read-back
+    bool ctl_pending = false;
+
+    // per-batch scratch, grown on demand
+    size_t cap_n = 0;
+    double* abs0 = nullptr;
+    unsigned int *list25 = nullptr, *listLoop = nullptr, *listS = nullptr, *listP = nullptr;
+
+    size_t slab_d_elems = 0, slab_w_elems = 0;
+    double* slab_d = nullptr;
+    int* slab_w = nullptr;
+
+    size_t dev_pts_cap = 0;
+    double* dev_pts = nullptr;     // shared points (device copy)
+    double* host_pts = nullptr;    // pinned staging for the shared points
+    size_t host_pts_cap = 0;
+
+    // host-entry staging (gkq_integrate_batch_host)
+    cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
+    size_t stage_bytes = 0;
+    char* stage_dev = nullptr;
+    size_t stage_pin_bytes = 0;
+    char* stage_pin = nullptr;
+
+    // optional per-kernel timing (gkq_set_profiling): one CUDA event pair per launch
+    bool profiling = false;
+    struct ProfEntry {
+        const char* name;
+        cudaEvent_t e0, e1;
+    };
+    std::vector<ProfEntry> prof;
+    std::vector<cudaEvent_t> prof_pool;
+
+    Launch1D l1[F1_COUNT];
+    int occ_loop[F1_COUNT], occ_qagp[F1_COUNT], occ_init25[F1_COUNT];
+    Launch2D l2[F2_COUNT];
+    int occ_2d[F2_COUNT][2];
+};
+
+namespace {
+
+int fail(gkq_handle_t h, int code, const std::string& msg) {
+    if (h)
+        h->err = msg;
+    else
+        g_create_error = msg;
+    return code;
+}
+#define GKQ_CUDA(h, call)                                                                       \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            char buf_[512];                                                                     \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                     __FILE__, __LINE__);                                                       \
+            return fail(h, e_ == cudaErrorMemoryAllocation ? GKQ_ERR_OUT_OF_MEMORY : GKQ_ERR_CUDA, \
+                        buf_);                                                                  \
+        }                                                                                       \
+    } while (0)
+
+template <int ID>
+struct FillL1 {
+    static void go(gkq_handle_s* h) {
+        h->l1[ID] = make_launch1d<ID>();
+        h->occ_loop[ID] = h->occ_qagp[ID] = h->occ_init25[ID] = -1;
+        FillL1<ID + 1>::go(h);
+    }
+};
+template <>
+struct FillL1<F1_COUNT> {
+    static void go(gkq_handle_s*) {}
+};
+template <int ID>
+struct FillL2 {
+    static void go(gkq_handle_s* h) {
+        h->l2[ID] = make_launch2d<ID>();
+        h->occ_2d[ID][0] = h->occ_2d[ID][1] = -1;
+        FillL2<ID + 1>::go(h);
+    }
+};
+template <>
+struct FillL2<F2_COUNT> {
+    static void go(gkq_handle_s*) {}
+};
+
+template <class T>
+int grow(gkq_handle_t h, T*& p, size_t& have, size_t want) {
+    if (want <= have) return 0;
+    if (p) {
+        GKQ_CUDA(h, cudaFree(p));
+        h->stats.scratch_bytes -= have * sizeof(T);
+        p = nullptr;
+        have = 0;
+    }
+    size_t w = want + want / 8;
+    GKQ_CUDA(h, cudaMalloc(&p, w * sizeof(T)));
+    have = w;
+    h->stats.scratch_bytes += w * sizeof(T);
+    return 0;
+}
+
+int ensure_batch_scratch(gkq_handle_t h, size_t n) {
+    if (n <= h->cap_n) return 0;
+    size_t dummy;
+    size_t w = n + n / 8 + 1024;
+    auto re = [&](auto*& p) -> int {
+        using T = std::remove_reference_t<decltype(*p)>;
+        size_t have = h->cap_n;
+        T* q = p;
+        dummy = have;
+        int rc = grow(h, q, dummy, w);
+        p = q;
+        return rc;
+    };
+    int rc;
+    if ((rc = re(h->abs0))) return rc;
+    if ((rc = re(h->list25))) return rc;
+    if ((rc = re(h->listLoop))) return rc;
+    if ((rc = re(h->listS))) return rc;
+    if ((rc = re(h->listP))) return rc;
+    h->cap_n = w;  // every grow() call allocated >= w elements
+    return 0;
+}
+
+// Per-thread slabs for `threads` persistent threads with `cap` interval slots each.
+int ensure_slab(gkq_handle_t h, unsigned long long threads, int cap, int npts_max, SlabGeom& g) {
+    const unsigned long long nd = slab_doubles(cap, npts_max) * threads;
+    const unsigned long long nw = slab_ints(cap) * threads;
+    int rc;
+    if ((rc = grow(h, h->slab_d, h->slab_d_elems, (size_t)nd))) return rc;
+    if ((rc = grow(h, h->slab_w, h->slab_w_elems, (size_t)nw))) return rc;
+    g.dbase = h->slab_d;
+    g.wbase = h->slab_w;
+    g.stride = threads;
+    g.cap = cap;
+    g.npts_max = npts_max;
+    return 0;
+}
+
+int check_tol(gkq_handle_t h, const gkq_tolerance& t) {
+    if (t.kind < 0 || t.kind > 3) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown tolerance kind");
+    const bool need_abs = t.kind != GKQ_TOL_RELATIVE, need_rel = t.kind != GKQ_TOL_ABSOLUTE;
+    if ((need_abs && t.abs_tol != t.abs_tol) || (need_rel && t.rel_tol != t.rel_tol))
+        return fail(h, GKQ_ERR_NAN_INPUT, "Tolerance must not contain NAN.");  // integrator.rs:71
+    return 0;
+}
+
+int upload_shared_points(gkq_handle_t h, const double* pts, size_t count, cudaStream_t st) {
+    if (count == 0) return 0;
+    int rc;
+    if ((rc = grow(h, h->dev_pts, h->dev_pts_cap, count))) return rc;
+    if (count > h->host_pts_cap) {
+        if (h->host_pts) GKQ_CUDA(h, cudaFreeHost(h->host_pts));
+        h->host_pts = nullptr;
+        GKQ_CUDA(h, cudaMallocHost(&h->host_pts, (count + 64) * sizeof(double)));
+        h->host_pts_cap = count + 64;
+    } else {
+        // the previous batch may still be reading the staging buffer
+        GKQ_CUDA(h, cudaStreamSynchronize(st));
+    }
+    memcpy(h->host_pts, pts, count * sizeof(double));
+    GKQ_CUDA(h, cudaMemcpyAsync(h->dev_pts, h->host_pts, count * sizeof(double),
+                                cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+// Persistent grid size: resident blocks on every SM, bounded by the slab memory budget.
+int persistent_grid(gkq_handle_t h, int occ, int cap, int npts_max) {
+    if (occ < 1) occ = 1;
+    unsigned long long per_thread = slab_doubles(cap, npts_max) * 8ull + slab_ints(cap) * 4ull;
+    unsigned long long budget = (unsigned long long)h->total_mem / 3ull;
+    unsigned long long max_threads = budget / per_thread;
+    long long grid = (long long)h->sm_count * occ;
+    long long max_grid = (long long)(max_threads / BLOCK);
+    if (max_grid < 1) return -1;
+    if (grid > max_grid) grid = max_grid;
+    return (int)grid;
+}
+
+int launch_check(gkq_handle_t h, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "launch of %s failed: %s", what, cudaGetErrorString(e));
+        return fail(h, GKQ_ERR_CUDA, buf);
+    }
+    h->stats.kernel_launches += 1;
+    return 0;
+}
+
+// Bracket a kernel launch with events on its own stream when profiling is on.
+void prof_begin(gkq_handle_t h, const char* name, cudaStream_t st) {
+    if (!h->profiling) return;
+    gkq_handle_s::ProfEntry pe;
+    pe.name = name;
+    auto get = [&]() {
+        cudaEvent_t ev;
+        if (!h->prof_pool.empty()) {
+            ev = h->prof_pool.back();
+            h->prof_pool.pop_back();
+        } else {
+            cudaEventCreate(&ev);
+        }
+        return ev;
+    };
+    pe.e0 = get();
+    pe.e1 = get();
+    cudaEventRecord(pe.e0, st);
+    h->prof.push_back(pe);
+}
+void prof_end(gkq_handle_t h, cudaStream_t st) {
+    if (!h->profiling || h->prof.empty()) return;
+    cudaEventRecord(h->prof.back().e1, st);
+}
+void prof_clear(gkq_handle_t h) {
+    for (auto& pe : h->prof) {
+        h->prof_pool.push_back(pe.e0);
+        h->prof_pool.push_back(pe.e1);
+    }
+    h->prof.clear();
+}
+
+}  // namespace
+
+// ---- C ABI -----------------------------------------------------------------------------------
+extern "C" {
+
+int gkq_abi_version(void) { return GKQ_ABI_VERSION; }
+
+int gkq_config_default(int dim, gkq_config* cfg) {
+    if (!cfg || (dim != 1 && dim != 2)) return GKQ_ERR_INVALID_ARGUMENT;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->algo = GKQ_ALGO_AUTO;
+    cfg->tol.kind = GKQ_TOL_ABS_OR_REL;  // common.rs:44-49
+    cfg->tol.abs_tol = 1.49e-8;
+    cfg->tol.rel_tol = 1.49e-8;
+    cfg->max_evals = dim == 1 ? 2000 : 100000;  // single/common.rs:120, double/common.rs:27
+    cfg->workspace_capacity = 0;
+    cfg->points = nullptr;
+    cfg->npoints = 0;
+    return GKQ_OK;
+}
+
+int gkq_create(int device, gkq_handle_t* out) {
+    if (!out) return fail(nullptr, GKQ_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, GKQ_ERR_NO_DEVICE,
+                    std::string("no CUDA device available (there is no CPU fallback): ") +
+                        cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, GKQ_ERR_INVALID_ARGUMENT, "bad device index");
+    gkq_handle_s* h = new gkq_handle_s();
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, GKQ_ERR_CUDA, "cudaSetDevice failed");
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, GKQ_ERR_CUDA, "cudaGetDeviceProperties failed");
+    }
+    if (prop.major < 10) {
+        delete h;
+        return fail(nullptr, GKQ_ERR_UNSUPPORTED,
+                    "this library carries sm_100a code only (B200); device is older");
+    }
+    h->sm_count = prop.multiProcessorCount;
+    h->total_mem = prop.totalGlobalMem;
+    FillL1<0>::go(h);
+    FillL2<0>::go(h);
+    if (cudaMalloc(&h->ctl, sizeof(Control)) != cudaSuccess ||
+        cudaMallocHost(&h->ctl_host, sizeof(Control)) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, GKQ_ERR_CUDA, "handle allocation failed");
+    }
+    memset(h->ctl_host, 0, sizeof(Control));
+    *out = h;
+    return GKQ_OK;
+}
+
+int gkq_destroy(gkq_handle_t h) {
+    if (!h) return GKQ_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    cudaFree(h->ctl);
+    cudaFreeHost(h->ctl_host);
+    cudaFree(h->abs0);
+    cudaFree(h->list25);
+    cudaFree(h->listLoop);
+    cudaFree(h->listS);
+    cudaFree(h->listP);
+    cudaFree(h->slab_d);
+    cudaFree(h->slab_w);
+    cudaFree(h->dev_pts);
+    cudaFreeHost(h->host_pts);
+    cudaFree(h->stage_dev);
+    cudaFreeHost(h->stage_pin);
+    prof_clear(h);
+    for (auto ev : h->prof_pool) cudaEventDestroy(ev);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    delete h;
+    return GKQ_OK;
+}
+
+const char* gkq_last_error(gkq_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+static const FunctorInfo* table_of(int dim, int* count) {
+    switch (dim) {
+        case 1: *count = F1_COUNT; return F1_TABLE;
+        case 2: *count = F2_COUNT; return F2_TABLE;
+        case 0: *count = YR_COUNT; return YR_TABLE;
+        default: *count = 0; return nullptr;
+    }
+}
+int gkq_functor_count(int dim) {
+    int c;
+    return table_of(dim, &c) ? c : GKQ_ERR_INVALID_ARGUMENT;
+}
+int gkq_functor_info(int dim, int id, const char** name, int* nparams, double* flops_per_eval) {
+    int c;
+    const FunctorInfo* t = table_of(dim, &c);
+    if (!t || id < 0 || id >= c) return GKQ_ERR_INVALID_ARGUMENT;
+    if (name) *name = t[id].name;
+    if (nparams) *nparams = t[id].nparams;
+    if (flops_per_eval) *flops_per_eval = t[id].flops;
+    return GKQ_OK;
+}
+int gkq_functor_lookup(int dim, const char* name) {
+    int c;
+    const FunctorInfo* t = table_of(dim, &c);
+    if (!t || !name) return GKQ_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < c; ++i)
+        if (strcmp(t[i].name, name) == 0) return i;
+    return GKQ_ERR_INVALID_ARGUMENT;
+}
+
+int gkq_sync(gkq_handle_t h, void* stream) {
+    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
+    GKQ_CUDA(h, cudaSetDevice(h->device));
+    GKQ_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+    if (h->ctl_pending) {
+        h->stats.last_survivors_qk25 = h->ctl_host->count25;
+        h->stats.last_survivors_loop = h->ctl_host->countLoop;
+        h->ctl_pending = false;
+    }
+    return GKQ_OK;
+}
+
+int gkq_get_stats(gkq_handle_t h, gkq_stats* out) {
+    if (!h || !out) return GKQ_ERR_INVALID_ARGUMENT;
+    *out = h->stats;
+    return GKQ_OK;
+}
+int gkq_reset_stats(gkq_handle_t h) {
+    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
+    uint64_t keep = h->stats.scratch_bytes;
+    memset(&h->stats, 0, sizeof h->stats);
+    h->stats.scratch_bytes = keep;
+    return GKQ_OK;
+}
+
+int gkq_set_profiling(gkq_handle_t h, int enable) {
+    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
+    h->profiling = enable != 0;
+    if (!h->profiling) prof_clear(h);
+    return GKQ_OK;
+}
+
+int gkq_get_profile(gkq_handle_t h, int max_entries, const char** names, float* ms) {
+    if (!h || max_entries < 0) return GKQ_ERR_INVALID_ARGUMENT;
+    int k = 0;
+    for (auto& pe : h->prof) {
+        if (k >= max_entries) break;
+        if (cudaEventSynchronize(pe.e1) != cudaSuccess) return fail(h, GKQ_ERR_CUDA, "profile event sync failed");
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, pe.e0, pe.e1) != cudaSuccess) return fail(h, GKQ_ERR_CUDA, "profile event read failed");
+        if (names) names[k] = pe.name;
+        if (ms) ms[k] = t;
+        ++k;
+    }
+    return k;
+}
+
+int gkq_measure_fp64_peak(gkq_handle_t h, int repeats, double* flops_per_s, double* ms_out) {
+    if (!h || !flops_per_s) return GKQ_ERR_INVALID_ARGUMENT;
+    GKQ_CUDA(h, cudaSetDevice(h->device));
+    if (repeats < 1) repeats = 1;
+    const int iters = 1 << 16;
+    const int grid = h->sm_count * 8;
+    cudaEvent_t e0, e1;
+    GKQ_CUDA(h, cudaEventCreate(&e0));
+    GKQ_CUDA(h, cudaEventCreate(&e1));
+    double best = 1e30;
+    for (int r = 0; r < repeats + 1; ++r) {  // first trip is a warm-up
+        GKQ_CUDA(h, cudaEventRecord(e0, 0));
+        k_dfma_peak<<<grid, BLOCK>>>((double*)h->ctl, iters, 1.0 + r);
+        GKQ_CUDA(h, cudaEventRecord(e1, 0));
+        GKQ_CUDA(h, cudaEventSynchronize(e1));
+        float ms = 0;
+        GKQ_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+        if (r > 0 && ms < best) best = ms;
+    }
+    int rc = launch_check(h, "k_dfma_peak");
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+    const double flops = (double)grid * BLOCK * 8.0 * (double)iters * 2.0;
+    *flops_per_s = flops / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    return GKQ_OK;
+}
+
+// ---- 1-D ----------------------------------------------------------------------------------------
+static int run_qags(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, cudaStream_t st) {
+    // P.worklist / worklist_count may select a subset (AUTO split); n is the upper bound
+    int rc;
+    if (P.max_evals < 17) {  // qags.rs:86-88 -- only reachable without a worklist split
+        const int grid = (int)((P.n + BLOCK - 1) / BLOCK);
+        if (P.worklist) return fail(h, GKQ_ERR_UNSUPPORTED, "max_evals < 17 with a CSR AUTO batch");
+        k_fill_result<<<grid, BLOCK, 0, st>>>(P.n, P.out, 0.0, F64_MAX, 0u, ST_INSUFFICIENT_ITERATION);
+        return launch_check(h, "k_fill_result");
+    }
+    const long long nblocks = (P.n + BLOCK - 1) / BLOCK;
+    prof_begin(h, "k_qags_init<qk17>", st);
+    L.qags_init17(P, (int)nblocks, st);
+    prof_end(h, st);
+    if ((rc = launch_check(h, "k_qags_init<qk17>"))) return rc;
+
+    if (h->occ_init25[fid] < 0) h->occ_init25[fid] = L.occupancy_init25();
+    long long g25 = (long long)h->sm_count * (h->occ_init25[fid] > 0 ? h->occ_init25[fid] : 1);
+    if (g25 > nblocks) g25 = nblocks;
+    prof_begin(h, "k_qags_init<qk25>", st);
+    L.qags_init25(P, (int)g25, st);
+    prof_end(h, st);
+    if ((rc = launch_check(h, "k_qags_init<qk25>"))) return rc;
+
+    if (h->occ_loop[fid] < 0) h->occ_loop[fid] = L.occupancy_loop();
+    const unsigned long long need = (P.max_evals - 17) / 50 + 1;  // qags.rs:98-99, nevals >= 17
+    const unsigned long long lim = reserve_cap(P.ws_capacity, need);
+    if (need > (1ull << 26)) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
+    const int cap = (int)need;  // list length never exceeds the reserve request
+    (void)lim;
+    int grid = persistent_grid(h, h->occ_loop[fid], cap, 0);
+    if (grid < 1) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
+    if ((long long)grid > nblocks) grid = (int)nblocks;
+    if ((rc = ensure_slab(h, (unsigned long long)grid * BLOCK, cap, 0, P.slab))) return rc;
+    prof_begin(h, "k_adaptive<QAGS>", st);
+    L.qags_loop(P, grid, st);
+    prof_end(h, st);
+    return launch_check(h, "k_adaptive<QAGS>");
+}
+
+static int run_qagp(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, int npts_max,
+                    cudaStream_t st) {
+    int rc;
+    if (h->occ_qagp[fid] < 0) h->occ_qagp[fid] = L.occupancy_qagp();
+    // list length <= nint + (max_evals - 25 nint)/50 <= nint + max_evals/50
+    const unsigned long long need = (unsigned long long)npts_max + 1ull + P.max_evals / 50ull + 1ull;
+    if (need > (1ull << 26)) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
+    const int cap = (int)need;
+    const long long nblocks = (P.n + BLOCK - 1) / BLOCK;
+    int grid = persistent_grid(h, h->occ_qagp[fid], cap, npts_max + 2);
+    if (grid < 1) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
+    if ((long long)grid > nblocks) grid = (int)nblocks;
+    if ((rc = ensure_slab(h, (unsigned long long)grid * BLOCK, cap, npts_max + 2, P.slab))) return rc;
+    prof_begin(h, "k_adaptive<QAGP>", st);
+    L.qagp(P, grid, st);
+    prof_end(h, st);
+    return launch_check(h, "k_adaptive<QAGP>");
+}
+
+int gkq_integrate_batch(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
+                        const double* a, const double* b, int64_t range_stride,
+                        const double* params, int64_t param_stride, const int64_t* pts_offsets,
+                        const double* pts, double* out_estimate, double* out_delta,
+                        uint32_t* out_nevals, uint32_t* out_status, void* stream) {
+    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
+    if (!cfg) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "cfg is NULL");
+    if (functor_id < 0 || functor_id >= F1_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown functor id");
+    if (n < 0 || n > 0xffffffffll) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "n out of range");
+    if (cfg->algo < 0 || cfg->algo > 2) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown algorithm");
+    if (range_stride != 0 && range_stride != 1) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "range_stride must be 0 or 1");
+    if (param_stride != 0 && param_stride < n) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "param_stride must be 0 or >= n");
+    if (cfg->max_evals > 0x7fffffffull) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "max_evals must fit in 31 bits");
+    if (cfg->npoints < 0 || (cfg->npoints > 0 && !cfg->points)) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "points is NULL");
+    int rc;
+    if ((rc = check_tol(h, cfg->tol))) return rc;
+    for (int64_t k = 0; k < cfg->npoints; ++k)
+        if (cfg->points[k] != cfg->points[k])  // integrator.rs:86-90
+            return fail(h, GKQ_ERR_NAN_INPUT, "cannot include NAN value in singular points");
+    if (n == 0) return GKQ_OK;
+    if (!a || !b || !out_estimate || !out_delta || !out_nevals || !out_status)
+        return fail(h, GKQ_ERR_INVALID_ARGUMENT, "NULL array argument");
+    if (F1_TABLE[functor_id].nparams > 0 && !params) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "params is NULL");
+    if (pts_offsets && !pts) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "pts is NULL");
+
+    GKQ_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = ensure_batch_scratch(h, (size_t)n))) return rc;
+
+    Batch1D P;
+    memset(&P, 0, sizeof P);
+    P.n = n;
+    P.a = a;
+    P.b = b;
+    P.range_stride = range_stride;
+    P.params = params;
+    P.param_stride = param_stride;
+    P.tol.kind = cfg->tol.kind;
+    P.tol.abs_tol = cfg->tol.abs_tol;
+    P.tol.rel_tol = cfg->tol.rel_tol;
+    P.max_evals = cfg->max_evals;
+    P.ws_capacity = cfg->workspace_capacity;
+    P.out.estimate = out_estimate;
+    P.out.delta = out_delta;
+    P.out.nevals = out_nevals;
+    P.out.status = out_status;
+    P.ctl = h->ctl;
+    P.abs0 = h->abs0;
+    P.list25 = h->list25;
+    P.listLoop = h->listLoop;
+
+    if (h->profiling) prof_clear(h);
+    GKQ_CUDA(h, cudaMemsetAsync(h->ctl, 0, sizeof(Control), st));
+    const Launch1D& L = h->l1[functor_id];
+    h->stats.batches += 1;
+    h->stats.integrals += (uint64_t)n;
+
+    if (!pts_offsets) {
+        const bool use_qags = cfg->algo == GKQ_ALGO_QAGS || (cfg->algo == GKQ_ALGO_AUTO && cfg->npoints == 0);
+        if (use_qags) {
+            rc = run_qags(h, L, functor_id, P, st);
+        } else {
+            if ((rc = upload_shared_points(h, cfg->points, (size_t)cfg->npoints, st))) return rc;
+            P.pts = h->dev_pts;
+            P.npts_shared = (int)cfg->npoints;
+            rc = run_qagp(h, L, functor_id, P, (int)cfg->npoints, st);
+        }
+    } else if (cfg->algo == GKQ_ALGO_QAGS) {
+        rc = run_qags(h, L, functor_id, P, st);  // explicit QAGS ignores points
+    } else {
+        // CSR points: split for AUTO and find the largest point count (one small sync)
+        const int grid = (int)((n + BLOCK - 1) / BLOCK);
+        const int mode = cfg->algo == GKQ_ALGO_AUTO ? 0 : 1;
+        k_split_auto<<<grid, BLOCK, 0, st>>>(n, (const long long*)pts_offsets, h->listS, h->listP, h->ctl, mode);
+        if ((rc = launch_check(h, "k_split_auto"))) return rc;
+        GKQ_CUDA(h, cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
+        GKQ_CUDA(h, cudaStreamSynchronize(st));
+        const int npts_max = (int)h->ctl_host->pad[0];
+        P.pts_offsets = (const long long*)pts_offsets;
+        P.pts = pts;
+        if (mode == 0) {
+            Batch1D PS = P;
+            PS.worklist = h->listS;
+            PS.worklist_count = &h->ctl->countS;
+            if (h->ctl_host->countS > 0 && (rc = run_qags(h, L, functor_id, PS, st))) return rc;
+            Batch1D PP = P;
+            PP.worklist = h->listP;
+            PP.worklist_count = &h->ctl->countP;
+            if (h->ctl_host->countP > 0) rc = run_qagp(h, L, functor_id, PP, npts_max, st);
+        } else {
+            rc = run_qagp(h, L, functor_id, P, npts_max, st);
+        }
+    }
+    if (rc) return rc;
+    // lazy read-back of the worklist sizes for gkq_get_stats
+    GKQ_CUDA(h, cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
+    h->ctl_pending = true;
+    return GKQ_OK;
+}
+
+int gkq_qk_batch(gkq_handle_t h, int rule, int functor_id, int64_t n, const double* a,
+                 const double* b, int64_t range_stride, const double* params,
+                 int64_t param_stride, double* out4, void* stream) {
+    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
+    if (rule != 17 && rule != 25) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "rule must be 17 or 25");
+    if (functor_id < 0 || functor_id >= F1_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown functor id");
+    if (n < 0 || !a || !b || !out4) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "bad argument");
+    if (F1_TABLE[functor_id].nparams > 0 && !params) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "params is NULL");
+    if (n == 0) return GKQ_OK;
+    GKQ_CUDA(h, cudaSetDevice(h->device));
+    Batch1D P;
+    memset(&P, 0, sizeof P);
+    P.n = n;
+    P.a = a;
+    P.b = b;
+    P.range_stride = range_stride;
+    P.params = params;
+    P.param_stride = param_stride;
+    const int grid = (int)((n + BLOCK - 1) / BLOCK);
+    if (rule == 17)
+        h->l1[functor_id].qk17(P, out4, grid, (cudaStream_t)stream);
+    else
+        h->l1[functor_id].qk25(P, out4, grid, (cudaStream_t)stream);
+    return launch_check(h, "k_qk_batch");
+}
+
+// Host-pointer entry: chunked, double-buffered H2D -> kernels -> D2H pipeline.
+int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
+                             const double* a, const double* b, int64_t range_stride,
+                             const double* params, int64_t param_stride,
+                             const int64_t* pts_offsets, const double* pts, double* out_estimate,
+                             double* out_delta, uint32_t* out_nevals, uint32_t* out_status) {
+    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
+    if (!cfg) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "cfg is NULL");
+    if (functor_id < 0 || functor_id >= F1_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown functor id");
+    if (n < 0) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "n out of range");
+    if (n == 0) return GKQ_OK;
+    if (!a || !b || !out_estimate || !out_delta || !out_nevals || !out_status)
+        return fail(h, GKQ_ERR_INVALID_ARGUMENT, "NULL array argument");
+    if (pts_offsets) return fail(h, GKQ_ERR_UNSUPPORTED, "per-integral points: use the device entry");
+    GKQ_CUDA(h, cudaSetDevice(h->device));
+    const int np = F1_TABLE[functor_id].nparams;
+    if (np > 0 && !params) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "params is NULL");
+    const int np_batch = param_stride ? np : 0;  // per-integral parameter rows
+
+    // device staging layout for one chunk of C integrals (two buffers, ping-pong):
+    //   a[C] b[C] (when per-integral) | params[np][C] | est[C] delta[C] nevals[C] status[C]
+    const int64_t C = n < (1 << 18) ? n : (1 << 18);
+    const size_t in_doubles = (size_t)((range_stride ? 2 : 0) + np_batch) * (size_t)C;
+    const size_t chunk_bytes = in_doubles * 8 + (size_t)C * (8 + 8 + 4 + 4) + 256;
+    const size_t fixed_bytes = 64 * 8;  // shared range / shared params
+    int rc;
+    {
+        size_t want = 2 * chunk_bytes + fixed_bytes;
+        if (want > h->stage_bytes) {
+            if (h->stage_dev) GKQ_CUDA(h, cudaFree(h->stage_dev));
+            h->stage_dev = nullptr;
+            h->stats.scratch_bytes -= h->stage_bytes;
+            GKQ_CUDA(h, cudaMalloc(&h->stage_dev, want));
+            h->stage_bytes = want;
+            h->stats.scratch_bytes += want;
+        }
+    }
+    // shared (stride-0) inputs live at the front of the staging area
+    double* d_fixed = (double*)h->stage_dev;
+    double fixed_host[64];
+    memset(fixed_host, 0, sizeof fixed_host);
+    if (!range_stride) {
+        fixed_host[0] = a[0];
+        fixed_host[1] = b[0];
+    }
+    if (!param_stride)
+        for (int k = 0; k < np; ++k) fixed_host[2 + k] = params[k];
+    GKQ_CUDA(h, cudaMemcpyAsync(d_fixed, fixed_host, sizeof fixed_host, cudaMemcpyHostToDevice, h->s_compute));
+    GKQ_CUDA(h, cudaStreamSynchronize(h->s_compute));  // fixed_host is a stack buffer
+
+    cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
+    for (int k = 0; k < 2; ++k) {
+        GKQ_CUDA(h, cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+        GKQ_CUDA(h, cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
+        GKQ_CUDA(h, cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
+    }
+    rc = GKQ_OK;
+    int64_t chunk_idx = 0;
+    for (int64_t off = 0; off < n && rc == GKQ_OK; off += C, ++chunk_idx) {
+        const int64_t m = (n - off) < C ? (n - off) : C;
+        const int buf = (int)(chunk_idx & 1);
+        char* base = h->stage_dev + fixed_bytes + (size_t)buf * chunk_bytes;
+        double* d_in = (double*)base;
+        double* d_a = range_stride ? d_in : d_fixed;
+        double* d_b = range_stride ? d_in + C : d_fixed + 1;
+        double* d_par = param_stride ? d_in + (range_stride ? 2 * C : 0) : d_fixed + 2;
+        double* d_est = (double*)(base + in_doubles * 8);
+        double* d_dlt = d_est + C;
+        uint32_t* d_nev = (uint32_t*)(d_dlt + C);
+        uint32_t* d_st = d_nev + C;
+
+        // the buffer is free once the D2H copies of chunk_idx-2 have completed
+        if (chunk_idx >= 2) GKQ_CUDA(h, cudaStreamWaitEvent(h->s_in, ev_out[buf], 0));
+        if (range_stride) {
+            GKQ_CUDA(h, cudaMemcpyAsync(d_a, a + off, (size_t)m * 8, cudaMemcpyHostToDevice, h->s_in));
+            GKQ_CUDA(h, cudaMemcpyAsync(d_b, b + off, (size_t)m * 8, cudaMemcpyHostToDevice, h->s_in));
+        }
+        for (int k = 0; k < np_batch; ++k)
+            GKQ_CUDA(h, cudaMemcpyAsync(d_par + (size_t)k * C, params + (size_t)k * param_stride + off,
+                                        (size_t)m * 8, cudaMemcpyHostToDevice, h->s_in));
+        GKQ_CUDA(h, cudaEventRecord(ev_in[buf], h->s_in));
+
+        GKQ_CUDA(h, cudaStreamWaitEvent(h->s_compute, ev_in[buf], 0));
+        rc = gkq_integrate_batch(h, cfg, functor_id, m, d_a, d_b, range_stride, d_par,
+                                 param_stride ? C : 0, nullptr, nullptr, d_est, d_dlt, d_nev, d_st,
+                                 h->s_compute);
+        if (rc) break;
+        GKQ_CUDA(h, cudaEventRecord(ev_done[buf], h->s_compute));
+
+        GKQ_CUDA(h, cudaStreamWaitEvent(h->s_out, ev_done[buf], 0));
+        GKQ_CUDA(h, cudaMemcpyAsync(out_estimate + off, d_est, (size_t)m * 8, cudaMemcpyDeviceToHost, h->s_out));
+        GKQ_CUDA(h, cudaMemcpyAsync(out_delta + off, d_dlt, (size_t)m * 8, cudaMemcpyDeviceToHost, h->s_out));
+        GKQ_CUDA(h, cudaMemcpyAsync(out_nevals + off, d_nev, (size_t)m * 4, cudaMemcpyDeviceToHost, h->s_out));
+        GKQ_CUDA(h, cudaMemcpyAsync(out_status + off, d_st, (size_t)m * 4, cudaMemcpyDeviceToHost, h->s_out));
+        GKQ_CUDA(h, cudaEventRecord(ev_out[buf], h->s_out));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(h->s_in);
+    cudaError_t e2 = cudaStreamSynchronize(h->s_compute);
+    cudaError_t e3 = cudaStreamSynchronize(h->s_out);
+    for (int k = 0; k < 2; ++k) {
+        cudaEventDestroy(ev_in[k]);
+        cudaEventDestroy(ev_done[k]);
+        cudaEventDestroy(ev_out[k]);
+    }
+    if (rc) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return fail(h, GKQ_ERR_CUDA, std::string("host pipeline failed: ") +
+                                         cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    gkq_sync(h, h->s_compute);
+    return GKQ_OK;
+}
+
+// ---- 2-D ----------------------------------------------------------------------------------------
+int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id, int yrange_id,
+                         int64_t n, const double* x0, const double* x1, int64_t range_stride,
+                         const double* fparams, int64_t fparam_stride, const double* yparams,
+                         int64_t yparam_stride, const int64_t* pts_offsets, const double* pts_xy,
+                         double* out_estimate, double* out_delta, uint32_t* out_nevals,
+                         uint32_t* out_status, void* stream) {
+    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
+    if (!cfg) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "cfg is NULL");
+    if (functor2_id < 0 || functor2_id >= F2_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown 2-D functor id");
+    if (yrange_id < 0 || yrange_id >= YR_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown y-range functor id");
+    if (n < 0 || n > 0xffffffffll) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "n out of range");
+    if (cfg->algo < 0 || cfg->algo > 2) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown algorithm");
+    if (range_stride != 0 && range_stride != 1) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "range_stride must be 0 or 1");
+    if (cfg->max_evals > 0x7fffffffull) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "max_evals must fit in 31 bits");
+    if (cfg->npoints < 0 || (cfg->npoints > 0 && !cfg->points)) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "points is NULL");
+    int rc;
+    if ((rc = check_tol(h, cfg->tol))) return rc;
+    for (int64_t k = 0; k < 2 * cfg->npoints; ++k)
+        if (cfg->points[k] != cfg->points[k])  // double/integrator.rs:60-66
+            return fail(h, GKQ_ERR_NAN_INPUT, "cannot include NAN value in singular points");
+    if (n == 0) return GKQ_OK;
+    if (!x0 || !x1 || !out_estimate || !out_delta || !out_nevals || !out_status)
+        return fail(h, GKQ_ERR_INVALID_ARGUMENT, "NULL array argument");
+    if (F2_TABLE[functor2_id].nparams > 0 && !fparams) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "fparams is NULL");
+    if (YR_TABLE[yrange_id].nparams > 0 && !yparams) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "yparams is NULL");
+    if (pts_offsets && !pts_xy) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "pts_xy is NULL");
+
+    GKQ_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = ensure_batch_scratch(h, (size_t)n))) return rc;
+
+    Batch2D P;
+    memset(&P, 0, sizeof P);
+    P.n = n;
+    P.x0 = x0;
+    P.x1 = x1;
+    P.range_stride = range_stride;
+    P.fparams = fparams;
+    P.fparam_stride = fparam_stride;
+    P.yparams = yparams;
+    P.yparam_stride = yparam_stride;
+    P.yrange_id = yrange_id;
+    P.nyparams = YR_TABLE[yrange_id].nparams;
+    P.tol.kind = cfg->tol.kind;
+    P.tol.abs_tol = cfg->tol.abs_tol;
+    P.tol.rel_tol = cfg->tol.rel_tol;
+    P.max_evals = cfg->max_evals;
+    P.out.estimate = out_estimate;
+    P.out.delta = out_delta;
+    P.out.nevals = out_nevals;
+    P.out.status = out_status;
+    P.ctl = h->ctl;
+    if (h->profiling) prof_clear(h);
+    GKQ_CUDA(h, cudaMemsetAsync(h->ctl, 0, sizeof(Control), st));
+    h->stats.batches += 1;
+    h->stats.integrals += (uint64_t)n;
+
+    // which algorithm(s) run, and over which integrals
+    bool run_s = false, run_p = false, split = false;
+    int npts_max = 0;
+    if (!pts_offsets) {
+        run_s = cfg->algo == GKQ_ALGO_QAGS || (cfg->algo == GKQ_ALGO_AUTO && cfg->npoints == 0);
+        run_p = !run_s;
+        if (run_p) {
+            npts_max = (int)cfg->npoints;
+            P.npts = npts_max;
+            if (npts_max > 0) {
+                if ((rc = upload_shared_points(h, cfg->points, (size_t)(2 * npts_max), st))) return rc;
+                P.pts_xy = h->dev_pts;
+            }
+        }
+    } else if (cfg->algo == GKQ_ALGO_QAGS) {
+        run_s = true;  // explicit QAGS2 never looks at points
+    } else {
+        const int grid = (int)((n + BLOCK - 1) / BLOCK);
+        const int mode = cfg->algo == GKQ_ALGO_AUTO ? 0 : 1;
+        k_split_auto<<<grid, BLOCK, 0, st>>>(n, (const long long*)pts_offsets, h->listS, h->listP, h->ctl, mode);
+        if ((rc = launch_check(h, "k_split_auto"))) return rc;
+        GKQ_CUDA(h, cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
+        GKQ_CUDA(h, cudaStreamSynchronize(st));
+        npts_max = (int)h->ctl_host->pad[0];
+        P.pts_offsets = (const long long*)pts_offsets;
+        P.pts_xy = pts_xy;
+        if (mode == 0) {
+            split = true;
+            run_s = h->ctl_host->countS > 0;
+            run_p = h->ctl_host->countP > 0;
+        } else {
+            run_p = true;
+        }
+    }
+    P.npts_max = npts_max;
+
+    for (int alg = 0; alg < 2; ++alg) {
+        if (alg == 0 ? !run_s : !run_p) continue;
+        Batch2D Q = P;
+        if (alg == 0) {  // QAGS2 ignores points entirely
+            Q.npts = 0;
+            Q.pts_offsets = nullptr;
+            Q.pts_xy = nullptr;
+            Q.npts_max = 0;
+        }
+        if (split) {
+            Q.worklist = alg == 0 ? h->listS : h->listP;
+            Q.worklist_count = alg == 0 ? &h->ctl->countS : &h->ctl->countP;
+        }
+        const Launch2D& L = h->l2[functor2_id];
+        if (h->occ_2d[functor2_id][alg] < 0) h->occ_2d[functor2_id][alg] = L.occupancy[alg]();
+        // list lengths: outer <= npts+1 + (max_evals/17)/50 + 1, inner <= npts+1 + max_evals/50 + 1
+        const unsigned long long outer_need = (unsigned long long)Q.npts_max + 2ull + (cfg->max_evals / 17ull) / 50ull;
+        const unsigned long long inner_need = (unsigned long long)Q.npts_max + 2ull + cfg->max_evals / 50ull;
+        if (inner_need > (1ull << 24)) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
+        const int cap_total = (int)(outer_need + inner_need);
+        const long long nblocks = (n + BLOCK - 1) / BLOCK;
+        int grid = persistent_grid(h, h->occ_2d[functor2_id][alg], cap_total, 2 * (Q.npts_max + 2) + 110);
+        if (grid < 1) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
+        if ((long long)grid > nblocks) grid = (int)nblocks;
+        SlabGeom g;
+        if ((rc = ensure_slab(h, (unsigned long long)grid * BLOCK, cap_total, 2 * (Q.npts_max + 2) + 110, g))) return rc;
+        Q.slab = g;
+        Q.cap_outer = (int)outer_need;
+        Q.cap_inner = (int)inner_need;
+        prof_begin(h, alg == 0 ? "k_nested<QAGS2>" : "k_nested<QAGP2>", st);
+        L.run[alg](Q, grid, st);
+        prof_end(h, st);
+        if ((rc = launch_check(h, alg == 0 ? "k_nested<QAGS2>" : "k_nested<QAGP2>"))) return rc;
+    }
+    return GKQ_OK;
+}
+
+int gkq_integrate2_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
+                              int yrange_id, int64_t n, const double* x0, const double* x1,
+                              int64_t range_stride, const double* fparams, int64_t fparam_stride,
+                              const double* yparams, int64_t yparam_stride,
+                              const int64_t* pts_offsets, const double* pts_xy,
+                              double* out_estimate, double* out_delta, uint32_t* out_nevals,
+                              uint32_t* out_status) {
+    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
+    if (n < 0) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "n out of range");
+    if (n == 0) return GKQ_OK;
+    if (functor2_id < 0 || functor2_id >= F2_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown 2-D functor id");
+    if (yrange_id < 0 || yrange_id >= YR_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown y-range functor id");
+    if (!x0 || !x1 || !out_estimate || !out_delta || !out_nevals || !out_status)
+        return fail(h, GKQ_ERR_INVALID_ARGUMENT, "NULL array argument");
+    if (pts_offsets && !pts_xy) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "pts_xy is NULL");
+    GKQ_CUDA(h, cudaSetDevice(h->device));
+    const int np = F2_TABLE[functor2_id].nparams, nq = YR_TABLE[yrange_id].nparams;
+    const size_t npairs = pts_offsets ? (size_t)pts_offsets[n] : 0;
+    if ((np > 0 && !fparams) || (nq > 0 && !yparams)) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "params is NULL");
+    // single-shot staging (2-D batches are compute-heavy: copies are negligible)
+    const size_t N = (size_t)n;
+    const size_t nx = range_stride ? N : 1, nfp = fparam_stride ? N : 1, nyp = yparam_stride ? N : 1;
+    const size_t in_d = 2 * nx + (size_t)np * nfp + (size_t)nq * nyp;
+    const size_t csr_d = pts_offsets ? (N + 1) + 2 * npairs : 0;  // offsets (as 8-byte) + pairs
+    const size_t bytes = (in_d + csr_d) * 8 + N * 24 + 256;
+    if (bytes > h->stage_bytes) {
+        if (h->stage_dev) GKQ_CUDA(h, cudaFree(h->stage_dev));
+        h->stage_dev = nullptr;
+        h->stats.scratch_bytes -= h->stage_bytes;
+        h->stage_bytes = 0;
+        GKQ_CUDA(h, cudaMalloc(&h->stage_dev, bytes));
+        h->stage_bytes = bytes;
+        h->stats.scratch_bytes += bytes;
+    }
+    cudaStream_t st = h->s_compute;
+    double* d = (double*)h->stage_dev;
+    double* d_x0 = d;
+    double* d_x1 = d + nx;
+    double* d_fp = d + 2 * nx;
+    double* d_yp = d_fp + (size_t)np * nfp;
+    long long* d_off = (long long*)(d + in_d);
+    double* d_pairs = (double*)(d_off + (pts_offsets ? N + 1 : 0));
+    double* d_est = d + in_d + csr_d;
+    double* d_dlt = d_est + N;
+    uint32_t* d_nev = (uint32_t*)(d_dlt + N);
+    uint32_t* d_st = d_nev + N;
+    if (pts_offsets) {
+        GKQ_CUDA(h, cudaMemcpyAsync(d_off, pts_offsets, (N + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (npairs) GKQ_CUDA(h, cudaMemcpyAsync(d_pairs, pts_xy, npairs * 16, cudaMemcpyHostToDevice, st));
+    }
+    GKQ_CUDA(h, cudaMemcpyAsync(d_x0, x0, nx * 8, cudaMemcpyHostToDevice, st));
+    GKQ_CUDA(h, cudaMemcpyAsync(d_x1, x1, nx * 8, cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < np; ++k)
+        GKQ_CUDA(h, cudaMemcpyAsync(d_fp + (size_t)k * nfp, fparams + (size_t)k * (fparam_stride ? fparam_stride : 1),
+                                    nfp * 8, cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < nq; ++k)
+        GKQ_CUDA(h, cudaMemcpyAsync(d_yp + (size_t)k * nyp, yparams + (size_t)k * (yparam_stride ? yparam_stride : 1),
+                                    nyp * 8, cudaMemcpyHostToDevice, st));
+    int rc = gkq_integrate2_batch(h, cfg, functor2_id, yrange_id, n, d_x0, d_x1, range_stride, d_fp,
+                                  fparam_stride ? (int64_t)N : 0, d_yp, yparam_stride ? (int64_t)N : 0,
+                                  pts_offsets ? (const int64_t*)d_off : nullptr,
+                                  pts_offsets ? d_pairs : nullptr, d_est, d_dlt, d_nev, d_st, st);
+    if (rc) return rc;
+    GKQ_CUDA(h, cudaMemcpyAsync(out_estimate, d_est, N * 8, cudaMemcpyDeviceToHost, st));
+    GKQ_CUDA(h, cudaMemcpyAsync(out_delta, d_dlt, N * 8, cudaMemcpyDeviceToHost, st));
+    GKQ_CUDA(h, cudaMemcpyAsync(out_nevals, d_nev, N * 4, cudaMemcpyDeviceToHost, st));
+    GKQ_CUDA(h, cudaMemcpyAsync(out_status, d_st, N * 4, cudaMemcpyDeviceToHost, st));
+    GKQ_CUDA(h, cudaStreamSynchronize(st));
+    return GKQ_OK;
+}
+
+}  // extern "C"

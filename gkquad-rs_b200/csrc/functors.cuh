@@ -1,0 +1,154 @@
+// functors.cuh -- the device integrand registry.
+//
+// The reference takes closures (trait Integrand, single/common.rs:129-145; Integrand2,
+// double/common.rs:35-45; DynamicY's range closure, double/range.rs:77-112).  Closures cannot
+// cross an FFI, so integrands are device functors compiled into the kernels as template
+// arguments (a function-pointer table would block inlining) and selected by ID through
+// gkq_functor_lookup / the `functor_id` argument of the batch calls.
+//
+// To add an integrand: add an id to the enum, a GKQ_F1 / GKQ_F2 body, a row in the table
+// (name, nparams, flops) and rebuild.  Bodies use plain C arithmetic; with -fmad=false the
+// polynomial/rational ones round exactly like the Rust closures they restate
+// (/root/reference/gkquad/benches/*.rs, tests/common/functions.rs).
+#pragma once
+#include "gk_common.cuh"
+
+namespace gkq {
+
+constexpr int MAX_PARAMS = 4;
+
+struct FunctorInfo {
+    const char* name;
+    int nparams;
+    // Algorithmic FP64 flops of one evaluation: counted from source
+    // for polynomial/rational bodies; for transcendental bodies the DADD+DMUL+2*DFMA SASS
+    // count of one evaluation (measured, see profiles/).
+    double flops;
+};
+
+// ---- 1-D ------------------------------------------------------------------------------
+enum F1Id : int {
+    F1_SQUARE = 0, F1_RECIP_P, F1_LORENTZ_P, F1_EXPCOS_P, F1_GAUSS_P, F1_ABSPOW_P, F1_LOGABS_P,
+    F1_F1, F1_F2, F1_F3, F1_F4, F1_F5, F1_F6, F1_EXP_P, F1_SQRT_SHIFT_P, F1_INV_ABS_SHIFT_P,
+    F1_COS_P, F1_COUNT
+};
+
+// HEAVY = body calls transcendental libdevice routines: the rule loop is then only partly
+// unrolled to keep the instruction footprint inside the instruction cache.
+template <int ID> struct F1;
+#define GKQ_F1(ID, HEAVY_, BODY)                                   \
+    template <> struct F1<ID> {                                    \
+        static constexpr bool HEAVY = HEAVY_;                      \
+        double p[MAX_PARAMS];                                      \
+        GKQ_DEV double operator()(double x) const { BODY }         \
+    };
+GKQ_F1(F1_SQUARE, false, return x * x;)                                   // benches/single.rs:11
+GKQ_F1(F1_RECIP_P, false, return p[0] / x;)                               // benches/single.rs:20
+GKQ_F1(F1_LORENTZ_P, false, return 1.0 / (1.0 + p[0] * (x * x));)         // benches/single.rs:32
+GKQ_F1(F1_EXPCOS_P, true, return exp(-p[0] * x) * cos(p[1] * x);)         // S1 / S3
+GKQ_F1(F1_GAUSS_P, true, return exp(-p[0] * (x * x));)                    // I2
+GKQ_F1(F1_ABSPOW_P, true, return pow(fabs(x - p[0]), -p[1]);)             // P1
+GKQ_F1(F1_LOGABS_P, true, return log(fabs(x - p[0]));)                    // P2
+GKQ_F1(F1_F1, true, return pow(x, 2.6) * log(1. / x);)                    // functions.rs:3-5
+GKQ_F1(F1_F2, true, return pow(x, -0.9) * log(1. / x);)                   // functions.rs:8-10
+GKQ_F1(F1_F3, true, return cos(2.4622888266898326 * sin(x));)             // functions.rs:13-15 (2^1.3)
+GKQ_F1(F1_F4, true, return log(1. / x);)                                  // functions.rs:17-19
+GKQ_F1(F1_F5, true, double x2 = x * x;
+       return x2 * x * log(fabs((x2 - 1.) * (x2 - 2.)));)                 // functions.rs:22-25
+GKQ_F1(F1_F6, false, double x2 = x * x; double x3 = x2 * x;
+       return 1.0 / (x3 - x2 + x - 1.);)                                  // functions.rs:27-31
+GKQ_F1(F1_EXP_P, true, return exp(p[0] * x);)
+GKQ_F1(F1_SQRT_SHIFT_P, false, return sqrt(x - p[0]);)
+GKQ_F1(F1_INV_ABS_SHIFT_P, false, return 1.0 / fabs(x - p[0]);)
+GKQ_F1(F1_COS_P, true, return cos(p[0] * x);)
+#undef GKQ_F1
+
+// ---- 2-D ------------------------------------------------------------------------------
+enum F2Id : int {
+    F2_XY = 0, F2_RECIP_XY_P, F2_RSQRT3, F2_G1, F2_G2, F2_G3, F2_G4, F2_GP1, F2_GP2, F2_GP3,
+    F2_D1_P, F2_COUNT
+};
+template <int ID> struct F2;
+#define GKQ_F2(ID, HEAVY_, BODY)                                          \
+    template <> struct F2<ID> {                                           \
+        static constexpr bool HEAVY = HEAVY_;                             \
+        double p[MAX_PARAMS];                                             \
+        GKQ_DEV double operator()(double x, double y) const { BODY }      \
+    };
+GKQ_F2(F2_XY, false, return x * y;)                                       // benches/double.rs:10
+GKQ_F2(F2_RECIP_XY_P, false, return p[0] / (x * y);)                      // benches/double.rs:19
+GKQ_F2(F2_RSQRT3, false, double denom = 1.0 + x * x + y * y;
+       return 1.0 / (denom * sqrt(denom));)                               // benches/double.rs:31-33
+GKQ_F2(F2_G1, false, return 1.0 - x * y;)                                 // functions.rs:37-39
+GKQ_F2(F2_G2, true, return exp(y / x);)                                   // functions.rs:41-43
+GKQ_F2(F2_G3, false, return sqrt(0.25 - x * x - y * y);)                  // functions.rs:45-47
+GKQ_F2(F2_G4, false, double a = 1.0 + x + y; return 1.0 / (a * (a * a));) // functions.rs:49-51 powi(3)
+GKQ_F2(F2_GP1, false, return 1.0 / sqrt(fabs(x) + fabs(y));)              // functions.rs:54-56
+GKQ_F2(F2_GP2, false, return x / (x * x + y * y);)                        // functions.rs:58-60
+GKQ_F2(F2_GP3, false, return 0.5 / sqrt(x * x + y * y);)                  // functions.rs:62-64
+GKQ_F2(F2_D1_P, false, return 1.0 / sqrt(fabs(x - p[0]) + fabs(y - p[1]));)  // D1
+#undef GKQ_F2
+
+// ---- y-range functors: run-time switch (evaluated once per inner integral) -------------
+enum YRId : int { YR_CONST = 0, YR_ZERO_TO_X = 1, YR_CIRCLE = 2, YR_COUNT = 3 };
+struct YRange {
+    int id;
+    double q[2];
+    GKQ_DEV void operator()(double x, double& y0, double& y1) const {
+        if (id == YR_CONST) {
+            y0 = q[0];
+            y1 = q[1];
+        } else if (id == YR_ZERO_TO_X) {
+            y0 = 0.0;
+            y1 = x;
+        } else {
+            double ymax = sqrt(q[0] - x * x);
+            y0 = -ymax;
+            y1 = ymax;
+        }
+    }
+};
+
+// Registry rows: X(id, name, nparams, flops_per_eval).  Single source of truth for the host
+// tables (engine.cu), the launch tables and the explicit instantiations (inst_*.cu).
+// flops: counted from source for polynomial/rational bodies (add, sub,
+// mul, div, sqrt = 1); for transcendental bodies the DADD+DMUL+2*DFMA SASS count of one
+// evaluation (see profiles/functor_flops_r01.md for how they were obtained).
+#define GKQ_F1_LIST(X)                       \
+    X(F1_SQUARE, "square", 0, 1.0)           \
+    X(F1_RECIP_P, "recip_p", 1, 1.0)         \
+    X(F1_LORENTZ_P, "lorentz_p", 1, 4.0)     \
+    X(F1_EXPCOS_P, "expcos_p", 2, 100.0)     \
+    X(F1_GAUSS_P, "gauss_p", 1, 45.0)        \
+    X(F1_ABSPOW_P, "abspow_p", 2, 150.0)     \
+    X(F1_LOGABS_P, "logabs_p", 1, 50.0)      \
+    X(F1_F1, "f1", 0, 200.0)                 \
+    X(F1_F2, "f2", 0, 200.0)                 \
+    X(F1_F3, "f3", 0, 110.0)                 \
+    X(F1_F4, "f4", 0, 51.0)                  \
+    X(F1_F5, "f5", 0, 57.0)                  \
+    X(F1_F6, "f6", 0, 6.0)                   \
+    X(F1_EXP_P, "exp_p", 1, 44.0)            \
+    X(F1_SQRT_SHIFT_P, "sqrt_shift_p", 1, 2.0)       \
+    X(F1_INV_ABS_SHIFT_P, "inv_abs_shift_p", 1, 2.0) \
+    X(F1_COS_P, "cos_p", 1, 55.0)
+
+#define GKQ_F2_LIST(X)                       \
+    X(F2_XY, "xy", 0, 1.0)                   \
+    X(F2_RECIP_XY_P, "recip_xy_p", 1, 2.0)   \
+    X(F2_RSQRT3, "rsqrt3", 0, 8.0)           \
+    X(F2_G1, "g1", 0, 2.0)                   \
+    X(F2_G2, "g2", 0, 45.0)                  \
+    X(F2_G3, "g3", 0, 5.0)                   \
+    X(F2_G4, "g4", 0, 5.0)                   \
+    X(F2_GP1, "gp1", 0, 3.0)                 \
+    X(F2_GP2, "gp2", 0, 4.0)                 \
+    X(F2_GP3, "gp3", 0, 5.0)                 \
+    X(F2_D1_P, "d1_p", 2, 5.0)
+
+#define GKQ_YR_LIST(X)                       \
+    X(YR_CONST, "const", 2, 0.0)             \
+    X(YR_ZERO_TO_X, "zero_to_x", 0, 0.0)     \
+    X(YR_CIRCLE, "circle", 1, 3.0)
+
+}  // namespace gkq

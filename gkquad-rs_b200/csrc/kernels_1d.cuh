@@ -1,0 +1,487 @@
+// kernels_1d.cuh -- the 1-D kernels (templates over the integrand functor).
+//
+//   k_qags_init<F,8>    qk17 on the whole range of every integral + the exit tests of
+//                       initial_integral (single/algorithm/qags.rs:315-376, pass i = 0);
+//                       survivors are compacted into two worklists by warp-aggregated
+//                       atomics: "needs qk25" and "straight to the bisection loop".
+//   k_qags_init<F,12>   qk25 on the first worklist (pass i = 1), survivors join the second.
+//   k_adaptive<F,false> persistent self-refilling lanes: QAGS main loop (qags.rs:98-311).
+//   k_adaptive<F,true>  the same machine with QAGP's break-point seeding (qagp.rs:68-372).
+//   k_qk_batch<F,N>     rule-level entry (single/qk/mod.rs:28-41).
+//
+// All kernels are thread-per-integral: 100 % lane utilisation in the
+// integrand samples, reference summation order for free, node tables broadcast from
+// constant memory.
+#pragma once
+#include "adaptive.cuh"
+#include "functors.cuh"
+
+namespace gkq {
+
+constexpr int BLOCK = 256;
+
+// Device-side control block of one batch call (zeroed by a memset node before the kernels).
+struct Control {
+    unsigned long long count25;    // entries in list25  (integrals that need the qk25 pass)
+    unsigned long long countLoop;  // entries in listLoop (integrals entering the main loop)
+    unsigned long long headLoop;   // queue head of the persistent QAGS kernel
+    unsigned long long headP;      // queue head of the persistent QAGP kernel
+    unsigned long long countP;     // QAGP worklist size when built on the device (AUTO split)
+    unsigned long long countS;     // QAGS worklist size when built on the device (AUTO split)
+    unsigned long long pad[2];
+};
+
+struct Batch1D {
+    long long n;
+    const double* a;
+    const double* b;
+    long long range_stride;
+    const double* params;
+    long long param_stride;
+    const long long* pts_offsets;  // per-integral CSR or nullptr
+    const double* pts;             // CSR values, or the shared points (device copy)
+    int npts_shared;
+    Tol tol;
+    unsigned long long max_evals;
+    unsigned long long ws_capacity;
+    Outputs out;
+    // scratch owned by the handle
+    Control* ctl;
+    double* abs0;               // [n] absvalue of the initial rule (qags.rs:315-376 returns it)
+    unsigned int* list25;       // [n]
+    unsigned int* listLoop;     // [n]
+    const unsigned int* worklist;        // optional subset of integrals (AUTO split) or nullptr
+    const unsigned long long* worklist_count;  // device count for `worklist`
+    SlabGeom slab;
+};
+
+template <class F>
+GKQ_DEV void load_functor(F& f, const Batch1D& P, long long i, int nparams) {
+#pragma unroll
+    for (int k = 0; k < MAX_PARAMS; ++k)
+        f.p[k] = (k < nparams) ? (P.param_stride ? P.params[(long long)k * P.param_stride + i]
+                                                 : P.params[k])
+                               : 0.0;
+}
+
+// Range of integral i, mapped to [-1, 1] coordinates when either end is infinite
+// (qags.rs:48-57, util.rs:162-176).
+GKQ_DEV void load_range(const Batch1D& P, long long i, double& a, double& b, bool& transform) {
+    a = P.a[i * P.range_stride];
+    b = P.b[i * P.range_stride];
+    transform = !is_finite(a) || !is_finite(b);
+    if (transform) {
+        a = transform_point(a);
+        b = transform_point(b);
+    }
+}
+
+// Warp-aggregated append of `i` to a worklist: one atomic per warp per list.
+// Must be reached by all 32 lanes of the warp (callers keep whole warps in their loops).
+GKQ_DEV void list_append(bool pred, unsigned int i, unsigned int* list, unsigned long long* count) {
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (!pred) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    list[base + __popc(mask & ((1u << lane) - 1u))] = i;
+}
+
+template <class F, int N>
+struct RuleUnroll {
+    // heavy (transcendental) bodies: one node pair per loop trip; light bodies: fully unrolled
+    static constexpr int value = F::HEAVY ? 1 : N;
+};
+
+// ---- QAGS initial passes -------------------------------------------------------------------
+// PASS 0: N = 8 (qk17) over the whole batch (or `worklist`); PASS 1: N = 12 (qk25) over list25.
+template <class F, int N, int NPARAMS>
+__global__ void __launch_bounds__(BLOCK) k_qags_init(const Batch1D P) {
+    constexpr int PASS = (N == 8) ? 0 : 1;
+    long long total;
+    if (PASS == 0)
+        total = P.worklist ? (long long)*P.worklist_count : P.n;
+    else
+        total = (long long)P.ctl->count25;
+
+    for (long long k = (long long)blockIdx.x * BLOCK + threadIdx.x;
+         k - threadIdx.x % 32 < total;  // keep whole warps in the loop for the ballots below
+         k += (long long)gridDim.x * BLOCK) {
+        const bool valid = k < total;
+        long long i = 0;
+        bool to25 = false, toLoop = false;
+        if (valid) {
+            i = (PASS == 0) ? (P.worklist ? (long long)P.worklist[k] : k) : (long long)P.list25[k];
+            Wrapped<F> g;
+            double a, b;
+            load_range(P, i, a, b, g.transform);
+            load_functor(g.f, P, i, NPARAMS);
+
+            const QK q = qk_rule<N, RuleUnroll<F, N>::value>(g, a, b);
+            const uint32_t nevals = (PASS == 0) ? 17u : 42u;
+
+            // initial_integral, pass i = PASS (qags.rs:336-372)
+            uint32_t status = ST_NONE;
+            bool done = true;
+            const double tolerance = P.tol.to_abs(fabs(q.estimate));
+            const double round_off = 100. * F64_EPSILON * q.absvalue;
+            if (q.estimate != q.estimate) {
+                status = ST_NAN;
+            } else if ((q.delta <= tolerance && q.delta != q.asc) || q.delta == 0.0) {
+                status = ST_NONE;
+            } else if (q.delta <= round_off && q.delta > tolerance) {
+                status = ST_ROUNDOFF_ERROR;
+            } else if (P.max_evals < (unsigned long long)(42 + PASS * 25)) {
+                status = ST_INSUFFICIENT_ITERATION;
+            } else {
+                done = false;
+                if (PASS == 0 && !(q.delta > tolerance * 1024.))
+                    to25 = true;  // second pass with qk25
+                else
+                    toLoop = true;  // qags.rs:370-372 (`break`) or end of the 2-pass loop
+            }
+            // finished integrals get their final answer; loop entrants park result0 in the
+            // output arrays (estimate, delta, nevals) + abs0 until k_adaptive picks them up
+            if (done || toLoop) {
+                write_result(P.out, i, q.estimate, q.delta, nevals, status);
+                if (toLoop) P.abs0[i] = q.absvalue;
+            }
+        }
+        if (PASS == 0) list_append(to25, (unsigned int)i, P.list25, &P.ctl->count25);
+        list_append(toLoop, (unsigned int)i, P.listLoop, &P.ctl->countLoop);
+    }
+}
+
+// ---- QAGP break points (qagp.rs:375-400) ------------------------------------------------------
+// Builds [begin, sorted user points inside [min,max]..., end] into the lane's PTS slots and
+// returns nint = len - 1.  The insertion sort is util.rs:178-211 with a strict comparator in
+// range direction.
+GKQ_DEV int make_sorted_points(const Slab& S, double begin, double end, const double* pts, int npts,
+                               bool transform) {
+    const bool ascending = begin < end;
+    const double mn = ascending ? begin : end;
+    const double mx = ascending ? end : begin;
+    // pts2[0] = begin, pts2[1..] = user points (transformed when the range is infinite)
+    S.PTS(0) = begin;
+    for (int k = 0; k < npts; ++k) {
+        double v = pts[k];
+        S.PTS(1 + k) = transform ? transform_point(v) : v;
+    }
+    // insert_sort(&mut pts2[1..])
+    for (int sp = 2; sp <= npts; ++sp) {
+        const double target = S.PTS(sp);
+        const double prev = S.PTS(sp - 1);
+        if (ascending ? (prev < target) : (prev > target)) continue;
+        int insert_pos = 1;
+        for (int ip = sp - 2; ip >= 1; --ip) {
+            const double another = S.PTS(ip);
+            if (ascending ? (another < target) : (another > target)) {
+                insert_pos = ip + 1;
+                break;
+            }
+        }
+        for (int k = sp; k > insert_pos; --k) S.PTS(k) = S.PTS(k - 1);
+        S.PTS(insert_pos) = target;
+    }
+    // retain(min <= x <= max) then push(end)
+    int len = 0;
+    for (int k = 0; k <= npts; ++k) {
+        const double x = S.PTS(k);
+        if (mn <= x && x <= mx) {
+            S.PTS(len) = x;
+            len += 1;
+        }
+    }
+    S.PTS(len) = end;
+    return len;  // = pts.len() - 1 = nint
+}
+
+// ---- persistent adaptive kernel ------------------------------------------------------------------
+template <class F, bool QAGP, int NPARAMS>
+__global__ void __launch_bounds__(BLOCK) k_adaptive(const Batch1D P) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long t = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x;
+
+    Slab S;
+    S.d = P.slab.dbase + t;
+    S.w = P.slab.wbase + t;
+    S.stride = P.slab.stride;
+    S.cap = P.slab.cap;
+
+    unsigned long long total;
+    if (QAGP)
+        total = P.worklist ? *P.worklist_count : (unsigned long long)P.n;
+    else
+        total = P.ctl->countLoop;
+    unsigned long long* head = QAGP ? &P.ctl->headP : &P.ctl->headLoop;
+
+    Lane s;
+    s.active = false;
+    s.idx = 0;
+    GlobalSink sink;
+    sink.O = P.out;
+    Wrapped<F> g;
+    g.transform = false;
+    bool exhausted = false;
+
+    for (;;) {
+        // ---- refill idle lanes from the global queue (one atomic per warp per trip) ----
+        const unsigned want = __ballot_sync(FULL, !s.active && !exhausted);
+        if (want) {
+            const int leader = __ffs(want) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(head, (unsigned long long)__popc(want));
+            base = __shfl_sync(FULL, base, leader);
+            if (!s.active && !exhausted) {
+                const unsigned long long my = base + __popc(want & ((1u << lane) - 1u));
+                if (my >= total) {
+                    exhausted = true;
+                } else {
+                    lane_reset_common(s);
+                    double a, b;
+                    if (!QAGP) {
+                        // result0 of the initial passes was parked in the outputs (k_qags_init)
+                        s.idx = (long long)P.listLoop[my];
+                        load_range(P, s.idx, a, b, s.transform);
+                        load_functor(g.f, P, s.idx, NPARAMS);
+                        g.transform = s.transform;
+                        s.est0 = P.out.estimate[s.idx];
+                        s.delta0 = P.out.delta[s.idx];
+                        s.abs0 = P.abs0[s.idx];
+                        s.nevals = P.out.nevals[s.idx];
+                        // ws.reserve((max_evals - nevals) / 50 + 1)   qags.rs:98-99
+                        s.max_iters = (P.max_evals - s.nevals) / 50;
+                        s.limit = (int)reserve_cap(P.ws_capacity, s.max_iters + 1);
+                        ws_push(S, s, a, b, s.est0, s.delta0, 0);
+                        tab_append(S, s, s.est0);
+                        s.area = s.est0;
+                        s.errsum = s.delta0;
+                        s.res_ext = s.est0;
+                        s.err_ext = F64_MAX;
+                        s.ertest = 0.;
+                        s.eolr = 0.;
+                        s.iteration = 1;
+                        s.active = true;
+                        if (s.iteration > s.max_iters) adaptive_epilogue(S, s, sink);
+                    } else {
+                        s.idx = P.worklist ? (long long)P.worklist[my] : (long long)my;
+                        load_range(P, s.idx, a, b, s.transform);
+                        load_functor(g.f, P, s.idx, NPARAMS);
+                        g.transform = s.transform;
+                        const double* up;
+                        int nup;
+                        if (P.pts_offsets) {
+                            const long long o0 = P.pts_offsets[s.idx];
+                            up = P.pts + o0;
+                            nup = (int)(P.pts_offsets[s.idx + 1] - o0);
+                        } else {
+                            up = P.pts;
+                            nup = P.npts_shared;
+                        }
+                        s.nint = make_sorted_points(S, a, b, up, nup, s.transform);
+                        s.nevals = 0;
+                        s.est0 = s.delta0 = s.abs0 = s.asc0 = 0.;
+                        if (P.max_evals < (unsigned long long)s.nint * 25ull) {  // qagp.rs:79-81
+                            write_result(P.out, s.idx, 0.0, F64_MAX, 0u, ST_INSUFFICIENT_ITERATION);
+                        } else {
+                            // ws.reserve(nint + (max_evals - nint*25)/50)   qagp.rs:83-84
+                            s.limit = (int)reserve_cap(
+                                P.ws_capacity, s.nint + (P.max_evals - (unsigned long long)s.nint * 25ull) / 50ull);
+                            s.seeding = true;
+                            s.seed_k = 0;
+                            s.active = true;
+                        }
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(FULL, s.active) == 0u) break;
+
+        // ---- plan this trip: up to two ranges to run the 25-point rule on ----
+        double ra0 = 0., rb0 = 0., ra1 = 0., rb1 = 0.;
+        bool has0 = false, has1 = false;
+        double ia = 0., ib = 0., ie = 0., id = 0., center = 0.;
+        int ilv = 0;
+        if (s.active) {
+            if (QAGP && s.seeding) {
+                // next two break-point windows wide enough to integrate (qagp.rs:102-106)
+                s.w0 = s.w1 = -1;
+                int k = s.seed_k;
+                for (; k < s.nint && s.w1 < 0; ++k) {
+                    const double lo = S.PTS(k), hi = S.PTS(k + 1);
+                    if (fabs(hi - lo) < 100. * F64_MIN_POSITIVE) continue;
+                    if (s.w0 < 0) {
+                        s.w0 = k; ra0 = lo; rb0 = hi; has0 = true;
+                    } else {
+                        s.w1 = k; ra1 = lo; rb1 = hi; has1 = true;
+                    }
+                }
+                s.seed_k = k;
+            } else {
+                // bisect the interval with the largest error (qags.rs:122-125, util.rs:151-159)
+                const int wi = s.wi;
+                ia = S.A(wi); ib = S.B(wi); ie = S.E(wi); id = S.D(wi); ilv = S.LV(wi);
+                center = (ia + ib) * 0.5;
+                ra0 = ia; rb0 = center; ra1 = center; rb1 = ib;
+                has0 = has1 = true;
+            }
+        }
+
+        // ---- the hot part: 2 x 25 integrand samples per active lane, warp-converged ----
+        QK q0, q1;
+        q0.estimate = q0.delta = q0.absvalue = q0.asc = 0.;
+        q1 = q0;
+        __syncwarp();
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+            const bool on = hh ? has1 : has0;
+            if (on) {
+                const QK q = qk_rule<12, RuleUnroll<F, 12>::value>(g, hh ? ra1 : ra0, hh ? rb1 : rb0);
+                if (hh) q1 = q; else q0 = q;
+            }
+        }
+
+        // ---- bookkeeping (per lane, divergent, short) ----
+        if (s.active) {
+            if (QAGP && s.seeding) {
+                bool dead = false;
+#pragma unroll 1
+                for (int hh = 0; hh < 2 && !dead; ++hh) {
+                    const int w = hh ? s.w1 : s.w0;
+                    if (w < 0) continue;
+                    const QK q = hh ? q1 : q0;
+                    s.nevals += 25;
+                    if (q.estimate != q.estimate) {  // qagp.rs:112-119
+                        s.active = false;
+                        write_result(P.out, s.idx, s.est0, s.delta0, s.nevals, ST_NAN);
+                        dead = true;
+                        break;
+                    }
+                    const int lv = (q.delta == q.asc && q.delta != 0.0) ? 1 : 0;
+                    s.est0 += q.estimate;  // add_qkresult, qagp.rs:403-408
+                    s.delta0 += q.delta;
+                    s.abs0 += q.absvalue;
+                    s.asc0 += q.asc;
+                    ws_push(S, s, hh ? ra1 : ra0, hh ? rb1 : rb0, q.estimate, q.delta, lv);
+                }
+                if (!dead && s.seed_k >= s.nint) {
+                    // all windows seeded: qagp.rs:132-179
+                    s.seeding = false;
+                    double deltasum = 0.;
+                    for (int k = 0; k < s.size; ++k) {
+                        if (S.LV(k) > 0) S.D(k) = s.delta0;
+                        deltasum += S.D(k);
+                    }
+                    for (int k = 0; k < s.size; ++k) S.LV(k) = 0;
+                    ws_sort_results(S, s);
+
+                    const double tolerance = P.tol.to_abs(fabs(s.est0));
+                    const double round_off = 100. * F64_EPSILON * s.abs0;
+                    if (s.delta0 <= round_off && s.delta0 > tolerance) {
+                        s.active = false;
+                        write_result(P.out, s.idx, s.est0, s.delta0, s.nevals, ST_ROUNDOFF_ERROR);
+                    } else if ((s.delta0 <= tolerance && s.delta0 != s.asc0) || s.delta0 == 0.0) {
+                        s.active = false;
+                        write_result(P.out, s.idx, s.est0, s.delta0, s.nevals, ST_NONE);
+                    } else if ((unsigned long long)s.nevals == P.max_evals) {
+                        s.active = false;
+                        write_result(P.out, s.idx, s.est0, s.delta0, s.nevals,
+                                     ST_INSUFFICIENT_ITERATION);
+                    } else {
+                        tab_append(S, s, s.est0);
+                        s.area = s.est0;
+                        s.res_ext = s.est0;
+                        s.err_ext = F64_MAX;
+                        s.errsum = deltasum;
+                        s.eolr = deltasum;
+                        s.ertest = tolerance;
+                        s.max_iters = (unsigned long long)s.nint + (P.max_evals - s.nevals) / 50ull;
+                        s.iteration = (unsigned long long)s.nint;
+                    }
+                }
+            } else {
+                adaptive_step<QAGP>(S, s, P.tol, P.max_evals, sink, ia, ib, center, ie, id, ilv,
+                                    q0, q1);
+            }
+        }
+    }
+}
+
+// ---- rule-level batch (single/qk/mod.rs:28-41) --------------------------------------------------
+template <class F, int N, int NPARAMS>
+__global__ void __launch_bounds__(BLOCK) k_qk_batch(const Batch1D P, double* out4) {
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= P.n) return;
+    Wrapped<F> g;
+    g.transform = false;  // the public rules take finite ranges only (naive.rs:53)
+    load_functor(g.f, P, i, NPARAMS);
+    const double a = P.a[i * P.range_stride], b = P.b[i * P.range_stride];
+    const QK q = qk_rule<N, RuleUnroll<F, N>::value>(g, a, b);
+    out4[i] = q.estimate;
+    out4[P.n + i] = q.delta;
+    out4[2 * P.n + i] = q.absvalue;
+    out4[3 * P.n + i] = q.asc;
+}
+
+// ---- launch table (one entry per registered functor; defined by GKQ_INSTANTIATE_F1) ----------
+struct Launch1D {
+    void (*qags_init17)(const Batch1D&, int grid, cudaStream_t);
+    void (*qags_init25)(const Batch1D&, int grid, cudaStream_t);
+    void (*qags_loop)(const Batch1D&, int grid, cudaStream_t);
+    void (*qagp)(const Batch1D&, int grid, cudaStream_t);
+    void (*qk17)(const Batch1D&, double* out4, int grid, cudaStream_t);
+    void (*qk25)(const Batch1D&, double* out4, int grid, cudaStream_t);
+    int (*occupancy_loop)();   // resident blocks per SM of the persistent kernels
+    int (*occupancy_qagp)();
+    int (*occupancy_init25)();
+};
+
+template <int ID>
+Launch1D make_launch1d();
+#define GKQ_DECL_F1(ID, NAME, NP, FL) template <> Launch1D make_launch1d<ID>();
+GKQ_F1_LIST(GKQ_DECL_F1)
+#undef GKQ_DECL_F1
+
+#define GKQ_INSTANTIATE_F1(ID, NAME, NP, FL)                                                                   \
+    template <> Launch1D make_launch1d<ID>() {                                                       \
+        Launch1D L;                                                                                  \
+        L.qags_init17 = [](const Batch1D& P, int grid, cudaStream_t st) {                            \
+            k_qags_init<F1<ID>, 8, NP><<<grid, BLOCK, 0, st>>>(P);                                   \
+        };                                                                                           \
+        L.qags_init25 = [](const Batch1D& P, int grid, cudaStream_t st) {                            \
+            k_qags_init<F1<ID>, 12, NP><<<grid, BLOCK, 0, st>>>(P);                                  \
+        };                                                                                           \
+        L.qags_loop = [](const Batch1D& P, int grid, cudaStream_t st) {                              \
+            k_adaptive<F1<ID>, false, NP><<<grid, BLOCK, 0, st>>>(P);                                \
+        };                                                                                           \
+        L.qagp = [](const Batch1D& P, int grid, cudaStream_t st) {                                   \
+            k_adaptive<F1<ID>, true, NP><<<grid, BLOCK, 0, st>>>(P);                                 \
+        };                                                                                           \
+        L.qk17 = [](const Batch1D& P, double* o, int grid, cudaStream_t st) {                        \
+            k_qk_batch<F1<ID>, 8, NP><<<grid, BLOCK, 0, st>>>(P, o);                                 \
+        };                                                                                           \
+        L.qk25 = [](const Batch1D& P, double* o, int grid, cudaStream_t st) {                        \
+            k_qk_batch<F1<ID>, 12, NP><<<grid, BLOCK, 0, st>>>(P, o);                                \
+        };                                                                                           \
+        L.occupancy_loop = []() {                                                                    \
+            int nb = 0;                                                                              \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_adaptive<F1<ID>, false, NP>, BLOCK, 0); \
+            return nb;                                                                               \
+        };                                                                                           \
+        L.occupancy_qagp = []() {                                                                    \
+            int nb = 0;                                                                              \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_adaptive<F1<ID>, true, NP>, BLOCK, 0); \
+            return nb;                                                                               \
+        };                                                                                           \
+        L.occupancy_init25 = []() {                                                                  \
+            int nb = 0;                                                                              \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_qags_init<F1<ID>, 12, NP>, BLOCK, 0); \
+            return nb;                                                                               \
+        };                                                                                           \
+        return L;                                                                                    \
+    }
+
+}  // namespace gkq

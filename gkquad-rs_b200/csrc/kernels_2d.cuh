@@ -1,0 +1,512 @@
+// kernels_2d.cuh -- the nested double-integral drivers QAGS2 / QAGP2.
+//
+// Reference: double/algorithm/qags.rs:46-97 and double/algorithm/qagp.rs:70-139 -- an outer
+// 1-D algorithm over x whose integrand runs an inner 1-D algorithm over y(x), with
+//   * one running evaluation budget: before EACH inner call max_evals = total - nevals so far
+//     (0 once an inner call has failed), in the outer rule's evaluation order
+//     (single/qk/naive.rs:60-68: lower nodes j = 0..n-1, upper nodes, centre);
+//   * an inner workspace that is re-used, so its Vec capacity (= `limit`) is the running max
+//     of the reserve requests (qags.rs:60-61);
+//   * an inner failure injected as NaN into the outer integrand and the FIRST inner error
+//     overriding the outer status (qags.rs:75-80, 90-93); nevals = sum of inner evaluations.
+//
+// Mapping: one thread owns one outer integral and runs the whole nest sequentially out of
+// two slab regions (outer list + inner list); threads pull outer integrals from a global
+// queue until it is empty.  Inner rule evaluations (the hot part) are ordinary pure functor
+// samples; the outer rule uses the ORDERED variant because its "integrand" has state.
+#pragma once
+#include "adaptive.cuh"
+#include "functors.cuh"
+#include "kernels_1d.cuh"
+
+namespace gkq {
+
+struct Res {
+    double est, dlt;
+    uint32_t nev, st;
+};
+
+// qk rule in the reference's evaluation order, for integrands with side effects.
+template <int N, class G>
+__device__ __noinline__ QK qk_rule_ordered(G& g, double a, double b) {
+    using R = Rule<N>;
+    double fv1[N], fv2[N];
+    const double center = 0.5 * (a + b);
+    const double half_length = 0.5 * (b - a);
+    const double abs_half_length = fabs(half_length);
+#pragma unroll 1
+    for (int j = 0; j < N; ++j) fv1[j] = g(center - half_length * R::xgk(j));
+#pragma unroll 1
+    for (int j = 0; j < N; ++j) fv2[j] = g(center + half_length * R::xgk(j));
+    const double f_center = g(center);
+
+    double result_gauss = 0.;
+    double result_kronrod = f_center * R::WCK;
+    double result_abs = fabs(result_kronrod);
+#pragma unroll 1
+    for (int j = 0; j < N; ++j) {
+        double fsum = fv1[j] + fv2[j];
+        result_kronrod += R::wgk(j) * fsum;
+        result_abs += R::wgk(j) * (fabs(fv1[j]) + fabs(fv2[j]));
+        if ((j & 1) == 0) result_gauss += R::wg(j >> 1) * fsum;
+    }
+    const double mean = result_kronrod * 0.5;
+    double result_asc = R::WCK * fabs(f_center - mean);
+#pragma unroll 1
+    for (int j = 0; j < N; ++j)
+        result_asc += R::wgk(j) * (fabs(fv1[j] - mean) + fabs(fv2[j] - mean));
+    double err = (result_kronrod - result_gauss) * half_length;
+    result_kronrod *= half_length;
+    result_abs *= abs_half_length;
+    result_asc *= abs_half_length;
+    QK q;
+    q.estimate = result_kronrod;
+    q.delta = rescale_error(err, result_abs, result_asc);
+    q.absvalue = result_abs;
+    q.asc = result_asc;
+    return q;
+}
+
+template <bool ORDERED, int N, int U, class G>
+GKQ_DEV QK rule_any(G& g, double a, double b) {
+    if constexpr (ORDERED)
+        return qk_rule_ordered<N>(g, a, b);
+    else
+        return qk_rule<N, U>(g, a, b);
+}
+
+// Sequential QAGS for one thread: single/algorithm/qags.rs:67-311 on an already
+// transformed range.  `ws_cap` is the workspace capacity before the call and is updated
+// like Vec::reserve would (persistent inner workspace).
+template <bool ORDERED, int U, class G>
+__device__ __noinline__ Res seq_qags(G& g, double a, double b, const Tol& tol,
+                                     unsigned long long max_evals, unsigned long long& ws_cap,
+                                     const Slab& S) {
+    Res r;
+    r.est = 0.;
+    r.dlt = F64_MAX;
+    r.nev = 0;
+    r.st = ST_INSUFFICIENT_ITERATION;
+    if (max_evals < 17) return r;  // qags.rs:86-88
+
+    // initial_integral (qags.rs:315-376)
+    QK q;
+    uint32_t nevals = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 0) {
+            nevals += 17;
+            q = rule_any<ORDERED, 8, U>(g, a, b);
+        } else {
+            nevals += 25;
+            q = rule_any<ORDERED, 12, U>(g, a, b);
+        }
+        r.est = q.estimate;
+        r.dlt = q.delta;
+        r.nev = nevals;
+        if (q.estimate != q.estimate) {
+            r.st = ST_NAN;
+            return r;
+        }
+        const double tolerance = tol.to_abs(fabs(q.estimate));
+        if ((q.delta <= tolerance && q.delta != q.asc) || q.delta == 0.0) {
+            r.st = ST_NONE;
+            return r;
+        }
+        const double round_off = 100. * F64_EPSILON * q.absvalue;
+        if (q.delta <= round_off && q.delta > tolerance) {
+            r.st = ST_ROUNDOFF_ERROR;
+            return r;
+        }
+        if (max_evals < (unsigned long long)(42 + pass * 25)) {
+            r.st = ST_INSUFFICIENT_ITERATION;
+            return r;
+        }
+        if (pass == 0 && q.delta > tolerance * 1024.) break;
+    }
+
+    Lane s;
+    lane_reset_common(s);
+    s.idx = 0;
+    s.transform = false;
+    s.est0 = q.estimate;
+    s.delta0 = q.delta;
+    s.abs0 = q.absvalue;
+    s.asc0 = 0.;
+    s.nevals = nevals;
+    s.max_iters = (max_evals - nevals) / 50;
+    ws_cap = reserve_cap(ws_cap, s.max_iters + 1);  // ws.clear(); ws.reserve(..)  qags.rs:98-99
+    s.limit = (int)ws_cap;
+    ws_push(S, s, a, b, s.est0, s.delta0, 0);
+    tab_append(S, s, s.est0);
+    s.area = s.est0;
+    s.errsum = s.delta0;
+    s.res_ext = s.est0;
+    s.err_ext = F64_MAX;
+    s.ertest = 0.;
+    s.eolr = 0.;
+    s.iteration = 1;
+    s.active = true;
+    LocalSink sink;
+    sink.est = 0.;
+    sink.dlt = 0.;
+    sink.nev = 0;
+    sink.st = 0;
+    if (s.iteration > s.max_iters) adaptive_epilogue(S, s, sink);
+    while (s.active) {
+        const int wi = s.wi;
+        const double ia = S.A(wi), ib = S.B(wi), ie = S.E(wi), id = S.D(wi);
+        const int ilv = S.LV(wi);
+        const double center = (ia + ib) * 0.5;
+        const QK q1 = rule_any<ORDERED, 12, U>(g, ia, center);
+        const QK q2 = rule_any<ORDERED, 12, U>(g, center, ib);
+        adaptive_step<false>(S, s, tol, max_evals, sink, ia, ib, center, ie, id, ilv, q1, q2);
+    }
+    r.est = sink.est;
+    r.dlt = sink.dlt;
+    r.nev = sink.nev;
+    r.st = sink.st;
+    return r;
+}
+
+// Sequential QAGP for one thread: single/algorithm/qagp.rs:68-372.  `pts` are the user
+// break points (read through `PT(k)`), the range is already transformed.
+template <bool ORDERED, int U, class G, class PointAt>
+__device__ __noinline__ Res seq_qagp(G& g, double a, double b, bool transform, PointAt user_pt,
+                                     int npts, const Tol& tol, unsigned long long max_evals,
+                                     unsigned long long& ws_cap, const Slab& S) {
+    Res r;
+    // make_sorted_points (qagp.rs:375-400) into the slab's PTS slots
+    const bool ascending = a < b;
+    const double mn = ascending ? a : b, mx = ascending ? b : a;
+    S.PTS(0) = a;
+    for (int k = 0; k < npts; ++k) {
+        const double v = user_pt(k);
+        S.PTS(1 + k) = transform ? transform_point(v) : v;
+    }
+    for (int sp = 2; sp <= npts; ++sp) {
+        const double target = S.PTS(sp);
+        const double prev = S.PTS(sp - 1);
+        if (ascending ? (prev < target) : (prev > target)) continue;
+        int insert_pos = 1;
+        for (int ip = sp - 2; ip >= 1; --ip) {
+            const double another = S.PTS(ip);
+            if (ascending ? (another < target) : (another > target)) {
+                insert_pos = ip + 1;
+                break;
+            }
+        }
+        for (int k = sp; k > insert_pos; --k) S.PTS(k) = S.PTS(k - 1);
+        S.PTS(insert_pos) = target;
+    }
+    int len = 0;
+    for (int k = 0; k <= npts; ++k) {
+        const double x = S.PTS(k);
+        if (mn <= x && x <= mx) {
+            S.PTS(len) = x;
+            len += 1;
+        }
+    }
+    S.PTS(len) = b;
+    const int nint = len;
+
+    if (max_evals < (unsigned long long)nint * 25ull) {  // qagp.rs:79-81
+        r.est = 0.;
+        r.dlt = F64_MAX;
+        r.nev = 0;
+        r.st = ST_INSUFFICIENT_ITERATION;
+        return r;
+    }
+
+    Lane s;
+    lane_reset_common(s);
+    s.idx = 0;
+    s.transform = transform;
+    ws_cap = reserve_cap(ws_cap, nint + (max_evals - (unsigned long long)nint * 25ull) / 50ull);
+    s.limit = (int)ws_cap;
+    s.nint = nint;
+    s.nevals = 0;
+    s.est0 = s.delta0 = s.abs0 = s.asc0 = 0.;
+
+    // first pass over the break-point windows (qagp.rs:102-130)
+#pragma unroll 1
+    for (int w = 0; w < nint; ++w) {
+        const double lo = S.PTS(w), hi = S.PTS(w + 1);
+        if (fabs(hi - lo) < 100. * F64_MIN_POSITIVE) continue;
+        const QK q = rule_any<ORDERED, 12, U>(g, lo, hi);
+        s.nevals += 25;
+        if (q.estimate != q.estimate) {
+            r.est = s.est0;
+            r.dlt = s.delta0;
+            r.nev = s.nevals;
+            r.st = ST_NAN;
+            return r;
+        }
+        const int lv = (q.delta == q.asc && q.delta != 0.0) ? 1 : 0;
+        s.est0 += q.estimate;
+        s.delta0 += q.delta;
+        s.abs0 += q.absvalue;
+        s.asc0 += q.asc;
+        ws_push(S, s, lo, hi, q.estimate, q.delta, lv);
+    }
+    double deltasum = 0.;
+    for (int k = 0; k < s.size; ++k) {
+        if (S.LV(k) > 0) S.D(k) = s.delta0;
+        deltasum += S.D(k);
+    }
+    for (int k = 0; k < s.size; ++k) S.LV(k) = 0;
+    ws_sort_results(S, s);
+
+    const double tolerance = tol.to_abs(fabs(s.est0));
+    const double round_off = 100. * F64_EPSILON * s.abs0;
+    r.est = s.est0;
+    r.dlt = s.delta0;
+    r.nev = s.nevals;
+    if (s.delta0 <= round_off && s.delta0 > tolerance) {
+        r.st = ST_ROUNDOFF_ERROR;
+        return r;
+    } else if ((s.delta0 <= tolerance && s.delta0 != s.asc0) || s.delta0 == 0.0) {
+        r.st = ST_NONE;
+        return r;
+    } else if ((unsigned long long)s.nevals == max_evals) {
+        r.st = ST_INSUFFICIENT_ITERATION;
+        return r;
+    }
+
+    tab_append(S, s, s.est0);
+    s.area = s.est0;
+    s.res_ext = s.est0;
+    s.err_ext = F64_MAX;
+    s.errsum = deltasum;
+    s.eolr = deltasum;
+    s.ertest = tolerance;
+    s.max_iters = (unsigned long long)nint + (max_evals - s.nevals) / 50ull;
+    s.iteration = (unsigned long long)nint;
+    s.active = true;
+    LocalSink sink;
+    sink.est = 0.;
+    sink.dlt = 0.;
+    sink.nev = 0;
+    sink.st = 0;
+    while (s.active) {
+        const int wi = s.wi;
+        const double ia = S.A(wi), ib = S.B(wi), ie = S.E(wi), id = S.D(wi);
+        const int ilv = S.LV(wi);
+        const double center = (ia + ib) * 0.5;
+        const QK q1 = rule_any<ORDERED, 12, U>(g, ia, center);
+        const QK q2 = rule_any<ORDERED, 12, U>(g, center, ib);
+        adaptive_step<true>(S, s, tol, max_evals, sink, ia, ib, center, ie, id, ilv, q1, q2);
+    }
+    r.est = sink.est;
+    r.dlt = sink.dlt;
+    r.nev = sink.nev;
+    r.st = sink.st;
+    return r;
+}
+
+struct Batch2D {
+    long long n;
+    const double* x0;
+    const double* x1;
+    long long range_stride;
+    const double* fparams;
+    long long fparam_stride;
+    const double* yparams;
+    long long yparam_stride;
+    int yrange_id;
+    int nyparams;
+    const double* pts_xy;  // (x, y) pairs: shared by the batch (device copy) or CSR values
+    int npts;              // shared count (when pts_offsets == nullptr)
+    const long long* pts_offsets;  // per-integral CSR offsets (in pairs) or nullptr
+    int npts_max;                  // largest per-integral count (slab geometry)
+    const unsigned int* worklist;  // optional subset (AUTO split) or nullptr
+    const unsigned long long* worklist_count;
+    Tol tol;
+    unsigned long long max_evals;
+    Outputs out;
+    Control* ctl;
+    SlabGeom slab;
+    int cap_outer, cap_inner;
+};
+
+// f(x, .) as a 1-D integrand of y
+template <class F2T>
+struct InnerF {
+    F2T f;
+    double x;
+    GKQ_DEV double operator()(double y) const { return f(x, y); }
+};
+
+// The outer integrand of double/algorithm/qags.rs:66-87 / qagp.rs:108-131 with the infinite
+// range wrapper of the outer algorithm folded in (single/util.rs:74-103).
+template <class F2T, bool QAGP>
+struct OuterIntegrand {
+    F2T f;
+    YRange yr;
+    Tol tol;
+    unsigned long long total_evals;
+    unsigned long long nevals;  // running sum of inner evaluations (usize in the reference)
+    uint32_t error;             // first inner error
+    unsigned long long inner_cap;
+    Slab Sin;
+    const double* pts_xy;
+    int npts;
+    bool transform;  // outer x-range infinite
+
+    __device__ __noinline__ double inner_integral(double x) {
+        // config1.max_evals = if error.is_some() { 0 } else { config.max_evals - nevals }
+        // (if an inner QAGP call overshot the budget by its last 50 samples the reference's
+        // usize subtraction wraps and Vec::reserve panics; we hand out a zero budget instead)
+        const unsigned long long budget =
+            (error != ST_NONE || nevals > total_evals) ? 0ull : (total_evals - nevals);
+        double y0, y1;
+        yr(x, y0, y1);
+        const bool ytr = !is_finite(y0) || !is_finite(y1);
+        if (ytr) {
+            y0 = transform_point(y0);
+            y1 = transform_point(y1);
+        }
+        Wrapped<InnerF<F2T>> g;
+        g.f.f = f;
+        g.f.x = x;
+        g.transform = ytr;
+        Res r;
+        if (QAGP) {
+            const double* p = pts_xy;
+            auto user_pt = [p](int k) { return p[2 * k + 1]; };  // every y of the 2-D points
+            r = seq_qagp<false, RuleUnroll<F2T, 12>::value>(g, y0, y1, ytr, user_pt, npts, tol,
+                                                             budget, inner_cap, Sin);
+        } else {
+            r = seq_qags<false, RuleUnroll<F2T, 12>::value>(g, y0, y1, tol, budget, inner_cap, Sin);
+        }
+        nevals += r.nev;
+        if (r.st != ST_NONE) {
+            if (error == ST_NONE) error = r.st;
+            return __longlong_as_double(0x7ff8000000000000ll);  // f64::NAN
+        }
+        return r.est;
+    }
+
+    GKQ_DEV double operator()(double t) {
+        if (transform) {
+            const double coef = 1. / (1. - fabs(t));
+            const double x2 = t * coef;
+            return inner_integral(x2) * coef * coef;
+        }
+        return inner_integral(t);
+    }
+};
+
+template <class F2T, bool QAGP, int NPARAMS>
+__global__ void __launch_bounds__(BLOCK) k_nested(const Batch2D P) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x;
+    // slab regions of this thread: [outer lists | inner lists]
+    Slab Sout, Sin;
+    Sout.d = P.slab.dbase + t;
+    Sout.w = P.slab.wbase + t;
+    Sout.stride = P.slab.stride;
+    Sout.cap = P.cap_outer;
+    const unsigned long long outer_d = slab_doubles(P.cap_outer, P.npts_max + 2);
+    Sin.d = Sout.d + outer_d * P.slab.stride;
+    Sin.w = Sout.w + slab_ints(P.cap_outer) * P.slab.stride;
+    Sin.stride = P.slab.stride;
+    Sin.cap = P.cap_inner;
+
+    const unsigned long long total = P.worklist ? *P.worklist_count : (unsigned long long)P.n;
+    unsigned long long* head = QAGP ? &P.ctl->headP : &P.ctl->headLoop;
+    for (;;) {
+        const unsigned long long slot = atomicAdd(head, 1ull);
+        if (slot >= total) break;
+        const unsigned long long i = P.worklist ? (unsigned long long)P.worklist[slot] : slot;
+        const double* my_pts = P.pts_xy;
+        int my_npts = P.npts;
+        if (P.pts_offsets) {
+            const long long o0 = P.pts_offsets[i];
+            my_pts = P.pts_xy + 2 * o0;
+            my_npts = (int)(P.pts_offsets[i + 1] - o0);
+        }
+
+        OuterIntegrand<F2T, QAGP> G;
+#pragma unroll
+        for (int k = 0; k < MAX_PARAMS; ++k)
+            G.f.p[k] = (k < NPARAMS)
+                           ? (P.fparam_stride ? P.fparams[(long long)k * P.fparam_stride + (long long)i]
+                                              : P.fparams[k])
+                           : 0.0;
+        G.yr.id = P.yrange_id;
+        G.yr.q[0] = G.yr.q[1] = 0.;
+        for (int k = 0; k < P.nyparams && k < 2; ++k)
+            G.yr.q[k] = P.yparam_stride ? P.yparams[(long long)k * P.yparam_stride + (long long)i]
+                                        : P.yparams[k];
+        G.tol = P.tol;
+        G.total_evals = P.max_evals;
+        G.nevals = 0;
+        G.error = ST_NONE;
+        G.inner_cap = 0;  // WorkSpace::new()
+        G.Sin = Sin;
+        G.pts_xy = my_pts;
+        G.npts = my_npts;
+
+        double xa = P.x0[(long long)i * P.range_stride];
+        double xb = P.x1[(long long)i * P.range_stride];
+        const bool xtr = !is_finite(xa) || !is_finite(xb);
+        if (xtr) {
+            xa = transform_point(xa);
+            xb = transform_point(xb);
+        }
+        G.transform = xtr;
+
+        unsigned long long outer_cap = 0;  // QAGS::new() / QAGP::new(): fresh outer workspace
+        const unsigned long long outer_evals = P.max_evals / 17ull;
+        Res r;
+        if (QAGP) {
+            // outer points = x of the 2-D points, transformed HERE when the x-range is infinite
+            // (double/algorithm/qagp.rs:98-106) and once more inside make_sorted_points.
+            const double* p = my_pts;
+            auto user_pt = [p, xtr](int k) {
+                const double x = p[2 * k];
+                return xtr ? transform_point(x) : x;
+            };
+            r = seq_qagp<true, 1>(G, xa, xb, xtr, user_pt, my_npts, P.tol, outer_evals, outer_cap, Sout);
+        } else {
+            r = seq_qags<true, 1>(G, xa, xb, P.tol, outer_evals, outer_cap, Sout);
+        }
+        // result.value.nevals = nevals; if error.is_some() { result.error = error }
+        write_result(P.out, (long long)i, r.est, r.dlt, (uint32_t)G.nevals,
+                     G.error != ST_NONE ? G.error : r.st);
+    }
+}
+
+struct Launch2D {
+    void (*run[2])(const Batch2D&, int grid, cudaStream_t);  // [0] QAGS2, [1] QAGP2
+    int (*occupancy[2])();
+};
+template <int ID>
+Launch2D make_launch2d();
+#define GKQ_DECL_F2(ID, NAME, NP, FL) template <> Launch2D make_launch2d<ID>();
+GKQ_F2_LIST(GKQ_DECL_F2)
+#undef GKQ_DECL_F2
+
+#define GKQ_INSTANTIATE_F2(ID, NAME, NP, FL)                                                      \
+    template <> Launch2D make_launch2d<ID>() {                                                    \
+        Launch2D L;                                                                               \
+        L.run[0] = [](const Batch2D& P, int grid, cudaStream_t st) {                              \
+            k_nested<F2<ID>, false, NP><<<grid, BLOCK, 0, st>>>(P);                               \
+        };                                                                                        \
+        L.run[1] = [](const Batch2D& P, int grid, cudaStream_t st) {                              \
+            k_nested<F2<ID>, true, NP><<<grid, BLOCK, 0, st>>>(P);                                \
+        };                                                                                        \
+        L.occupancy[0] = []() {                                                                   \
+            int nb = 0;                                                                           \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_nested<F2<ID>, false, NP>, BLOCK, 0); \
+            return nb;                                                                            \
+        };                                                                                        \
+        L.occupancy[1] = []() {                                                                   \
+            int nb = 0;                                                                           \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_nested<F2<ID>, true, NP>, BLOCK, 0); \
+            return nb;                                                                            \
+        };                                                                                        \
+        return L;                                                                                 \
+    }
+
+}  // namespace gkq

@@ -1,0 +1,219 @@
+/* gkquad_b200.h -- C ABI of the B200-native batched adaptive quadrature engine.
+ *
+ * This is the drop-in boundary for ONE hot path of the Rust crate gkquad 0.0.4
+ * (Kogia-sima/gkquad-rs): QAGS / QAGP adaptive Gauss-Kronrod quadrature (qk17 + qk25
+ * rules, bisection worklist, Wynn epsilon table, infinite-range transform) and the nested
+ * 2-D drivers QAGS2 / QAGP2.  Each entry point below names the reference interface it
+ * replaces (paths relative to /root/reference/gkquad/src/).  A host crate binds these
+ * symbols through FFI (see INTEGRATION.md for the Rust `extern "C"` block and the
+ * `impl Algorithm<DeviceIntegrand> for QagsB200` that sits on top of it).
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, POD structs; no C++/torch types cross the boundary;
+ *   - the unit of work is a BATCH of independent integrals (the reference integrates one
+ *     closure per call; closures cannot cross an FFI, so integrands are device functors
+ *     selected by ID from a registry -- gkq_functor_info / gkq_functor_lookup);
+ *   - every function returns 0 on success or a negative gkq_error; numerical failures are
+ *     NOT errors: like the reference's ValueWithError (common.rs:60-63) the partial value
+ *     is always written and the per-integral `status` carries the RuntimeError;
+ *   - there is no CPU fallback: without a CUDA device gkq_create fails with
+ *     GKQ_ERR_NO_DEVICE and nothing can be computed.
+ */
+#ifndef GKQUAD_B200_H
+#define GKQUAD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GKQ_ABI_VERSION 1
+
+typedef struct gkq_handle_s* gkq_handle_t;
+
+/* replaces: the Algorithm implementors QAGS / QAGP / AUTO
+ * (single/algorithm/{qags.rs:19-63, qagp.rs:20-64, auto.rs:7-35}) and, for the 2-D entry
+ * points, QAGS2 / QAGP2 / AUTO2 (double/algorithm/{qags.rs,qagp.rs,auto.rs}). */
+typedef enum gkq_algo { GKQ_ALGO_AUTO = 0, GKQ_ALGO_QAGS = 1, GKQ_ALGO_QAGP = 2 } gkq_algo;
+
+/* replaces: enum Tolerance (common.rs:9-19) and Tolerance::to_abs (common.rs:34-41). */
+typedef enum gkq_tol_kind {
+    GKQ_TOL_ABSOLUTE = 0,   /* delta <= abs                      */
+    GKQ_TOL_RELATIVE = 1,   /* delta <= rel * |I|                */
+    GKQ_TOL_ABS_OR_REL = 2, /* delta <= max(abs, rel * |I|)      */
+    GKQ_TOL_ABS_AND_REL = 3 /* delta <= min(abs, rel * |I|)      */
+} gkq_tol_kind;
+
+typedef struct gkq_tolerance {
+    int32_t kind; /* gkq_tol_kind */
+    int32_t _pad;
+    double abs_tol;
+    double rel_tol;
+} gkq_tolerance;
+
+/* replaces: enum RuntimeError (error.rs:140-178); numbering = declaration order, 0 = the
+ * `None` of ValueWithError::error. */
+typedef enum gkq_status {
+    GKQ_STATUS_NONE = 0,
+    GKQ_STATUS_INSUFFICIENT_ITERATION = 1,
+    GKQ_STATUS_ROUNDOFF_ERROR = 2,
+    GKQ_STATUS_SUBRANGE_TOO_SMALL = 3,
+    GKQ_STATUS_DIVERGENT = 4,
+    GKQ_STATUS_NAN_VALUE_ENCOUNTERED = 5
+} gkq_status;
+
+typedef enum gkq_error {
+    GKQ_OK = 0,
+    GKQ_ERR_INVALID_ARGUMENT = -1, /* NULL pointer, negative size, unknown id ...            */
+    GKQ_ERR_NAN_INPUT = -2,        /* NaN in tolerance / shared points (the reference panics:
+                                      single/integrator.rs:71,86-90, single/common.rs:94)     */
+    GKQ_ERR_NO_DEVICE = -3,        /* no usable CUDA device: there is no CPU fallback         */
+    GKQ_ERR_CUDA = -4,             /* a CUDA runtime call failed; see gkq_last_error          */
+    GKQ_ERR_OUT_OF_MEMORY = -5,
+    GKQ_ERR_UNSUPPORTED = -6
+} gkq_error;
+
+/* replaces: IntegrationConfig (single/common.rs:108-126; defaults tolerance =
+ * AbsOrRel(1.49e-8, 1.49e-8), max_evals = 2000, no points) and IntegrationConfig2
+ * (double/common.rs:14-32; default max_evals = 100000).  `points` are the singular points
+ * shared by every integral of the batch: for 1-D `npoints` doubles, for 2-D `npoints`
+ * interleaved (x, y) pairs.  HOST pointer, read during the call.
+ * `workspace_capacity` models WorkSpace::with_capacity(n) (single/workspace.rs:62-70): the
+ * Vec capacity is the `limit` seen by qpsrt / increase_nrmax (workspace.rs:165,236).
+ * 0 = a fresh WorkSpace::new() per integral, as single::integral does (integral.rs:17-19). */
+typedef struct gkq_config {
+    int32_t algo; /* gkq_algo */
+    int32_t _pad;
+    gkq_tolerance tol;
+    uint64_t max_evals;
+    uint64_t workspace_capacity;
+    const double* points;
+    int64_t npoints;
+} gkq_config;
+
+/* Fills *cfg with the reference's defaults: dim 1 -> IntegrationConfig::default(),
+ * dim 2 -> IntegrationConfig2::default(). */
+int gkq_config_default(int dim, gkq_config* cfg);
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+
+/* Creates an engine bound to CUDA device `device` (one handle per device per host thread;
+ * calls on one handle are stream-ordered).  Replaces the owned state of an Integrator
+ * (single/integrator.rs:31-35: algorithm + workspace): the handle owns all device scratch
+ * (survivor worklists, per-thread interval slabs, staging buffers), grown on demand and
+ * reused, so a warm call allocates nothing. */
+int gkq_create(int device, gkq_handle_t* out);
+int gkq_destroy(gkq_handle_t h);
+/* Message of the last failure on this handle (or of the last failed gkq_create when h is
+ * NULL).  Never NULL. */
+const char* gkq_last_error(gkq_handle_t h);
+int gkq_abi_version(void);
+
+/* ---- integrand registry ----------------------------------------------------------------
+ * replaces: trait Integrand (single/common.rs:129-145) / Integrand2 (double/common.rs:35-45)
+ * and DynamicY's range closure (double/range.rs:77-112).
+ * dim: 1 = 1-D integrands f(x; p), 2 = 2-D integrands f(x, y; p), 0 = y-range functors
+ * y(x; q) -> (y0, y1).  `flops_per_eval` is the algorithmic FP64 flop count of one
+ * evaluation used for the roofline figure. */
+int gkq_functor_count(int dim);
+int gkq_functor_info(int dim, int id, const char** name, int* nparams, double* flops_per_eval);
+int gkq_functor_lookup(int dim, const char* name); /* id, or GKQ_ERR_INVALID_ARGUMENT */
+
+/* ---- 1-D batches ------------------------------------------------------------------------
+ * replaces: Algorithm::integrate(&mut self, f, range, config) -> IntegrationResult
+ * (single/algorithm/mod.rs:16-23) as reached from Integrator::run (single/integrator.rs:
+ * 103-106), single::integral (integral.rs:17-19) and integral_with_config (:25-31), for `n`
+ * independent integrals at once.
+ *
+ *   a, b          range of integral i is [a[i*range_stride], b[i*range_stride]];
+ *                 range_stride 1 = per-integral, 0 = one shared range.  +-inf allowed:
+ *                 either end non-finite => the variable transform of single/util.rs:74-103,
+ *                 162-176 is applied to that integral (qags.rs:48, qagp.rs:50).
+ *   params        structure-of-arrays: parameter k of integral i is
+ *                 params[k*param_stride + i]; param_stride 0 = params[k] shared by all.
+ *                 May be NULL when the functor has no parameters.
+ *   pts_offsets,  optional per-integral singular points in CSR form (n+1 offsets into pts);
+ *   pts           NULL = every integral uses cfg->points.  With GKQ_ALGO_AUTO an integral
+ *                 with no points runs QAGS, otherwise QAGP (auto.rs:29-33).
+ *   out_*         estimate, delta (Solution, common.rs:213-231), nevals, status.
+ *
+ * gkq_integrate_batch: every array pointer is a DEVICE pointer; work is enqueued on
+ * `stream` (a cudaStream_t, NULL = default stream) and the call returns without
+ * synchronising.  gkq_integrate_batch_host: every array pointer is a HOST pointer
+ * (pageable or pinned); the call stages inputs to the device, computes, copies the four
+ * result arrays back (chunked and overlapped) and returns when they are complete. */
+int gkq_integrate_batch(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
+                        const double* a, const double* b, int64_t range_stride,
+                        const double* params, int64_t param_stride,
+                        const int64_t* pts_offsets, const double* pts,
+                        double* out_estimate, double* out_delta, uint32_t* out_nevals,
+                        uint32_t* out_status, void* stream);
+
+int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
+                             const double* a, const double* b, int64_t range_stride,
+                             const double* params, int64_t param_stride,
+                             const int64_t* pts_offsets, const double* pts,
+                             double* out_estimate, double* out_delta, uint32_t* out_nevals,
+                             uint32_t* out_status);
+
+/* ---- 2-D batches ------------------------------------------------------------------------
+ * replaces: Algorithm2::integrate(&mut self, f, range, config) (double/algorithm/mod.rs:7-10)
+ * for R = Rectangle / DynamicY (double/range.rs:11-34, 77-112) as reached from
+ * Integrator2::run (double/integrator.rs:80-87) and integral2 (double/integral.rs:9-16).
+ * Outer range of integral i: [x0[i*range_stride], x1[i*range_stride]]; inner range
+ * y(x) = yrange functor `yrange_id` with parameters yparams (SoA like params).  A Rectangle
+ * is yrange "const" with q = (y0, y1) (double/algorithm/qags.rs:18-27).  cfg->points holds
+ * (x, y) pairs; per-integral CSR pts_offsets counts pairs, pts_xy is interleaved. */
+int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id, int yrange_id,
+                         int64_t n, const double* x0, const double* x1, int64_t range_stride,
+                         const double* fparams, int64_t fparam_stride, const double* yparams,
+                         int64_t yparam_stride, const int64_t* pts_offsets, const double* pts_xy,
+                         double* out_estimate, double* out_delta, uint32_t* out_nevals,
+                         uint32_t* out_status, void* stream);
+
+int gkq_integrate2_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
+                              int yrange_id, int64_t n, const double* x0, const double* x1,
+                              int64_t range_stride, const double* fparams, int64_t fparam_stride,
+                              const double* yparams, int64_t yparam_stride,
+                              const int64_t* pts_offsets, const double* pts_xy,
+                              double* out_estimate, double* out_delta, uint32_t* out_nevals,
+                              uint32_t* out_status);
+
+/* ---- rule level -------------------------------------------------------------------------
+ * replaces: single::qk17 / qk25 (single/qk/mod.rs:28-41) -> QKResult (:16-25).  `rule` is 17
+ * or 25.  Device pointers; out4 is [4][n] SoA: estimate, delta, absvalue, asc. */
+int gkq_qk_batch(gkq_handle_t h, int rule, int functor_id, int64_t n, const double* a,
+                 const double* b, int64_t range_stride, const double* params,
+                 int64_t param_stride, double* out4, void* stream);
+
+/* ---- stream helpers / accounting --------------------------------------------------------- */
+int gkq_sync(gkq_handle_t h, void* stream);
+
+typedef struct gkq_stats {
+    uint64_t kernel_launches;   /* kernels of this library launched through the handle     */
+    uint64_t batches;           /* integrate calls                                         */
+    uint64_t integrals;         /* integrals submitted                                     */
+    uint64_t scratch_bytes;     /* device scratch currently owned by the handle            */
+    uint64_t last_survivors_qk25;  /* worklist sizes of the last QAGS batch, valid after    */
+    uint64_t last_survivors_loop;  /* gkq_sync (read back lazily): -> qk25 pass, -> loop    */
+} gkq_stats;
+int gkq_get_stats(gkq_handle_t h, gkq_stats* out);
+int gkq_reset_stats(gkq_handle_t h);
+
+/* Per-kernel timing for the roofline figure: when enabled every kernel launch of a batch call is
+ * bracketed by CUDA events on the launching stream (adds ~2 us per launch, so leave it off for
+ * throughput runs).  gkq_get_profile waits for the last batch and returns the number of
+ * entries written: kernel names (static strings) and durations in ms, in launch order. */
+int gkq_set_profiling(gkq_handle_t h, int enable);
+int gkq_get_profile(gkq_handle_t h, int max_entries, const char** names, float* ms);
+
+/* FP64 pipe calibration for the roofline denominator: runs a dependent-chain DFMA kernel
+ * that fills every SM and writes the achieved FLOP/s (2 flops per DFMA) to *flops_per_s.
+ * (MEASURED_PEAKS.json has no FP64 figure) */
+int gkq_measure_fp64_peak(gkq_handle_t h, int repeats, double* flops_per_s, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GKQUAD_B200_H */

@@ -1,0 +1,348 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI (libgkquad_b200.so), against the
+CPU oracle on the same seeded inputs and against the reference's golden vectors.
+
+Bars (BASELINE.json:north_star / SURVEY.md section 7):
+  * IEEE-exact integrands (+,-,*,/,sqrt): BIT-IDENTICAL estimate, delta, nevals, status;
+  * transcendental integrands (libdevice vs glibc differ by ulps): |delta| <= max(abs_tol,
+    rel_tol*|I|), identical status; nevals mismatches counted and bounded.
+Run with `pytest -m gpu` on a B200.
+"""
+import json
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import ALGO, STATUS, assert_rel, num
+
+pytestmark = pytest.mark.gpu
+
+G = json.load(open(Path(__file__).parent / "golden" / "reference_vectors.json"))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import gkquad_b200 as gk
+    return gk.default_engine(0)
+
+
+def _tol(t):
+    from gkquad_b200 import Tolerance
+    k = t[0]
+    return {"abs": lambda: Tolerance.Absolute(t[1]), "rel": lambda: Tolerance.Relative(t[1]),
+            "abs_or_rel": lambda: Tolerance.AbsOrRel(t[1], t[2]),
+            "abs_and_rel": lambda: Tolerance.AbsAndRel(t[1], t[2])}[k]()
+
+
+# ---- golden vectors of the reference, through the GPU ----------------------------------------
+# f1..f5 call libm (pow/ln/sin/cos): the reference's 1e-15 bound on the estimate is relaxed to
+# 1e-13 for those (libdevice differs from glibc by <= 2 ulp per call); f6/f7 are IEEE-exact and
+# keep 1e-15.  delta (1e-7), nevals and status stay exact.
+_EXACT_FUNCTORS = {"f6", "recip_p", "square", "lorentz_p"}
+
+
+@pytest.mark.parametrize("case", G["qk"], ids=lambda c: c["name"])
+def test_golden_qk(eng, case):
+    for a, b, sign in ((case["a"], case["b"], 1.0), (case["b"], case["a"], -1.0)):
+        out = eng.qk_batch(case["rule"], case["functor"], [a], [b], case["params"] or None).cpu().numpy()[:, 0]
+        assert_rel(out[0], sign * case["estimate"], 1e-13)
+        assert_rel(out[1], case["delta"], 1e-6)  # delta amplifies ulp noise of (kronrod - gauss)
+        assert_rel(out[2], case["absvalue"], 1e-13)
+        assert_rel(out[3], case["asc"], 1e-13)
+
+
+@pytest.mark.parametrize("case", G["single"], ids=lambda c: c["name"])
+def test_golden_single(eng, case):
+    etol = 1e-15 if case["functor"] in _EXACT_FUNCTORS else 1e-13
+    for a, b, sign in ((case["a"], case["b"], 1.0), (case["b"], case["a"], -1.0)):
+        r = eng.integrate_batch(case["functor"], a, b, case["params"] or None, algo=ALGO[case["algo"]],
+                                tol=_tol(case["tol"]), max_evals=case["max_evals"], points=case["points"],
+                                workspace_capacity=case["ws_capacity"], n=1)[0]
+        assert (r.error.value if r.error else 0) == STATUS[case["status"]], r
+        assert_rel(r.value.estimate, sign * case["estimate"], etol)
+        if case["name"] != "qags_f2":  # knife-edge case: SURVEY section 7 (nevals scatters under ulp noise)
+            assert r.value.nevals == case["nevals"], r
+            assert_rel(r.value.delta, case["delta"], 1e-6)
+
+
+@pytest.mark.parametrize("case", G["double"], ids=lambda c: c["name"])
+def test_golden_double(eng, case):
+    r = eng.integrate2_batch(case["functor2"], case["yrange"], num(case["x0"]), num(case["x1"]),
+                             fparams=case["fparams"] or None,
+                             yparams=[num(v) for v in case["yparams"]] or None, algo=ALGO[case["algo"]],
+                             tol=_tol(case["tol"]), max_evals=case["max_evals"],
+                             points=[tuple(p) for p in case["points"]], n=1)[0]
+    assert (r.error.value if r.error else 0) == STATUS[case["status"]], r
+    exact = case["functor2"] != "g2"  # g2 = exp(y/x) is the only transcendental one
+    assert_rel(r.value.estimate, case["estimate"], 1e-15 if exact else 1e-13)
+    assert_rel(r.value.delta, case["delta"], 1e-7 if exact else 1e-5)
+    assert r.value.nevals == case["nevals"], r
+
+
+@pytest.mark.parametrize("case", G["bench_asserts"], ids=lambda c: c["name"])
+def test_bench_assertions(eng, case):
+    probe = {c["name"]: c for c in G["probe_known_answers"]["cases"]}[case["name"]]
+    if case["dim"] == 1:
+        r = eng.integrate_batch(case["functor"], num(case["a"]), num(case["b"]), case["params"] or None,
+                                algo=ALGO[case["algo"]], tol=_tol(case["tol"]), max_evals=case["max_evals"],
+                                points=case["points"], n=1)[0]
+    else:
+        r = eng.integrate2_batch(case["functor2"], case["yrange"], num(case["x0"]), num(case["x1"]),
+                                 fparams=case["fparams"] or None, yparams=[num(v) for v in case["yparams"]] or None,
+                                 algo=ALGO[case["algo"]], tol=_tol(case["tol"]), max_evals=case["max_evals"],
+                                 points=[tuple(p) for p in case["points"]], n=1)[0]
+    assert r.error is None
+    assert abs(r.value.estimate - case["truth"]) <= case["abs_bound"]
+    # every bench integrand is IEEE-exact: bit-equal to the oracle's regenerated values
+    assert r.value.estimate == probe["estimate"] and r.value.nevals == probe["nevals"], r
+    assert_rel(r.value.delta, probe["delta"], 1e-12)
+
+
+# ---- seeded batches against the oracle ---------------------------------------------------------
+def _run_both(eng, wname, n, start=0, device=True):
+    import torch
+    from gkquad_b200.workloads import WORKLOADS, csr_points_from_param0
+    from gpu_common import compare, tol_to_oracle
+    from oracle import oracle as O
+    W = WORKLOADS[wname]
+    p = W.make_params(start, n)
+    kw_g, kw_o = {}, {}
+    if W.points == "param0":
+        off, pts = csr_points_from_param0(p)
+        kw_g = dict(pts_offsets=off, pts=pts)
+        kw_o = dict(pts_offsets=off, points=pts)
+    elif W.points:
+        kw_g = dict(points=W.points)
+        kw_o = dict(points=W.points)
+    pg = torch.as_tensor(p, device="cuda:0") if device else p
+    g = eng.integrate_batch(W.functor, W.a, W.b, pg, algo=ALGO[W.algo], tol=W.tol, max_evals=W.max_evals,
+                            n=n, **kw_g)
+    ref = O.integrate_batch(ALGO[W.algo], W.functor, W.a, W.b, params=p, tol=tol_to_oracle(W.tol),
+                            max_evals=W.max_evals, n=n, **kw_o)
+    return W, p, g, ref
+
+
+@pytest.mark.parametrize("wname", ["S2", "P0", "I0", "I1"])
+def test_batch_bit_exact(eng, wname):
+    """IEEE-exact integrands: estimate, delta, nevals and status bit-identical to the oracle."""
+    from gpu_common import compare
+    W, p, g, ref = _run_both(eng, wname, 20000)
+    s = compare(g, ref, W.tol, exact=True, label=wname)
+    if W.truth is not None:
+        truth = W.truth(p)
+        ok = ref["status"] == 0
+        from gpu_common import allowed_error
+        assert np.all(np.abs(g.numpy().estimate - truth)[ok] <= allowed_error(W.tol, truth)[ok] + 1e-14)
+
+
+@pytest.mark.parametrize("wname,max_nevals_mismatch", [("S1", 0.002), ("S3", 0.01), ("I2", 0.01),
+                                                        ("P1", 0.10), ("P2", 0.10)])
+def test_batch_tolerance_parity(eng, wname, max_nevals_mismatch):
+    """Transcendental integrands: within tolerance of the oracle, identical status."""
+    from gpu_common import compare
+    n = 20000 if wname.startswith("S") else 4000
+    W, p, g, ref = _run_both(eng, wname, n)
+    s = compare(g, ref, W.tol, label=wname)
+    print(s)
+    assert s["out_of_tol"] == 0, s
+    assert s["status_mismatch"] == 0, s
+    assert s["nevals_mismatch"] <= max_nevals_mismatch * n, s
+
+
+def test_host_entry_matches_device_entry(eng):
+    """gkq_integrate_batch_host (chunked H2D/compute/D2H pipeline) == device entry, bit for bit."""
+    from gkquad_b200.workloads import WORKLOADS
+    n = 300_001  # > one 2^18 chunk, ragged tail
+    W, p, g_dev, _ = (None, None, None, None)
+    import torch
+    W = WORKLOADS["S1"]
+    p = W.make_params(0, n)
+    g_host = eng.integrate_batch(W.functor, W.a, W.b, p, algo=ALGO[W.algo], tol=W.tol, n=n)
+    g_dev = eng.integrate_batch(W.functor, W.a, W.b, torch.as_tensor(p, device="cuda:0"), algo=ALGO[W.algo],
+                                tol=W.tol, n=n).numpy()
+    assert np.array_equal(g_host.estimate, g_dev.estimate) and np.array_equal(g_host.delta, g_dev.delta)
+    assert np.array_equal(g_host.nevals, g_dev.nevals) and np.array_equal(g_host.status, g_dev.status)
+    # per-integral ranges through the host entry
+    a = np.zeros(n)
+    b = np.ones(n)
+    g2 = eng.integrate_batch(W.functor, a, b, p, algo=ALGO[W.algo], tol=W.tol)
+    assert np.array_equal(g2.estimate, g_dev.estimate)
+
+
+def test_full_size_properties(eng):
+    """BASELINE cfg-2 size (1M, S1): properties that need no oracle -- closed-form truth within
+    tolerance, reversed range negates exactly, results independent of batch position."""
+    import torch
+    from gkquad_b200.workloads import WORKLOADS
+    W = WORKLOADS["S1"]
+    n = 1 << 20
+    p = W.make_params(0, n)
+    pt = torch.as_tensor(p, device="cuda:0")
+    g = eng.integrate_batch(W.functor, 0.0, 1.0, pt, algo=ALGO["QAGS"], tol=W.tol, n=n).numpy()
+    truth = W.truth(p)
+    # a few 1e-4 of S1 stop with RoundoffError at the initial rule (the oracle does the same)
+    assert set(np.unique(g.status)).issubset({0, 2}) and (g.status == 0).mean() > 0.999
+    ok = g.status == 0
+    assert np.all(np.abs(g.estimate - truth)[ok] <= 1e-10 * np.abs(truth)[ok] + 1e-16)
+    assert np.all(np.abs(g.estimate - truth) <= 1e-9 * np.abs(truth) + 1e-15)
+    assert np.all((g.nevals - 17) % 25 == 0) and g.nevals.max() <= 1992
+    rev = eng.integrate_batch(W.functor, 1.0, 0.0, pt, algo=ALGO["QAGS"], tol=W.tol, n=n).numpy()
+    assert np.array_equal(rev.estimate, -g.estimate) and np.array_equal(rev.nevals, g.nevals)
+    # a shuffled batch gives the same per-integral answers (no cross-lane leakage)
+    perm = np.random.default_rng(0).permutation(n)
+    gs = eng.integrate_batch(W.functor, 0.0, 1.0, torch.as_tensor(np.ascontiguousarray(p[:, perm]), device="cuda:0"),
+                             algo=ALGO["QAGS"], tol=W.tol, n=n).numpy()
+    assert np.array_equal(gs.estimate, g.estimate[perm]) and np.array_equal(gs.nevals, g.nevals[perm])
+
+
+# ---- edge cases against the oracle ------------------------------------------
+EDGE = [
+    dict(f="square", a=0.5, b=0.5, algo="QAGS"),
+    dict(f="f1", a=0.0, b=1.0, algo="QAGS", max_evals=16),
+    dict(f="lorentz_p", p=[3.0], a=0.0, b=1.0, algo="QAGS", tol=("rel", 1e-10), max_evals=41),
+    dict(f="lorentz_p", p=[3.0], a=0.0, b=1.0, algo="QAGS", tol=("rel", 1e-10), max_evals=66),
+    dict(f="recip_p", p=[1.0], a=0.0, b=1.0, algo="QAGS", tol=("abs", 1e-10), max_evals=60),
+    dict(f="sqrt_shift_p", p=[0.5], a=0.0, b=1.0, algo="QAGS"),
+    dict(f="sqrt_shift_p", p=[0.3], a=0.0, b=1.0, algo="QAGP", points=[0.5]),
+    dict(f="inv_abs_shift_p", p=[0.5], a=0.0, b=1.0, algo="QAGS"),
+    dict(f="lorentz_p", p=[2.0], a=0.0, b=math.inf, algo="QAGS", tol=("rel", 1e-10)),
+    dict(f="lorentz_p", p=[2.0], a=-math.inf, b=0.0, algo="QAGS", tol=("rel", 1e-10)),
+    dict(f="lorentz_p", p=[2.0], a=math.inf, b=-math.inf, algo="QAGS", tol=("rel", 1e-10)),
+    dict(f="recip_p", p=[1.0], a=-1.0, b=1.0, algo="QAGP", points=[0.0, 5.0, -7.0], tol=("abs", 1e-10)),
+    dict(f="recip_p", p=[1.0], a=-1.0, b=1.0, algo="QAGP", points=[0.0, 0.0, 1.0], tol=("abs", 1e-10)),
+    dict(f="f6", a=0.0, b=2.0, algo="QAGP", points=[1.0], tol=("abs", 1e-10)),
+    dict(f="f6", a=2.0, b=0.0, algo="QAGP", points=[1.0, 0.5, 1.5], tol=("abs", 1e-10)),
+    dict(f="f6", a=0.0, b=2.0, algo="QAGP", points=[1.0, 0.5], max_evals=74),
+    dict(f="f6", a=0.0, b=2.0, algo="QAGP", points=[1.0, 0.5], tol=("abs", 1e-12), max_evals=75),
+    dict(f="f6", a=0.0, b=2.0, algo="QAGP", points=[1.0], tol=("abs", 1e-12), max_evals=130),
+    dict(f="f6", a=0.0, b=2.0, algo="AUTO", points=[], tol=("abs", 1e-6)),
+    dict(f="lorentz_p", p=[1e4], a=-1.0, b=1.0, algo="QAGS", tol=("rel", 1e-13)),
+    dict(f="lorentz_p", p=[1e4], a=-1.0, b=1.0, algo="QAGS", tol=("rel", 1e-13), max_evals=400),
+    dict(f="recip_p", p=[1.0], a=0.0, b=1.0, algo="QAGS", tol=("rel", 1e-8)),          # divergent 1/x
+    dict(f="inv_abs_shift_p", p=[0.3], a=0.0, b=1.0, algo="QAGP", points=[0.3], tol=("rel", 1e-8)),
+    dict(f="lorentz_p", p=[1.0], a=-math.inf, b=math.inf, algo="QAGP", points=[0.0, 1.0], tol=("rel", 1e-10)),
+    dict(f="lorentz_p", p=[1.0], a=0.0, b=1.0, algo="QAGS", tol=("abs_and_rel", 1e-6, 1e-9)),
+    dict(f="lorentz_p", p=[1.0], a=0.0, b=1.0, algo="QAGS", tol=("abs_or_rel", 1e-12, 1e-4)),
+]
+
+
+@pytest.mark.parametrize("c", EDGE, ids=lambda c: f"{c['f']}-{c['algo']}-{c.get('max_evals', 2000)}-{c['a']}")
+def test_edge_cases_bit_exact(eng, c):
+    """All edge-case integrands are IEEE-exact -> the GPU must reproduce the oracle bit for bit
+    (estimate, delta, nevals, status), including NaN/inf poisoning and the status quirks."""
+    from oracle import oracle as O
+    tol = c.get("tol", ("abs_or_rel", 1.49e-8, 1.49e-8))
+    me = c.get("max_evals", 2000)
+    ref = O.integrate_one(ALGO[c["algo"]], c["f"], c["a"], c["b"], params=c.get("p", []), points=c.get("points", []),
+                          tol=tol, max_evals=me)
+    r = eng.integrate_batch(c["f"], c["a"], c["b"], c.get("p"), algo=ALGO[c["algo"]], tol=_tol(tol), max_evals=me,
+                            points=c.get("points", []), n=1)[0]
+    st = r.error.value if r.error else 0
+    assert st == ref["status"], (r, ref)
+    assert r.value.nevals == ref["nevals"], (r, ref)
+    for got, want in ((r.value.estimate, ref["estimate"]), (r.value.delta, ref["delta"])):
+        assert (math.isnan(got) and math.isnan(want)) or got == want, (r, ref)
+
+
+def test_workspace_capacity_changes_limit(eng):
+    """`limit` = Vec capacity (workspace.rs:165,236): a too-small persistent capacity changes the
+    bisection order; the engine must follow the oracle for both."""
+    from oracle import oracle as O
+    for cap in (0, 50, 12):
+        ref = O.integrate_one(O.ALGO_QAGS, "lorentz_p", -1.0, 1.0, params=[1e4], tol=("rel", 1e-13),
+                              max_evals=500, ws_capacity=cap)
+        r = eng.integrate_batch("lorentz_p", -1.0, 1.0, [1e4], algo=ALGO["QAGS"], tol=_tol(("rel", 1e-13)),
+                                max_evals=500, workspace_capacity=cap, n=1)[0]
+        assert (r.value.estimate, r.value.delta, r.value.nevals) == (ref["estimate"], ref["delta"], ref["nevals"])
+
+
+def test_mixed_auto_csr(eng):
+    """AUTO over per-integral points: integrals without points run QAGS, the others QAGP
+    (auto.rs:29-33); ragged CSR incl. empty rows, duplicated and out-of-range points."""
+    import torch
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    n = 5000
+    cnt = rng.integers(0, 4, n)
+    cnt[:7] = [0, 1, 0, 3, 2, 0, 1]
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    pts = rng.uniform(-1.2, 1.2, off[-1])
+    p = (0.5 + 50 * rng.random(n))[None, :]
+    ref = O.integrate_batch(O.ALGO_AUTO, "lorentz_p", -1.0, 1.0, params=p, points=pts, pts_offsets=off,
+                            tol=("rel", 1e-12), n=n)
+    g = eng.integrate_batch("lorentz_p", -1.0, 1.0, torch.as_tensor(p, device="cuda:0"), algo=ALGO["AUTO"],
+                            tol=_tol(("rel", 1e-12)), pts_offsets=off, pts=pts, n=n)
+    from gpu_common import compare
+    compare(g, ref, _tol(("rel", 1e-12)), exact=True)
+
+
+# ---- 2-D batches ---------------------------------------------------------------------------------
+def test_double_batch_bit_exact(eng):
+    """cfg-5 shapes at oracle-friendly sizes: D0 (literal bench, parameterised) and D1 (singular point
+    per integral, CSR).  All 2-D bench integrands are IEEE-exact -> bit-identical to the oracle."""
+    import torch
+    from gkquad_b200.workloads import WORKLOADS
+    from gpu_common import compare, tol_to_oracle
+    from oracle import oracle as O
+    W = WORKLOADS["D0"]
+    n = 512
+    p = W.make_params(0, n)
+    ref = O.integrate2_batch(ALGO[W.algo], W.functor, W.yrange, W.a, W.b, fparams=p, yparams=W.yparams,
+                             points=W.points, tol=tol_to_oracle(W.tol), max_evals=W.max_evals, n=n)
+    g = eng.integrate2_batch(W.functor, W.yrange, W.a, W.b, fparams=torch.as_tensor(p, device="cuda:0"),
+                             yparams=W.yparams, algo=ALGO[W.algo], tol=W.tol, max_evals=W.max_evals,
+                             points=W.points, n=n)
+    compare(g, ref, W.tol, exact=True, label="D0")
+    assert np.all(g.numpy().nevals == 12500) and np.all(g.numpy().estimate == 0.0)
+
+    W = WORKLOADS["D1"]
+    n = 96
+    p = W.make_params(0, n)
+    off = np.arange(n + 1, dtype=np.int64)
+    pxy = np.ascontiguousarray(p.T)
+    ref = O.integrate2_batch(ALGO[W.algo], W.functor, W.yrange, W.a, W.b, fparams=p, yparams=W.yparams,
+                             points=pxy, pts_offsets=off, tol=tol_to_oracle(W.tol), max_evals=W.max_evals, n=n)
+    g = eng.integrate2_batch(W.functor, W.yrange, W.a, W.b, fparams=p, yparams=W.yparams, algo=ALGO[W.algo],
+                             tol=W.tol, max_evals=W.max_evals, pts_offsets=off, pts_xy=pxy, n=n)
+    s = compare(g, ref, W.tol, exact=True, label="D1")
+    print(s, np.bincount(ref["status"]))
+
+
+def test_double_dynamic_ranges(eng):
+    """DynamicY ranges (0..x, circle) and infinite x infinite rectangles against the oracle."""
+    from oracle import oracle as O
+    from gpu_common import compare
+    cases = [("g1", "const", 0.0, 1.0, [0.0, 1.0], ("rel", 1e-10), ALGO["QAGS"], []),
+             ("g3", "circle", -0.5, 0.5, [0.25], ("abs", 1e-12), ALGO["QAGS"], []),
+             ("g4", "const", 0.0, math.inf, [0.0, math.inf], ("abs", 1e-8), ALGO["QAGS"], []),
+             ("rsqrt3", "const", -math.inf, math.inf, [-math.inf, math.inf], ("abs_or_rel", 1.49e-8, 1.49e-8), 0, []),
+             ("gp2", "circle", -1.0, 1.0, [1.0], ("abs", 1e-5), ALGO["QAGP"], [(0.0, 0.0)]),
+             ("gp1", "const", -1.0, math.inf, [-math.inf, 2.0], ("rel", 1e-4), ALGO["QAGP"], [(0.0, 0.0), (1.0, 1.0)])]
+    for f, yr, x0, x1, yq, tol, algo, pts in cases:
+        ref = O.integrate2_batch(algo, f, yr, x0, x1, yparams=yq, points=pts, tol=tol, max_evals=100000, n=1)
+        g = eng.integrate2_batch(f, yr, x0, x1, yparams=yq, algo=algo, tol=_tol(tol), max_evals=100000,
+                                 points=pts, n=1)
+        compare(g, ref, _tol(tol), exact=True, label=f)
+
+
+def test_api_mirror_on_gpu(eng):
+    """The host-side mirror of gkquad's API (single::integral, Integrator builder, integral2)."""
+    from gkquad_b200 import Tolerance, double, single
+    r = single.integral(single.DeviceIntegrand("square"), (0.0, 1.0)).unwrap()
+    assert abs(r.estimate - 1.0 / 3.0) <= 1.49e-8 and r.nevals == 17
+    it = single.Integrator.new(single.DeviceIntegrand("recip_p", [1.0])).points([0.0]).tolerance(Tolerance.Absolute(1.49e-8))
+    r = it.run((-1.0, 1.0)).unwrap()
+    assert abs(r.estimate) <= 1.49e-8 and r.nevals == 250
+    r = single.Integrator.new(single.DeviceIntegrand("lorentz_p", [1.0])).run(slice(None, None)).unwrap()
+    assert abs(r.estimate - math.pi) <= 1.49e-8
+    r = double.integral2(double.DeviceIntegrand2("xy"), ((0.0, 1.0), (0.0, 1.0))).unwrap()
+    assert abs(r.estimate - 0.25) <= 1.49e-8 and r.nevals == 289
+    q = single.qk17(single.DeviceIntegrand("square"), (0.0, 1.0))
+    assert abs(q.estimate - 1.0 / 3.0) < 1e-15
+    res = single.Integrator.new(single.DeviceIntegrand("recip_p", [1.0])).tolerance(Tolerance.Relative(1e-8)).run((0.0, 1.0))
+    assert res.has_err()
+    with pytest.raises(ValueError):
+        res.unwrap()
