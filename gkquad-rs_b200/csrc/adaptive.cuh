@@ -82,7 +82,11 @@ struct Lane {
     // QAGP seeding phase
     bool seeding;
     int nint, seed_k, w0, w1;
+    int pad_[2];
 };
+// k_adaptive keeps one Lane per thread in shared memory: a size of 8 x (odd) bytes makes the
+// 64-bit fields of consecutive lanes fall into distinct bank pairs.
+static_assert(sizeof(Lane) % 8 == 0 && (sizeof(Lane) / 8) % 2 == 1, "Lane must be 8 x odd bytes");
 
 // ---- WorkSpace on a slab --------------------------------------------------------------
 GKQ_DEV void ws_push(const Slab& S, Lane& s, double a, double b, double e, double d, int lv) {

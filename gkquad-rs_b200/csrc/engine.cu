@@ -244,13 +244,13 @@ int upload_shared_points(gkq_handle_t h, const double* pts, size_t count, cudaSt
 }
 
 // Persistent grid size: resident blocks on every SM, bounded by the slab memory budget.
-int persistent_grid(gkq_handle_t h, int occ, int cap, int npts_max) {
+int persistent_grid(gkq_handle_t h, int occ, int cap, int npts_max, int block = BLOCK) {
     if (occ < 1) occ = 1;
     unsigned long long per_thread = slab_doubles(cap, npts_max) * 8ull + slab_ints(cap) * 4ull;
     unsigned long long budget = (unsigned long long)h->total_mem / 3ull;
     unsigned long long max_threads = budget / per_thread;
     long long grid = (long long)h->sm_count * occ;
-    long long max_grid = (long long)(max_threads / BLOCK);
+    long long max_grid = (long long)(max_threads / block);
     if (max_grid < 1) return -1;
     if (grid > max_grid) grid = max_grid;
     return (int)grid;
@@ -527,10 +527,11 @@ static int run_qags(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, cudaS
     if (need > (1ull << 26)) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
     const int cap = (int)need;  // list length never exceeds the reserve request
     (void)lim;
-    int grid = persistent_grid(h, h->occ_loop[fid], cap, 0);
+    int grid = persistent_grid(h, h->occ_loop[fid], cap, 0, ABLOCK);
     if (grid < 1) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
-    if ((long long)grid > nblocks) grid = (int)nblocks;
-    if ((rc = ensure_slab(h, (unsigned long long)grid * BLOCK, cap, 0, P.slab))) return rc;
+    const long long ablocks = (P.n + ABLOCK - 1) / ABLOCK;
+    if ((long long)grid > ablocks) grid = (int)ablocks;
+    if ((rc = ensure_slab(h, (unsigned long long)grid * ABLOCK, cap, 0, P.slab))) return rc;
     prof_begin(h, "k_adaptive<QAGS>", st);
     L.qags_loop(P, grid, st);
     prof_end(h, st);
@@ -545,11 +546,11 @@ static int run_qagp(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, int n
     const unsigned long long need = (unsigned long long)npts_max + 1ull + P.max_evals / 50ull + 1ull;
     if (need > (1ull << 26)) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
     const int cap = (int)need;
-    const long long nblocks = (P.n + BLOCK - 1) / BLOCK;
-    int grid = persistent_grid(h, h->occ_qagp[fid], cap, npts_max + 2);
+    const long long nblocks = (P.n + ABLOCK - 1) / ABLOCK;
+    int grid = persistent_grid(h, h->occ_qagp[fid], cap, npts_max + 2, ABLOCK);
     if (grid < 1) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
     if ((long long)grid > nblocks) grid = (int)nblocks;
-    if ((rc = ensure_slab(h, (unsigned long long)grid * BLOCK, cap, npts_max + 2, P.slab))) return rc;
+    if ((rc = ensure_slab(h, (unsigned long long)grid * ABLOCK, cap, npts_max + 2, P.slab))) return rc;
     prof_begin(h, "k_adaptive<QAGP>", st);
     L.qagp(P, grid, st);
     prof_end(h, st);
@@ -680,6 +681,24 @@ int gkq_qk_batch(gkq_handle_t h, int rule, int functor_id, int64_t n, const doub
     else
         h->l1[functor_id].qk25(P, out4, grid, (cudaStream_t)stream);
     return launch_check(h, "k_qk_batch");
+}
+
+int gkq_functor_eval_batch(gkq_handle_t h, int functor_id, int64_t n, const double* x,
+                           const double* params, int64_t param_stride, double* y, void* stream) {
+    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
+    if (functor_id < 0 || functor_id >= F1_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown functor id");
+    if (n < 0 || !x || !y) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "bad argument");
+    if (F1_TABLE[functor_id].nparams > 0 && !params) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "params is NULL");
+    if (n == 0) return GKQ_OK;
+    GKQ_CUDA(h, cudaSetDevice(h->device));
+    Batch1D P;
+    memset(&P, 0, sizeof P);
+    P.n = n;
+    P.params = params;
+    P.param_stride = param_stride;
+    const int grid = (int)((n + BLOCK - 1) / BLOCK);
+    h->l1[functor_id].eval(P, x, y, grid, (cudaStream_t)stream);
+    return launch_check(h, "k_eval");
 }
 
 // Host-pointer entry: chunked, double-buffered H2D -> kernels -> D2H pipeline.

@@ -160,22 +160,14 @@ struct Wrapped {
 // to the CPU for IEEE-exact integrands.  UNROLL = how many node pairs are inlined per loop
 // trip (N = fully unrolled, values stay in registers; smaller = the 2N values live in
 // local memory, which is lane-interleaved and L1-resident).
-template <int N, int UNROLL, class G>
-GKQ_DEV QK qk_rule(const G& g, double a, double b) {
+// Second half of the rule (single/qk/naive.rs:70-105): Kronrod / Gauss / |f| sums and the asc
+// pass over already evaluated samples, in the reference's order.
+template <int N>
+GKQ_DEV QK qk_reduce(const double (&fv1)[N], const double (&fv2)[N], double f_center, double a,
+                     double b) {
     using R = Rule<N>;
-    double fv1[N], fv2[N];
-    const double center = 0.5 * (a + b);
     const double half_length = 0.5 * (b - a);
     const double abs_half_length = fabs(half_length);
-
-#pragma unroll UNROLL
-    for (int j = 0; j < N; ++j) {
-        double abscissa = half_length * R::xgk(j);
-        fv1[j] = g(center - abscissa);
-        fv2[j] = g(center + abscissa);
-    }
-    const double f_center = g(center);
-
     double result_gauss = 0.;
     double result_kronrod = f_center * R::WCK;
     double result_abs = fabs(result_kronrod);
@@ -202,6 +194,78 @@ GKQ_DEV QK qk_rule(const G& g, double a, double b) {
     q.absvalue = result_abs;
     q.asc = result_asc;
     return q;
+}
+
+// The Gauss-Kronrod rule of single/qk/naive.rs:32-106 for ONE thread: the thread evaluates
+// all 2N+1 nodes itself and accumulates the Kronrod / Gauss / |f| sums and the asc pass in
+// the reference's order (j = 0..N-1 from the centre outwards), so results are bit-equal
+// to the CPU for IEEE-exact integrands.  UNROLL = how many node pairs are inlined per loop
+// trip (N = fully unrolled, values stay in registers; smaller = the 2N values live in
+// local memory, which is lane-interleaved and L1-resident).
+template <int N, int UNROLL, class G>
+GKQ_DEV QK qk_rule(const G& g, double a, double b) {
+    using R = Rule<N>;
+    double fv1[N], fv2[N];
+    const double center = 0.5 * (a + b);
+    const double half_length = 0.5 * (b - a);
+#pragma unroll UNROLL
+    for (int j = 0; j < N; ++j) {
+        double abscissa = half_length * R::xgk(j);
+        fv1[j] = g(center - abscissa);
+        fv2[j] = g(center + abscissa);
+    }
+    const double f_center = g(center);
+    return qk_reduce<N>(fv1, fv2, f_center, a, b);
+}
+
+// Warp-cooperative 25-point rule on up to two ranges (one bisection step = 50 samples) of ONE
+// integral: lane L evaluates sample slots L and L+32; slot s < 25 belongs to range 0, 25 <= s
+// < 50 to range 1; inside a range t = s % 25: t < 12 -> centre - h*x_t, t < 24 -> centre +
+// h*x_(t-12), t = 24 -> centre.  Every lane then pulls the samples with shuffles in the
+// reference's summation order and reduces redundantly (uniform control flow), so the result is
+// bit-identical to qk_rule.  Used when a warp has only a few live integrals left (the tail),
+// where one thread walking 50 samples alone would be the critical path of the whole batch.
+template <class G>
+GKQ_DEV void qk25_pair_coop(const G& g, const double* xgk_sh, bool h0, double a0, double b0, bool h1,
+                            double a1, double b1, QK& q0, QK& q1) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    double v[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int slot = lane + 32 * r;
+        const int half = slot >= 25 ? 1 : 0;
+        const int t = slot - 25 * half;
+        const bool on = slot < 50 && (half ? h1 : h0);
+        v[r] = 0.;
+        if (on) {
+            const double a = half ? a1 : a0, b = half ? b1 : b0;
+            const double center = 0.5 * (a + b);
+            const double half_length = 0.5 * (b - a);
+            double x = center;
+            if (t < 24) {
+                const double abscissa = half_length * xgk_sh[t < 12 ? t : t - 12];
+                x = t < 12 ? center - abscissa : center + abscissa;
+            }
+            v[r] = g(x);
+        }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        if (half ? !h1 : !h0) continue;  // warp-uniform
+        double fv1[12], fv2[12];
+        auto pull = [&](int slot) {
+            return slot < 32 ? __shfl_sync(FULL, v[0], slot) : __shfl_sync(FULL, v[1], slot - 32);
+        };
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            fv1[j] = pull(25 * half + j);
+            fv2[j] = pull(25 * half + 12 + j);
+        }
+        const double fc = pull(25 * half + 24);
+        const QK q = qk_reduce<12>(fv1, fv2, fc, half ? a1 : a0, half ? b1 : b0);
+        if (half) q1 = q; else q0 = q;
+    }
 }
 
 }  // namespace gkq

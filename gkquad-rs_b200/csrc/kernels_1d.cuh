@@ -19,6 +19,19 @@
 namespace gkq {
 
 constexpr int BLOCK = 256;
+// The persistent adaptive kernels use smaller blocks: their per-lane scalars (struct Lane, 200 B)
+// live in static shared memory so that the sampling loops run at a low register count.
+constexpr int ABLOCK = 128;
+// A warp with at most this many live integrals evaluates them cooperatively (latency mode).
+#ifndef GKQ_COOP_MAX_LIVE
+#define GKQ_COOP_MAX_LIVE 8
+#endif
+constexpr int COOP_MAX_LIVE = GKQ_COOP_MAX_LIVE;
+// Resident 128-thread blocks per SM the adaptive kernels are compiled for (register cap
+// 65536 / (128 * N)): 6 -> 80 registers, 24 warps per SM (tuned with ncu, profiles/).
+#ifndef GKQ_ADAPTIVE_MIN_BLOCKS
+#define GKQ_ADAPTIVE_MIN_BLOCKS 6
+#endif
 
 // Device-side control block of one batch call (zeroed by a memset node before the kernels).
 struct Control {
@@ -200,10 +213,14 @@ GKQ_DEV int make_sorted_points(const Slab& S, double begin, double end, const do
 
 // ---- persistent adaptive kernel ------------------------------------------------------------------
 template <class F, bool QAGP, int NPARAMS>
-__global__ void __launch_bounds__(BLOCK) k_adaptive(const Batch1D P) {
+__global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(const Batch1D P) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const unsigned long long t = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x;
+    const unsigned long long t = (unsigned long long)blockIdx.x * ABLOCK + threadIdx.x;
+    // lane-indexed node table for the cooperative path (constant memory would serialise)
+    __shared__ double s_xgk[12];
+    if (threadIdx.x < 12) s_xgk[threadIdx.x] = c_xgk25[threadIdx.x];
+    __syncthreads();
 
     Slab S;
     S.d = P.slab.dbase + t;
@@ -217,8 +234,10 @@ __global__ void __launch_bounds__(BLOCK) k_adaptive(const Batch1D P) {
     else
         total = P.ctl->countLoop;
     unsigned long long* head = QAGP ? &P.ctl->headP : &P.ctl->headLoop;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * (ABLOCK / 32);
 
-    Lane s;
+    __shared__ Lane s_lanes[ABLOCK];
+    Lane& s = s_lanes[threadIdx.x];
     s.active = false;
     s.idx = 0;
     GlobalSink sink;
@@ -229,14 +248,33 @@ __global__ void __launch_bounds__(BLOCK) k_adaptive(const Batch1D P) {
 
     for (;;) {
         // ---- refill idle lanes from the global queue (one atomic per warp per trip) ----
+        // While the queue is long every idle lane takes an item (throughput mode).  When what
+        // is left would not fill the grid any more, warps only top up to an equal share of the
+        // remainder, so the last items are spread thinly over ALL warps and finish in the
+        // cooperative latency mode instead of piling up on the few warps that ask first.
         const unsigned want = __ballot_sync(FULL, !s.active && !exhausted);
         if (want) {
             const int leader = __ffs(want) - 1;
             unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(head, (unsigned long long)__popc(want));
+            int take = __popc(want);
+            // (all lanes) number of live integrals this warp already has
+            const int live_now = __popc(__ballot_sync(FULL, s.active));
+            if (lane == leader) {
+                const unsigned long long cur = *(volatile unsigned long long*)head;
+                const unsigned long long remaining = total > cur ? total - cur : 0ull;
+                const unsigned long long share = (remaining + nwarps - 1ull) / nwarps;
+                if (remaining > 0ull && share <= (unsigned long long)COOP_MAX_LIVE) {
+                    int room = (int)share - live_now;
+                    if (room < 1) room = live_now == 0 ? 1 : 0;
+                    if (room < take) take = room;
+                }
+                if (take > 0) base = atomicAdd(head, (unsigned long long)take);
+            }
             base = __shfl_sync(FULL, base, leader);
-            if (!s.active && !exhausted) {
-                const unsigned long long my = base + __popc(want & ((1u << lane) - 1u));
+            take = __shfl_sync(FULL, take, leader);
+            const int rank = __popc(want & ((1u << lane) - 1u));
+            if (!s.active && !exhausted && rank < take) {
+                const unsigned long long my = base + rank;
                 if (my >= total) {
                     exhausted = true;
                 } else {
@@ -298,49 +336,76 @@ __global__ void __launch_bounds__(BLOCK) k_adaptive(const Batch1D P) {
                 }
             }
         }
-        if (__ballot_sync(FULL, s.active) == 0u) break;
+        const unsigned live = __ballot_sync(FULL, s.active);
+        if (live == 0u) break;
 
         // ---- plan this trip: up to two ranges to run the 25-point rule on ----
         double ra0 = 0., rb0 = 0., ra1 = 0., rb1 = 0.;
         bool has0 = false, has1 = false;
-        double ia = 0., ib = 0., ie = 0., id = 0., center = 0.;
-        int ilv = 0;
         if (s.active) {
             if (QAGP && s.seeding) {
                 // next two break-point windows wide enough to integrate (qagp.rs:102-106)
-                s.w0 = s.w1 = -1;
+                int w0 = -1, w1 = -1;
                 int k = s.seed_k;
-                for (; k < s.nint && s.w1 < 0; ++k) {
+                for (; k < s.nint && w1 < 0; ++k) {
                     const double lo = S.PTS(k), hi = S.PTS(k + 1);
                     if (fabs(hi - lo) < 100. * F64_MIN_POSITIVE) continue;
-                    if (s.w0 < 0) {
-                        s.w0 = k; ra0 = lo; rb0 = hi; has0 = true;
+                    if (w0 < 0) {
+                        w0 = k; ra0 = lo; rb0 = hi; has0 = true;
                     } else {
-                        s.w1 = k; ra1 = lo; rb1 = hi; has1 = true;
+                        w1 = k; ra1 = lo; rb1 = hi; has1 = true;
                     }
                 }
+                s.w0 = w0;
+                s.w1 = w1;
                 s.seed_k = k;
             } else {
                 // bisect the interval with the largest error (qags.rs:122-125, util.rs:151-159)
                 const int wi = s.wi;
-                ia = S.A(wi); ib = S.B(wi); ie = S.E(wi); id = S.D(wi); ilv = S.LV(wi);
-                center = (ia + ib) * 0.5;
-                ra0 = ia; rb0 = center; ra1 = center; rb1 = ib;
+                ra0 = S.A(wi);
+                rb1 = S.B(wi);
+                rb0 = ra1 = (ra0 + rb1) * 0.5;
                 has0 = has1 = true;
             }
         }
 
-        // ---- the hot part: 2 x 25 integrand samples per active lane, warp-converged ----
+        // ---- the hot part: 2 x 25 integrand samples per live integral ----
         QK q0, q1;
         q0.estimate = q0.delta = q0.absvalue = q0.asc = 0.;
         q1 = q0;
-        __syncwarp();
+        if (__popc(live) > COOP_MAX_LIVE) {
+            // throughput mode: every lane walks its own 50 samples, warp-converged
 #pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-            const bool on = hh ? has1 : has0;
-            if (on) {
-                const QK q = qk_rule<12, RuleUnroll<F, 12>::value>(g, hh ? ra1 : ra0, hh ? rb1 : rb0);
-                if (hh) q1 = q; else q0 = q;
+            for (int hh = 0; hh < 2; ++hh) {
+                const bool on = hh ? has1 : has0;
+                if (on) {
+                    const QK q = qk_rule<12, RuleUnroll<F, 12>::value>(g, hh ? ra1 : ra0, hh ? rb1 : rb0);
+                    if (hh) q1 = q; else q0 = q;
+                }
+            }
+        } else {
+            // latency mode (tail of the batch): the warp spreads the 50 samples of each live
+            // integral over its 32 lanes, one live integral after the other
+            unsigned todo = live;
+#pragma unroll 1
+            while (todo) {
+                const int owner = __ffs(todo) - 1;
+                todo &= todo - 1;
+                Wrapped<F> go;
+#pragma unroll
+                for (int k = 0; k < MAX_PARAMS; ++k)
+                    go.f.p[k] = (k < NPARAMS) ? __shfl_sync(FULL, g.f.p[k], owner) : 0.0;
+                go.transform = __shfl_sync(FULL, (int)g.transform, owner) != 0;
+                const bool oh0 = __shfl_sync(FULL, (int)has0, owner) != 0;
+                const bool oh1 = __shfl_sync(FULL, (int)has1, owner) != 0;
+                const double oa0 = __shfl_sync(FULL, ra0, owner), ob0 = __shfl_sync(FULL, rb0, owner);
+                const double oa1 = __shfl_sync(FULL, ra1, owner), ob1 = __shfl_sync(FULL, rb1, owner);
+                QK c0 = q0, c1 = q1;
+                qk25_pair_coop(go, s_xgk, oh0, oa0, ob0, oh1, oa1, ob1, c0, c1);
+                if (lane == owner) {
+                    q0 = c0;
+                    q1 = c1;
+                }
             }
         }
 
@@ -403,8 +468,9 @@ __global__ void __launch_bounds__(BLOCK) k_adaptive(const Batch1D P) {
                     }
                 }
             } else {
-                adaptive_step<QAGP>(S, s, P.tol, P.max_evals, sink, ia, ib, center, ie, id, ilv,
-                                    q0, q1);
+                const int wi = s.wi;  // the bisected interval (untouched since the plan step)
+                adaptive_step<QAGP>(S, s, P.tol, P.max_evals, sink, ra0, rb1, rb0, S.E(wi), S.D(wi),
+                                    S.LV(wi), q0, q1);
             }
         }
     }
@@ -426,6 +492,18 @@ __global__ void __launch_bounds__(BLOCK) k_qk_batch(const Batch1D P, double* out
     out4[3 * P.n + i] = q.asc;
 }
 
+// ---- plain integrand evaluation y[i] = f(x[i]; p_i): the Integrand::apply_to_slice of the
+// reference (single/common.rs:135-137).  Also the micro-kernel on which the per-functor FP64
+// flop counts of the registry are measured with ncu (DADD + DMUL + 2*DFMA per evaluation).
+template <class F, int NPARAMS>
+__global__ void __launch_bounds__(BLOCK) k_eval(const Batch1D P, const double* x, double* y) {
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= P.n) return;
+    F f;
+    load_functor(f, P, i, NPARAMS);
+    y[i] = f(x[i]);
+}
+
 // ---- launch table (one entry per registered functor; defined by GKQ_INSTANTIATE_F1) ----------
 struct Launch1D {
     void (*qags_init17)(const Batch1D&, int grid, cudaStream_t);
@@ -434,6 +512,7 @@ struct Launch1D {
     void (*qagp)(const Batch1D&, int grid, cudaStream_t);
     void (*qk17)(const Batch1D&, double* out4, int grid, cudaStream_t);
     void (*qk25)(const Batch1D&, double* out4, int grid, cudaStream_t);
+    void (*eval)(const Batch1D&, const double* x, double* y, int grid, cudaStream_t);
     int (*occupancy_loop)();   // resident blocks per SM of the persistent kernels
     int (*occupancy_qagp)();
     int (*occupancy_init25)();
@@ -455,10 +534,10 @@ GKQ_F1_LIST(GKQ_DECL_F1)
             k_qags_init<F1<ID>, 12, NP><<<grid, BLOCK, 0, st>>>(P);                                  \
         };                                                                                           \
         L.qags_loop = [](const Batch1D& P, int grid, cudaStream_t st) {                              \
-            k_adaptive<F1<ID>, false, NP><<<grid, BLOCK, 0, st>>>(P);                                \
+            k_adaptive<F1<ID>, false, NP><<<grid, ABLOCK, 0, st>>>(P);                                \
         };                                                                                           \
         L.qagp = [](const Batch1D& P, int grid, cudaStream_t st) {                                   \
-            k_adaptive<F1<ID>, true, NP><<<grid, BLOCK, 0, st>>>(P);                                 \
+            k_adaptive<F1<ID>, true, NP><<<grid, ABLOCK, 0, st>>>(P);                                 \
         };                                                                                           \
         L.qk17 = [](const Batch1D& P, double* o, int grid, cudaStream_t st) {                        \
             k_qk_batch<F1<ID>, 8, NP><<<grid, BLOCK, 0, st>>>(P, o);                                 \
@@ -466,14 +545,17 @@ GKQ_F1_LIST(GKQ_DECL_F1)
         L.qk25 = [](const Batch1D& P, double* o, int grid, cudaStream_t st) {                        \
             k_qk_batch<F1<ID>, 12, NP><<<grid, BLOCK, 0, st>>>(P, o);                                \
         };                                                                                           \
+        L.eval = [](const Batch1D& P, const double* x, double* y, int grid, cudaStream_t st) {       \
+            k_eval<F1<ID>, NP><<<grid, BLOCK, 0, st>>>(P, x, y);                                     \
+        };                                                                                           \
         L.occupancy_loop = []() {                                                                    \
             int nb = 0;                                                                              \
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_adaptive<F1<ID>, false, NP>, BLOCK, 0); \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_adaptive<F1<ID>, false, NP>, ABLOCK, 0); \
             return nb;                                                                               \
         };                                                                                           \
         L.occupancy_qagp = []() {                                                                    \
             int nb = 0;                                                                              \
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_adaptive<F1<ID>, true, NP>, BLOCK, 0); \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_adaptive<F1<ID>, true, NP>, ABLOCK, 0); \
             return nb;                                                                               \
         };                                                                                           \
         L.occupancy_init25 = []() {                                                                  \

@@ -9,7 +9,10 @@ import ctypes as C
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG.parent / "lib" / "libgkquad_b200.so"
+import os
+
+# GKQ_LIB selects an alternative build of the same library (kernel-tuning variants)
+LIB_PATH = Path(os.environ["GKQ_LIB"]) if os.environ.get("GKQ_LIB") else _PKG.parent / "lib" / "libgkquad_b200.so"
 
 GKQ_OK = 0
 ERRORS = {-1: "GKQ_ERR_INVALID_ARGUMENT", -2: "GKQ_ERR_NAN_INPUT", -3: "GKQ_ERR_NO_DEVICE",
@@ -43,6 +46,7 @@ SYMBOLS = [
     "gkq_abi_version", "gkq_config_default", "gkq_create", "gkq_destroy", "gkq_last_error",
     "gkq_functor_count", "gkq_functor_info", "gkq_functor_lookup", "gkq_integrate_batch",
     "gkq_integrate_batch_host", "gkq_integrate2_batch", "gkq_integrate2_batch_host", "gkq_qk_batch",
+    "gkq_functor_eval_batch",
     "gkq_sync", "gkq_get_stats", "gkq_reset_stats", "gkq_set_profiling", "gkq_get_profile",
     "gkq_measure_fp64_peak",
 ]
@@ -80,6 +84,7 @@ def lib():
     L.gkq_integrate2_batch.argtypes = batch2 + [vp]
     L.gkq_integrate2_batch_host.argtypes = batch2
     L.gkq_qk_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int64, dp, dp, C.c_int64, dp, C.c_int64, dp, vp]
+    L.gkq_functor_eval_batch.argtypes = [vp, C.c_int, C.c_int64, dp, dp, C.c_int64, dp, vp]
     L.gkq_sync.argtypes = [vp, vp]
     L.gkq_get_stats.argtypes = [vp, C.POINTER(gkq_stats)]
     L.gkq_reset_stats.argtypes = [vp]

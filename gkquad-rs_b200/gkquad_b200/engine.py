@@ -198,6 +198,23 @@ class Engine:
                                         self._ptr(pp), ps, out.data_ptr(), self._stream()))
         return out
 
+    def eval_batch(self, functor, x, params=None):
+        """y[i] = f(x[i]; params[:, i]) on the device (Integrand::apply_to_slice)."""
+        import torch
+        fid, fname, npar, _ = self.functor(1, functor)
+        dev = f"cuda:{self.device}"
+        xx = x if _is_torch(x) else torch.as_tensor(np.asarray(x, dtype=np.float64), device=dev)
+        n = int(xx.shape[0])
+        pp, ps = None, 0
+        if npar:
+            pp = params if _is_torch(params) else torch.as_tensor(
+                np.ascontiguousarray(np.asarray(params, dtype=np.float64)), device=dev)
+            ps = n if pp.ndim == 2 else 0
+        y = torch.empty(n, dtype=torch.float64, device=dev)
+        self._check(self.L.gkq_functor_eval_batch(self.h, fid, n, xx.data_ptr(), self._ptr(pp), ps,
+                                                  y.data_ptr(), self._stream()))
+        return y
+
     # ---- 2-D ------------------------------------------------------------------------------
     def integrate2_batch(self, functor2, yrange, x0, x1, fparams=None, yparams=None, *, algo=ALGO_AUTO,
                          tol=None, max_evals=100000, points=None, pts_offsets=None, pts_xy=None, n=None):

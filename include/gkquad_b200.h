@@ -187,6 +187,12 @@ int gkq_qk_batch(gkq_handle_t h, int rule, int functor_id, int64_t n, const doub
                  const double* b, int64_t range_stride, const double* params,
                  int64_t param_stride, double* out4, void* stream);
 
+/* replaces: Integrand::apply_to_slice (single/common.rs:135-137): y[i] = f(x[i]; params_i).
+ * Device pointers.  Also the micro-kernel on which the registry's flops_per_eval figures are
+ * measured (ncu: DADD + DMUL + 2*DFMA thread instructions / n). */
+int gkq_functor_eval_batch(gkq_handle_t h, int functor_id, int64_t n, const double* x,
+                           const double* params, int64_t param_stride, double* y, void* stream);
+
 /* ---- stream helpers / accounting --------------------------------------------------------- */
 int gkq_sync(gkq_handle_t h, void* stream);
 
