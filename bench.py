@@ -218,21 +218,17 @@ def main():
     dlt = torch.empty(n, dtype=torch.float64, device=dev)
     nev = torch.empty(n, dtype=torch.int32, device=dev)
     st = torch.empty(n, dtype=torch.int32, device=dev)
-    # gather target (rank-major; un-permuted to block-cyclic positions by the consumer via `idx`)
+    # N > 1: one all-gather of the packed results (24 B / integral) ends every step; the buffer is
+    # rank-major and gkquad_b200.distributed.unpack_global maps it back to global order via `idx`
+    from gkquad_b200 import distributed as D
     if world > 1:
-        # one packed SoA buffer per rank: estimate | delta | (nevals, status) = 24 B / integral
-        packed = torch.empty(3 * n, dtype=torch.float64, device=dev)
         gathered = torch.empty(world * 3 * n, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step():
         eng.integrate_batch(W.functor, W.a, W.b, p_dev, out=(est, dlt, nev, st), **kw)
         if world > 1:
-            packed[:n].copy_(est)
-            packed[n:2 * n].copy_(dlt)
-            packed[2 * n:].view(torch.int32)[:n].copy_(nev)
-            packed[2 * n:].view(torch.int32)[n:].copy_(st)
-            dist.all_gather_into_tensor(gathered, packed)
+            dist.all_gather_into_tensor(gathered, D.pack_results(est, dlt, nev, st, n))
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -255,7 +251,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    launches = eng.stats()["kernel_launches"] + (4 * args.steps if world > 1 else 0)
+    launches = eng.stats()["kernel_launches"]  # our kernels only (torch copies / NCCL not counted)
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     conv_local = torch.tensor([(st == 0).sum().item()], dtype=torch.float64, device=dev)
@@ -288,7 +284,8 @@ def main():
     evals_by_kernel = {}
     if W.algo == "QAGS":
         evals_by_kernel = {"k_qags_init<qk17>": 17 * n, "k_qags_init<qk25>": 25 * n25,
-                           "k_adaptive<QAGS>": int(nev_h.sum()) - 17 * n - 25 * n25}
+                           "k_qags_first": 50 * nloop,
+                           "k_adaptive<QAGS>": int(nev_h.sum()) - 17 * n - 25 * n25 - 50 * nloop}
     else:
         evals_by_kernel = {"k_adaptive<QAGP>": int(nev_h.sum())}
     kernels = []

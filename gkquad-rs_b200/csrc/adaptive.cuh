@@ -101,7 +101,7 @@ GKQ_DEV void ws_push(const Slab& S, Lane& s, double a, double b, double e, doubl
 }
 
 // workspace.rs:107-138 (order[] indexed by value in the swap, restated literally)
-GKQ_DEV void ws_sort_results(const Slab& S, Lane& s) {
+static __device__ __noinline__ void ws_sort_results(const Slab& S, Lane& s) {
     int nint = s.size;
     if (nint == 0) return;
     for (int i = 0; i < nint; ++i) {
@@ -125,7 +125,7 @@ GKQ_DEV void ws_sort_results(const Slab& S, Lane& s) {
 }
 
 // workspace.rs:163-223
-GKQ_DEV void ws_qpsrt(const Slab& S, Lane& s) {
+static __device__ __noinline__ void ws_qpsrt(const Slab& S, Lane& s) {
     const int last = s.size - 1;
     const int limit = s.limit;
     int i_nrmax = s.nrmax;
@@ -193,7 +193,7 @@ GKQ_DEV void ws_update(const Slab& S, Lane& s, double a1, double b1, double e1, 
 }
 
 // workspace.rs:233-259
-GKQ_DEV bool ws_increase_nrmax(const Slab& S, Lane& s) {
+static __device__ __noinline__ bool ws_increase_nrmax(const Slab& S, Lane& s) {
     const int id = s.nrmax;
     const int limit = s.limit;
     const int last = s.size - 1;
@@ -224,7 +224,7 @@ GKQ_DEV void tab_append(const Slab& S, Lane& s, double y) {
     s.tab_n += 1;
 }
 
-GKQ_DEV void tab_qelg(const Slab& S, Lane& s, double& result, double& abserr) {
+static __device__ __noinline__ void tab_qelg(const Slab& S, Lane& s, double& result, double& abserr) {
     const int n = s.tab_n - 1;
     const double current = S.EPS(n);
     const int newelm = n / 2;
@@ -353,7 +353,7 @@ struct LocalSink {
 // Epilogue shared by QAGS (qags.rs:274-310) and QAGP (qagp.rs:338-371): choose between the
 // summed and the extrapolated result, then the divergence test.
 template <class Sink>
-GKQ_DEV void adaptive_epilogue(const Slab& S, Lane& s, Sink& O) {
+__device__ __noinline__ void adaptive_epilogue(const Slab& S, Lane& s, Sink& O) {
     s.active = false;
     uint32_t error = s.error;
     double err_ext = s.err_ext;

@@ -83,7 +83,10 @@ struct gkq_handle_s {
     // per-batch scratch, grown on demand
     size_t cap_n = 0;
     double* abs0 = nullptr;
-    unsigned int *list25 = nullptr, *listLoop = nullptr, *listS = nullptr, *listP = nullptr;
+    unsigned int *list25 = nullptr, *listLoop = nullptr, *listLoop2 = nullptr, *listS = nullptr, *listP = nullptr;
+    double* stage6 = nullptr;           // [6][cap_n]
+    unsigned char* stage_ro1 = nullptr;  // [cap_n]
+    size_t stage6_elems = 0, stage_ro1_elems = 0;
 
     size_t slab_d_elems = 0, slab_w_elems = 0;
     double* slab_d = nullptr;
@@ -195,6 +198,9 @@ int ensure_batch_scratch(gkq_handle_t h, size_t n) {
     if ((rc = re(h->abs0))) return rc;
     if ((rc = re(h->list25))) return rc;
     if ((rc = re(h->listLoop))) return rc;
+    if ((rc = re(h->listLoop2))) return rc;
+    if ((rc = grow(h, h->stage6, h->stage6_elems, 6 * w))) return rc;
+    if ((rc = grow(h, h->stage_ro1, h->stage_ro1_elems, w))) return rc;
     if ((rc = re(h->listS))) return rc;
     if ((rc = re(h->listP))) return rc;
     h->cap_n = w;  // every grow() call allocated >= w elements
@@ -372,6 +378,9 @@ int gkq_destroy(gkq_handle_t h) {
     cudaFree(h->abs0);
     cudaFree(h->list25);
     cudaFree(h->listLoop);
+    cudaFree(h->listLoop2);
+    cudaFree(h->stage6);
+    cudaFree(h->stage_ro1);
     cudaFree(h->listS);
     cudaFree(h->listP);
     cudaFree(h->slab_d);
@@ -428,6 +437,7 @@ int gkq_sync(gkq_handle_t h, void* stream) {
     if (h->ctl_pending) {
         h->stats.last_survivors_qk25 = h->ctl_host->count25;
         h->stats.last_survivors_loop = h->ctl_host->countLoop;
+        h->stats.last_survivors_step2 = h->ctl_host->countLoop2;
         h->ctl_pending = false;
     }
     return GKQ_OK;
@@ -521,6 +531,11 @@ static int run_qags(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, cudaS
     prof_end(h, st);
     if ((rc = launch_check(h, "k_qags_init<qk25>"))) return rc;
 
+    prof_begin(h, "k_qags_first", st);
+    L.qags_first(P, (int)g25, st);
+    prof_end(h, st);
+    if ((rc = launch_check(h, "k_qags_first"))) return rc;
+
     if (h->occ_loop[fid] < 0) h->occ_loop[fid] = L.occupancy_loop();
     const unsigned long long need = (P.max_evals - 17) / 50 + 1;  // qags.rs:98-99, nevals >= 17
     const unsigned long long lim = reserve_cap(P.ws_capacity, need);
@@ -607,6 +622,9 @@ int gkq_integrate_batch(gkq_handle_t h, const gkq_config* cfg, int functor_id, i
     P.abs0 = h->abs0;
     P.list25 = h->list25;
     P.listLoop = h->listLoop;
+    P.listLoop2 = h->listLoop2;
+    P.stage = h->stage6;
+    P.stage_ro1 = h->stage_ro1;
 
     if (h->profiling) prof_clear(h);
     GKQ_CUDA(h, cudaMemsetAsync(h->ctl, 0, sizeof(Control), st));

@@ -41,7 +41,8 @@ struct Control {
     unsigned long long headP;      // queue head of the persistent QAGP kernel
     unsigned long long countP;     // QAGP worklist size when built on the device (AUTO split)
     unsigned long long countS;     // QAGS worklist size when built on the device (AUTO split)
-    unsigned long long pad[2];
+    unsigned long long pad[1];     // pad[0]: largest per-integral point count (CSR batches)
+    unsigned long long countLoop2; // integrals still unfinished after their first bisection step
 };
 
 struct Batch1D {
@@ -63,6 +64,10 @@ struct Batch1D {
     double* abs0;               // [n] absvalue of the initial rule (qags.rs:315-376 returns it)
     unsigned int* list25;       // [n]
     unsigned int* listLoop;     // [n]
+    unsigned int* listLoop2;    // [n] survivors of the first bisection step
+    double* stage;              // [6][n] state parked between k_qags_first and k_adaptive:
+                                //        e1, d1, e2, d2 (the two halves), area, errsum
+    unsigned char* stage_ro1;   // [n] roundoff_type1 counter after the first step
     const unsigned int* worklist;        // optional subset of integrals (AUTO split) or nullptr
     const unsigned long long* worklist_count;  // device count for `worklist`
     SlabGeom slab;
@@ -167,6 +172,78 @@ __global__ void __launch_bounds__(BLOCK) k_qags_init(const Batch1D P) {
     }
 }
 
+// ---- QAGS: the first bisection step of every loop entrant, as a flat kernel ------------------
+// Iteration 1 of the main loop (qags.rs:120-271) works on a one-interval list, so its
+// bookkeeping is closed-form; most smooth integrands converge right here.  Running it
+// thread-per-integral over the compacted worklist keeps the sampling at full occupancy; only
+// the integrals that need a second step go on to the persistent kernel, which resumes them
+// from the state this kernel parks (list = the two halves ordered by error, order = [0, 1],
+// epsilon table = [result0, area], ktmin = 1: what qags.rs leaves behind after iteration 1).
+template <class F, int NPARAMS>
+__global__ void __launch_bounds__(BLOCK) k_qags_first(const Batch1D P) {
+    const long long total = (long long)P.ctl->countLoop;
+    for (long long k = (long long)blockIdx.x * BLOCK + threadIdx.x; k - threadIdx.x % 32 < total;
+         k += (long long)gridDim.x * BLOCK) {
+        bool survive = false;
+        long long i = 0;
+        if (k < total) {
+            i = (long long)P.listLoop[k];
+            Wrapped<F> g;
+            double a, b;
+            load_range(P, i, a, b, g.transform);
+            load_functor(g.f, P, i, NPARAMS);
+            const double est0 = P.out.estimate[i], delta0 = P.out.delta[i];
+            uint32_t nevals = P.out.nevals[i];
+            const unsigned long long max_iters = (P.max_evals - nevals) / 50;
+            if (max_iters >= 1) {  // else: zero trips, result0 already is the answer (qags.rs:274-276)
+                const double center = (a + b) * 0.5;
+                const QK q1 = qk_rule<12, RuleUnroll<F, 12>::value>(g, a, center);
+                const QK q2 = qk_rule<12, RuleUnroll<F, 12>::value>(g, center, b);
+                nevals += 50;
+                if (q1.estimate != q1.estimate || q2.estimate != q2.estimate) {
+                    // break before the update: sum_results() over the one-interval list
+                    write_result(P.out, i, 0.0 + est0, delta0, nevals, ST_NAN);
+                } else {
+                    const double area12 = q1.estimate + q2.estimate;
+                    const double error12 = q1.delta + q2.delta;
+                    double errsum = delta0;
+                    errsum += error12 - delta0;
+                    double area = est0;
+                    area += area12 - est0;
+                    const double tolerance = P.tol.to_abs(fabs(area));
+                    int ro1 = 0;
+                    if (q1.asc != q1.delta && q2.asc != q2.delta) {
+                        if (fabs(est0 - area12) <= 1e-5 * fabs(area12) && error12 >= 0.99 * delta0) ro1 = 1;
+                    }
+                    const uint32_t error = subrange_too_small(a, center, b) ? ST_SUBRANGE_TOO_SMALL : ST_NONE;
+                    // list after ws.update: slot 0 = the half with the larger error (workspace.rs:145-151)
+                    const bool swap = q2.delta > q1.delta;
+                    const double E0 = swap ? q2.estimate : q1.estimate, E1 = swap ? q1.estimate : q2.estimate;
+                    if (errsum <= tolerance) {
+                        const double total_est = (0.0 + est0) - est0 + q1.estimate + q2.estimate;
+                        write_result(P.out, i, total_est, errsum, nevals, error);
+                    } else if (error != ST_NONE || max_iters < 2) {
+                        // `break` after the update (error) or loop exhausted: err_ext is still
+                        // f64::MAX, so the answer is the plain sum of the list (qags.rs:274-276)
+                        write_result(P.out, i, (0.0 + E0) + E1, errsum, nevals, error);
+                    } else {
+                        survive = true;
+                        P.stage[i] = q1.estimate;
+                        P.stage[P.n + i] = q1.delta;
+                        P.stage[2 * P.n + i] = q2.estimate;
+                        P.stage[3 * P.n + i] = q2.delta;
+                        P.stage[4 * P.n + i] = area;
+                        P.stage[5 * P.n + i] = errsum;
+                        P.stage_ro1[i] = (unsigned char)ro1;
+                        P.out.nevals[i] = nevals;
+                    }
+                }
+            }
+        }
+        list_append(survive, (unsigned int)i, P.listLoop2, &P.ctl->countLoop2);
+    }
+}
+
 // ---- QAGP break points (qagp.rs:375-400) ------------------------------------------------------
 // Builds [begin, sorted user points inside [min,max]..., end] into the lane's PTS slots and
 // returns nint = len - 1.  The insertion sort is util.rs:178-211 with a strict comparator in
@@ -232,9 +309,16 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
     if (QAGP)
         total = P.worklist ? *P.worklist_count : (unsigned long long)P.n;
     else
-        total = P.ctl->countLoop;
+        total = P.ctl->countLoop2;
     unsigned long long* head = QAGP ? &P.ctl->headP : &P.ctl->headLoop;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * (ABLOCK / 32);
+    const unsigned long long warp_id = t >> 5;
+    // first fill: queue positions [0, first_span) are owned statically; later refills draw
+    // positions first_span + atomicAdd(head, ..)
+    const unsigned long long share0 = (total + nwarps - 1ull) / nwarps;
+    const bool thin_start = share0 <= (unsigned long long)COOP_MAX_LIVE;
+    const unsigned long long first_span = thin_start ? share0 * nwarps : nwarps * 32ull;
+    bool first_fill = true;
 
     __shared__ Lane s_lanes[ABLOCK];
     Lane& s = s_lanes[threadIdx.x];
@@ -254,56 +338,85 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
         // cooperative latency mode instead of piling up on the few warps that ask first.
         const unsigned want = __ballot_sync(FULL, !s.active && !exhausted);
         if (want) {
-            const int leader = __ffs(want) - 1;
-            unsigned long long base = 0;
-            int take = __popc(want);
-            // (all lanes) number of live integrals this warp already has
-            const int live_now = __popc(__ballot_sync(FULL, s.active));
-            if (lane == leader) {
-                const unsigned long long cur = *(volatile unsigned long long*)head;
-                const unsigned long long remaining = total > cur ? total - cur : 0ull;
-                const unsigned long long share = (remaining + nwarps - 1ull) / nwarps;
-                if (remaining > 0ull && share <= (unsigned long long)COOP_MAX_LIVE) {
-                    int room = (int)share - live_now;
-                    if (room < 1) room = live_now == 0 ? 1 : 0;
-                    if (room < take) take = room;
+            unsigned long long my = ~0ull;
+            bool granted = false;
+            if (first_fill) {
+                // first fill: static assignment, no atomics (every thread owns one slot of the
+                // first T queue positions; short queues are dealt round-robin over the warps)
+                if (thin_start) {
+                    if ((unsigned long long)lane < share0) my = (unsigned long long)lane * nwarps + warp_id;
+                } else {
+                    my = t;
                 }
-                if (take > 0) base = atomicAdd(head, (unsigned long long)take);
+                granted = my != ~0ull;
+                if (!granted) my = total;  // nothing for this lane in the first fill
+            } else {
+                const int leader = __ffs(want) - 1;
+                unsigned long long base = 0;
+                int take = __popc(want);
+                // (all lanes) number of live integrals this warp already has
+                const int live_now = __popc(__ballot_sync(FULL, s.active));
+                if (lane == leader) {
+                    const unsigned long long cur = first_span + *(volatile unsigned long long*)head;
+                    const unsigned long long remaining = total > cur ? total - cur : 0ull;
+                    const unsigned long long share = (remaining + nwarps - 1ull) / nwarps;
+                    if (remaining > 0ull && share <= (unsigned long long)COOP_MAX_LIVE) {
+                        int room = (int)share - live_now;
+                        if (room < 1) room = live_now == 0 ? 1 : 0;
+                        if (room < take) take = room;
+                    }
+                    if (take > 0) base = first_span + atomicAdd(head, (unsigned long long)take);
+                }
+                base = __shfl_sync(FULL, base, leader);
+                take = __shfl_sync(FULL, take, leader);
+                const int rank = __popc(want & ((1u << lane) - 1u));
+                granted = rank < take;
+                my = base + rank;
             }
-            base = __shfl_sync(FULL, base, leader);
-            take = __shfl_sync(FULL, take, leader);
-            const int rank = __popc(want & ((1u << lane) - 1u));
-            if (!s.active && !exhausted && rank < take) {
-                const unsigned long long my = base + rank;
+            if (!s.active && !exhausted && granted) {
                 if (my >= total) {
                     exhausted = true;
                 } else {
                     lane_reset_common(s);
                     double a, b;
                     if (!QAGP) {
-                        // result0 of the initial passes was parked in the outputs (k_qags_init)
-                        s.idx = (long long)P.listLoop[my];
-                        load_range(P, s.idx, a, b, s.transform);
-                        load_functor(g.f, P, s.idx, NPARAMS);
+                        // resume after iteration 1 from what k_qags_first parked
+                        s.idx = (long long)P.listLoop2[my];
+                        const long long i = s.idx;
+                        load_range(P, i, a, b, s.transform);
+                        load_functor(g.f, P, i, NPARAMS);
                         g.transform = s.transform;
-                        s.est0 = P.out.estimate[s.idx];
-                        s.delta0 = P.out.delta[s.idx];
-                        s.abs0 = P.abs0[s.idx];
-                        s.nevals = P.out.nevals[s.idx];
+                        s.est0 = P.out.estimate[i];  // result0 (still parked in the outputs)
+                        s.delta0 = P.out.delta[i];
+                        s.abs0 = P.abs0[i];
+                        s.nevals = P.out.nevals[i];  // nevals of result0 + 50
+                        const uint32_t nev0 = s.nevals - 50u;
                         // ws.reserve((max_evals - nevals) / 50 + 1)   qags.rs:98-99
-                        s.max_iters = (P.max_evals - s.nevals) / 50;
+                        s.max_iters = (P.max_evals - nev0) / 50;
                         s.limit = (int)reserve_cap(P.ws_capacity, s.max_iters + 1);
-                        ws_push(S, s, a, b, s.est0, s.delta0, 0);
+                        const double e1 = P.stage[i], d1 = P.stage[P.n + i];
+                        const double e2 = P.stage[2 * P.n + i], d2 = P.stage[3 * P.n + i];
+                        const double center = (a + b) * 0.5;
+                        if (d2 > d1) {  // workspace.rs:145-151
+                            ws_push(S, s, center, b, e2, d2, 1);
+                            ws_push(S, s, a, center, e1, d1, 1);
+                        } else {
+                            ws_push(S, s, a, center, e1, d1, 1);
+                            ws_push(S, s, center, b, e2, d2, 1);
+                        }
+                        s.maxlevel = 1;
+                        s.area = P.stage[4 * P.n + i];
+                        s.errsum = P.stage[5 * P.n + i];
+                        s.ro1 = (int)P.stage_ro1[i];
                         tab_append(S, s, s.est0);
-                        s.area = s.est0;
-                        s.errsum = s.delta0;
+                        tab_append(S, s, s.area);
+                        s.ktmin = 1;
                         s.res_ext = s.est0;
                         s.err_ext = F64_MAX;
                         s.ertest = 0.;
-                        s.eolr = 0.;
-                        s.iteration = 1;
+                        s.eolr = s.errsum;
+                        s.iteration = 2;
                         s.active = true;
-                        if (s.iteration > s.max_iters) adaptive_epilogue(S, s, sink);
                     } else {
                         s.idx = P.worklist ? (long long)P.worklist[my] : (long long)my;
                         load_range(P, s.idx, a, b, s.transform);
@@ -336,6 +449,7 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
                 }
             }
         }
+        first_fill = false;
         const unsigned live = __ballot_sync(FULL, s.active);
         if (live == 0u) break;
 
@@ -508,6 +622,7 @@ __global__ void __launch_bounds__(BLOCK) k_eval(const Batch1D P, const double* x
 struct Launch1D {
     void (*qags_init17)(const Batch1D&, int grid, cudaStream_t);
     void (*qags_init25)(const Batch1D&, int grid, cudaStream_t);
+    void (*qags_first)(const Batch1D&, int grid, cudaStream_t);
     void (*qags_loop)(const Batch1D&, int grid, cudaStream_t);
     void (*qagp)(const Batch1D&, int grid, cudaStream_t);
     void (*qk17)(const Batch1D&, double* out4, int grid, cudaStream_t);
@@ -532,6 +647,9 @@ GKQ_F1_LIST(GKQ_DECL_F1)
         };                                                                                           \
         L.qags_init25 = [](const Batch1D& P, int grid, cudaStream_t st) {                            \
             k_qags_init<F1<ID>, 12, NP><<<grid, BLOCK, 0, st>>>(P);                                  \
+        };                                                                                           \
+        L.qags_first = [](const Batch1D& P, int grid, cudaStream_t st) {                             \
+            k_qags_first<F1<ID>, NP><<<grid, BLOCK, 0, st>>>(P);                                     \
         };                                                                                           \
         L.qags_loop = [](const Batch1D& P, int grid, cudaStream_t st) {                              \
             k_adaptive<F1<ID>, false, NP><<<grid, ABLOCK, 0, st>>>(P);                                \

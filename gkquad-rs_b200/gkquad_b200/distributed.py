@@ -1,0 +1,71 @@
+"""Multi-GPU plumbing: batches of independent integrals shard statically across the ranks of one
+node (one process per GPU) and only the results are exchanged -- ONE all-gather of 24 bytes per
+integral (estimate f64 | delta f64 | nevals u32, status u32) over NCCL / NVLink.  There is no
+data-path collective during the computation.
+
+torch.distributed is used for the plumbing only; with CPU tensors the same code runs over gloo
+(tests/test_distributed_cpu.py)."""
+from __future__ import annotations
+
+import numpy as np
+
+from .workloads import block_cyclic_shard
+
+BLOCK = 4096
+
+
+def shard_indices(n_total: int, rank: int, world: int, block: int = BLOCK) -> np.ndarray:
+    """Global indices owned by `rank`: block-cyclic, i -> rank (i / block) mod world."""
+    return block_cyclic_shard(n_total, rank, world, block)
+
+
+def shard_sizes(n_total: int, world: int, block: int = BLOCK):
+    return [int(len(block_cyclic_shard(n_total, r, world, block))) for r in range(world)]
+
+
+def pack_results(est, dlt, nev, st, n_pad: int):
+    """Pack one rank's SoA results into a single float64 buffer of 3*n_pad elements
+    (all ranks use the same n_pad = largest shard so that all_gather_into_tensor applies)."""
+    import torch
+    n = int(est.shape[0])
+    buf = torch.zeros(3 * n_pad, dtype=torch.float64, device=est.device)
+    buf[:n] = est
+    buf[n_pad:n_pad + n] = dlt
+    ints = buf[2 * n_pad:].view(torch.int32)
+    ints[:n] = nev.view(torch.int32) if nev.dtype != torch.int32 else nev
+    ints[n_pad:n_pad + n] = st.view(torch.int32) if st.dtype != torch.int32 else st
+    return buf
+
+
+def gather_results(est, dlt, nev, st, n_total: int, group=None, block: int = BLOCK):
+    """All-gather the per-rank results and return (estimate, delta, nevals, status) in GLOBAL
+    integral order on every rank (torch tensors on the input device)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    sizes = shard_sizes(n_total, world, block)
+    n_pad = max(sizes)
+    packed = pack_results(est, dlt, nev, st, n_pad)
+    gathered = torch.empty(world * 3 * n_pad, dtype=torch.float64, device=est.device)
+    dist.all_gather_into_tensor(gathered, packed, group=group)
+    return unpack_global(gathered, n_total, world, n_pad, block)
+
+
+def unpack_global(gathered, n_total: int, world: int, n_pad: int, block: int = BLOCK):
+    """Un-permute the rank-major gather buffer back to global integral order."""
+    import torch
+    dev = gathered.device
+    est = torch.empty(n_total, dtype=torch.float64, device=dev)
+    dlt = torch.empty(n_total, dtype=torch.float64, device=dev)
+    nev = torch.empty(n_total, dtype=torch.int32, device=dev)
+    st = torch.empty(n_total, dtype=torch.int32, device=dev)
+    for r in range(world):
+        idx = torch.as_tensor(shard_indices(n_total, r, world, block), device=dev)
+        m = int(idx.shape[0])
+        base = gathered[r * 3 * n_pad:(r + 1) * 3 * n_pad]
+        est[idx] = base[:m]
+        dlt[idx] = base[n_pad:n_pad + m]
+        ints = base[2 * n_pad:].view(torch.int32)
+        nev[idx] = ints[:m]
+        st[idx] = ints[n_pad:n_pad + m]
+    return est, dlt, nev, st

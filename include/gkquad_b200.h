@@ -203,6 +203,7 @@ typedef struct gkq_stats {
     uint64_t scratch_bytes;     /* device scratch currently owned by the handle            */
     uint64_t last_survivors_qk25;  /* worklist sizes of the last QAGS batch, valid after    */
     uint64_t last_survivors_loop;  /* gkq_sync (read back lazily): -> qk25 pass, -> loop    */
+    uint64_t last_survivors_step2; /* integrals still unfinished after the first bisection  */
 } gkq_stats;
 int gkq_get_stats(gkq_handle_t h, gkq_stats* out);
 int gkq_reset_stats(gkq_handle_t h);
