@@ -280,12 +280,16 @@ def main():
     fl_eval = eng.functor(1, W.functor)[3]
     F_t = 6.0 if not (np.isfinite(W.a) and np.isfinite(W.b)) else 0.0
     w_eval = fl_eval + F_t + 8.0  # W_i = nevals_i * (F_f + F_t + 8)
-    n25, nloop = stats["last_survivors_qk25"], stats["last_survivors_loop"]
+    n25 = stats["last_survivors_qk25"]
+    cl, c2 = stats["last_chain_loop"], stats["last_chain_step2"]
     evals_by_kernel = {}
     if W.algo == "QAGS":
+        rest = int(nev_h.sum()) - 17 * n - 25 * n25 - 50 * (cl[0] + cl[1])
+        tail_share = [c2[k] / max(1, c2[0] + c2[1]) for k in range(2)]
         evals_by_kernel = {"k_qags_init<qk17>": 17 * n, "k_qags_init<qk25>": 25 * n25,
-                           "k_qags_first": 50 * nloop,
-                           "k_adaptive<QAGS>": int(nev_h.sum()) - 17 * n - 25 * n25 - 50 * nloop}
+                           "k_qags_first[0]": 50 * cl[0], "k_qags_first[1]": 50 * cl[1],
+                           "k_adaptive<QAGS>[0]": int(rest * tail_share[0]),
+                           "k_adaptive<QAGS>[1]": int(rest * tail_share[1])}
     else:
         evals_by_kernel = {"k_adaptive<QAGP>": int(nev_h.sum())}
     kernels = []

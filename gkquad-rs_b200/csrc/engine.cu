@@ -2,6 +2,7 @@
 // (include/gkquad_b200.h).  No torch, no oracle, no CPU fallback: without a CUDA device
 // gkq_create fails and nothing can be computed.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(BLOCK) k_split_auto(long long n, const long lo
         unsigned long long other = __shfl_xor_sync(0xffffffffu, m, o);
         m = other > m ? other : m;
     }
-    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(&ctl->pad[0], m);
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(&ctl->max_pts, m);
 }
 
 // FP64 pipe calibration: 8 independent dependent-DFMA chains per thread.
@@ -76,29 +77,42 @@ struct gkq_handle_s {
     std::string err;
     gkq_stats stats{};
 
+    // Two independent scratch contexts: the device entry uses context 0; the host entry alternates
+    // so that the latency-bound tail kernels of one chunk overlap the bulk kernels of the next.
+    struct Scratch {
     Control* ctl = nullptr;       // device
-    Control* ctl_host = nullptr;  // pinned mirror for lazy read-back
-    bool ctl_pending = false;
+        Control* ctl_host = nullptr;  // pinned mirror for lazy read-back
+        bool ctl_pending = false;
 
-    // per-batch scratch, grown on demand
-    size_t cap_n = 0;
-    double* abs0 = nullptr;
-    unsigned int *list25 = nullptr, *listLoop = nullptr, *listLoop2 = nullptr, *listS = nullptr, *listP = nullptr;
-    double* stage6 = nullptr;           // [6][cap_n]
-    unsigned char* stage_ro1 = nullptr;  // [cap_n]
-    size_t stage6_elems = 0, stage_ro1_elems = 0;
+        // per-batch scratch, grown on demand
+        size_t cap_n = 0;
+        double* abs0 = nullptr;
+        unsigned int *list25 = nullptr, *listS = nullptr, *listP = nullptr;
+        unsigned int* listLoop[2] = {nullptr, nullptr};
+        unsigned int* listLoop2[2] = {nullptr, nullptr};
+        // chain 1 of the QAGS pipeline runs on its own stream, forked / joined with events
+        cudaStream_t side = nullptr;
+        cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+        double* stage6 = nullptr;           // [6][cap_n]
+        unsigned char* stage_ro1 = nullptr;  // [cap_n]
+        size_t stage6_elems = 0, stage_ro1_elems = 0;
 
-    size_t slab_d_elems = 0, slab_w_elems = 0;
-    double* slab_d = nullptr;
-    int* slab_w = nullptr;
+        size_t slab_d_elems[2] = {0, 0}, slab_w_elems[2] = {0, 0};
+        double* slab_d[2] = {nullptr, nullptr};
+        int* slab_w[2] = {nullptr, nullptr};
 
-    size_t dev_pts_cap = 0;
-    double* dev_pts = nullptr;     // shared points (device copy)
-    double* host_pts = nullptr;    // pinned staging for the shared points
-    size_t host_pts_cap = 0;
+        size_t dev_pts_cap = 0;
+        double* dev_pts = nullptr;     // shared points (device copy)
+        double* host_pts = nullptr;    // pinned staging for the shared points
+        size_t host_pts_cap = 0;
+        size_t pts_count = 0;
+
+    };
+    Scratch sc[2];
+    int cur = 0;
 
     // host-entry staging (gkq_integrate_batch_host)
-    cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_compute = nullptr, s_compute2 = nullptr, s_out = nullptr;
     size_t stage_bytes = 0;
     char* stage_dev = nullptr;
     size_t stage_pin_bytes = 0;
@@ -182,12 +196,12 @@ int grow(gkq_handle_t h, T*& p, size_t& have, size_t want) {
 }
 
 int ensure_batch_scratch(gkq_handle_t h, size_t n) {
-    if (n <= h->cap_n) return 0;
+    if (n <= h->sc[h->cur].cap_n) return 0;
     size_t dummy;
     size_t w = n + n / 8 + 1024;
     auto re = [&](auto*& p) -> int {
         using T = std::remove_reference_t<decltype(*p)>;
-        size_t have = h->cap_n;
+        size_t have = h->sc[h->cur].cap_n;
         T* q = p;
         dummy = have;
         int rc = grow(h, q, dummy, w);
@@ -195,27 +209,31 @@ int ensure_batch_scratch(gkq_handle_t h, size_t n) {
         return rc;
     };
     int rc;
-    if ((rc = re(h->abs0))) return rc;
-    if ((rc = re(h->list25))) return rc;
-    if ((rc = re(h->listLoop))) return rc;
-    if ((rc = re(h->listLoop2))) return rc;
-    if ((rc = grow(h, h->stage6, h->stage6_elems, 6 * w))) return rc;
-    if ((rc = grow(h, h->stage_ro1, h->stage_ro1_elems, w))) return rc;
-    if ((rc = re(h->listS))) return rc;
-    if ((rc = re(h->listP))) return rc;
-    h->cap_n = w;  // every grow() call allocated >= w elements
+    if ((rc = re(h->sc[h->cur].abs0))) return rc;
+    if ((rc = re(h->sc[h->cur].list25))) return rc;
+    for (int c = 0; c < 2; ++c) {
+        if ((rc = re(h->sc[h->cur].listLoop[c]))) return rc;
+        if ((rc = re(h->sc[h->cur].listLoop2[c]))) return rc;
+    }
+    if ((rc = grow(h, h->sc[h->cur].stage6, h->sc[h->cur].stage6_elems, 6 * w))) return rc;
+    if ((rc = grow(h, h->sc[h->cur].stage_ro1, h->sc[h->cur].stage_ro1_elems, w))) return rc;
+    if ((rc = re(h->sc[h->cur].listS))) return rc;
+    if ((rc = re(h->sc[h->cur].listP))) return rc;
+    h->sc[h->cur].cap_n = w;  // every grow() call allocated >= w elements
     return 0;
 }
 
-// Per-thread slabs for `threads` persistent threads with `cap` interval slots each.
-int ensure_slab(gkq_handle_t h, unsigned long long threads, int cap, int npts_max, SlabGeom& g) {
+// Per-thread slabs for `threads` persistent threads with `cap` interval slots each (one slab
+// per chain of the QAGS pipeline; every other kernel uses slab 0).
+int ensure_slab(gkq_handle_t h, unsigned long long threads, int cap, int npts_max, SlabGeom& g, int which = 0) {
+    gkq_handle_s::Scratch& s = h->sc[h->cur];
     const unsigned long long nd = slab_doubles(cap, npts_max) * threads;
     const unsigned long long nw = slab_ints(cap) * threads;
     int rc;
-    if ((rc = grow(h, h->slab_d, h->slab_d_elems, (size_t)nd))) return rc;
-    if ((rc = grow(h, h->slab_w, h->slab_w_elems, (size_t)nw))) return rc;
-    g.dbase = h->slab_d;
-    g.wbase = h->slab_w;
+    if ((rc = grow(h, s.slab_d[which], s.slab_d_elems[which], (size_t)nd))) return rc;
+    if ((rc = grow(h, s.slab_w[which], s.slab_w_elems[which], (size_t)nw))) return rc;
+    g.dbase = s.slab_d[which];
+    g.wbase = s.slab_w[which];
     g.stride = threads;
     g.cap = cap;
     g.npts_max = npts_max;
@@ -232,20 +250,23 @@ int check_tol(gkq_handle_t h, const gkq_tolerance& t) {
 
 int upload_shared_points(gkq_handle_t h, const double* pts, size_t count, cudaStream_t st) {
     if (count == 0) return 0;
+    gkq_handle_s::Scratch& s = h->sc[h->cur];
+    // unchanged points (the usual case: one Integrator, many batches) stay resident
+    if (s.dev_pts && s.host_pts && s.pts_count == count && memcmp(s.host_pts, pts, count * sizeof(double)) == 0)
+        return 0;
     int rc;
-    if ((rc = grow(h, h->dev_pts, h->dev_pts_cap, count))) return rc;
-    if (count > h->host_pts_cap) {
-        if (h->host_pts) GKQ_CUDA(h, cudaFreeHost(h->host_pts));
-        h->host_pts = nullptr;
-        GKQ_CUDA(h, cudaMallocHost(&h->host_pts, (count + 64) * sizeof(double)));
-        h->host_pts_cap = count + 64;
-    } else {
-        // the previous batch may still be reading the staging buffer
-        GKQ_CUDA(h, cudaStreamSynchronize(st));
+    if ((rc = grow(h, s.dev_pts, s.dev_pts_cap, count))) return rc;
+    // an earlier batch may still be copying out of the pinned staging buffer
+    GKQ_CUDA(h, cudaStreamSynchronize(st));
+    if (count > s.host_pts_cap) {
+        if (s.host_pts) GKQ_CUDA(h, cudaFreeHost(s.host_pts));
+        s.host_pts = nullptr;
+        GKQ_CUDA(h, cudaMallocHost(&s.host_pts, (count + 64) * sizeof(double)));
+        s.host_pts_cap = count + 64;
     }
-    memcpy(h->host_pts, pts, count * sizeof(double));
-    GKQ_CUDA(h, cudaMemcpyAsync(h->dev_pts, h->host_pts, count * sizeof(double),
-                                cudaMemcpyHostToDevice, st));
+    memcpy(s.host_pts, pts, count * sizeof(double));
+    s.pts_count = count;
+    GKQ_CUDA(h, cudaMemcpyAsync(s.dev_pts, s.host_pts, count * sizeof(double), cudaMemcpyHostToDevice, st));
     return 0;
 }
 
@@ -356,15 +377,22 @@ int gkq_create(int device, gkq_handle_t* out) {
     h->total_mem = prop.totalGlobalMem;
     FillL1<0>::go(h);
     FillL2<0>::go(h);
-    if (cudaMalloc(&h->ctl, sizeof(Control)) != cudaSuccess ||
-        cudaMallocHost(&h->ctl_host, sizeof(Control)) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+    bool ok = true;
+    for (int c = 0; c < 2; ++c) {
+        ok = ok && cudaMalloc(&h->sc[c].ctl, sizeof(Control)) == cudaSuccess &&
+             cudaMallocHost(&h->sc[c].ctl_host, sizeof(Control)) == cudaSuccess;
+        if (ok) memset(h->sc[c].ctl_host, 0, sizeof(Control));
+        ok = ok && cudaStreamCreateWithFlags(&h->sc[c].side, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->sc[c].ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->sc[c].ev_join, cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok || cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->s_compute2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess) {
         delete h;
         return fail(nullptr, GKQ_ERR_CUDA, "handle allocation failed");
     }
-    memset(h->ctl_host, 0, sizeof(Control));
     *out = h;
     return GKQ_OK;
 }
@@ -373,26 +401,35 @@ int gkq_destroy(gkq_handle_t h) {
     if (!h) return GKQ_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    cudaFree(h->ctl);
-    cudaFreeHost(h->ctl_host);
-    cudaFree(h->abs0);
-    cudaFree(h->list25);
-    cudaFree(h->listLoop);
-    cudaFree(h->listLoop2);
-    cudaFree(h->stage6);
-    cudaFree(h->stage_ro1);
-    cudaFree(h->listS);
-    cudaFree(h->listP);
-    cudaFree(h->slab_d);
-    cudaFree(h->slab_w);
-    cudaFree(h->dev_pts);
-    cudaFreeHost(h->host_pts);
+    for (int c = 0; c < 2; ++c) {
+        gkq_handle_s::Scratch& s = h->sc[c];
+        cudaFree(s.ctl);
+        cudaFreeHost(s.ctl_host);
+        cudaFree(s.abs0);
+        cudaFree(s.list25);
+        for (int k = 0; k < 2; ++k) {
+            cudaFree(s.listLoop[k]);
+            cudaFree(s.listLoop2[k]);
+            cudaFree(s.slab_d[k]);
+            cudaFree(s.slab_w[k]);
+        }
+        if (s.side) cudaStreamDestroy(s.side);
+        if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+        if (s.ev_join) cudaEventDestroy(s.ev_join);
+        cudaFree(s.stage6);
+        cudaFree(s.stage_ro1);
+        cudaFree(s.listS);
+        cudaFree(s.listP);
+        cudaFree(s.dev_pts);
+        cudaFreeHost(s.host_pts);
+    }
     cudaFree(h->stage_dev);
     cudaFreeHost(h->stage_pin);
     prof_clear(h);
     for (auto ev : h->prof_pool) cudaEventDestroy(ev);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    if (h->s_compute2) cudaStreamDestroy(h->s_compute2);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     delete h;
     return GKQ_OK;
@@ -434,11 +471,17 @@ int gkq_sync(gkq_handle_t h, void* stream) {
     if (!h) return GKQ_ERR_INVALID_ARGUMENT;
     GKQ_CUDA(h, cudaSetDevice(h->device));
     GKQ_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
-    if (h->ctl_pending) {
-        h->stats.last_survivors_qk25 = h->ctl_host->count25;
-        h->stats.last_survivors_loop = h->ctl_host->countLoop;
-        h->stats.last_survivors_step2 = h->ctl_host->countLoop2;
-        h->ctl_pending = false;
+    h->cur = 0;
+    if (h->sc[h->cur].ctl_pending) {
+        h->stats.last_survivors_qk25 = h->sc[h->cur].ctl_host->count25;
+        const Control* c = h->sc[h->cur].ctl_host;
+        h->stats.last_survivors_loop = c->chain[0].countLoop + c->chain[1].countLoop;
+        h->stats.last_survivors_step2 = c->chain[0].countLoop2 + c->chain[1].countLoop2;
+        for (int k = 0; k < 2; ++k) {
+            h->stats.last_chain_loop[k] = c->chain[k].countLoop;
+            h->stats.last_chain_step2[k] = c->chain[k].countLoop2;
+        }
+        h->sc[h->cur].ctl_pending = false;
     }
     return GKQ_OK;
 }
@@ -490,7 +533,7 @@ int gkq_measure_fp64_peak(gkq_handle_t h, int repeats, double* flops_per_s, doub
     double best = 1e30;
     for (int r = 0; r < repeats + 1; ++r) {  // first trip is a warm-up
         GKQ_CUDA(h, cudaEventRecord(e0, 0));
-        k_dfma_peak<<<grid, BLOCK>>>((double*)h->ctl, iters, 1.0 + r);
+        k_dfma_peak<<<grid, BLOCK>>>((double*)h->sc[h->cur].ctl, iters, 1.0 + r);
         GKQ_CUDA(h, cudaEventRecord(e1, 0));
         GKQ_CUDA(h, cudaEventSynchronize(e1));
         float ms = 0;
@@ -511,6 +554,7 @@ int gkq_measure_fp64_peak(gkq_handle_t h, int repeats, double* flops_per_s, doub
 static int run_qags(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, cudaStream_t st) {
     // P.worklist / worklist_count may select a subset (AUTO split); n is the upper bound
     int rc;
+    gkq_handle_s::Scratch& S = h->sc[h->cur];
     if (P.max_evals < 17) {  // qags.rs:86-88 -- only reachable without a worklist split
         const int grid = (int)((P.n + BLOCK - 1) / BLOCK);
         if (P.worklist) return fail(h, GKQ_ERR_UNSUPPORTED, "max_evals < 17 with a CSR AUTO batch");
@@ -526,31 +570,47 @@ static int run_qags(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, cudaS
     if (h->occ_init25[fid] < 0) h->occ_init25[fid] = L.occupancy_init25();
     long long g25 = (long long)h->sm_count * (h->occ_init25[fid] > 0 ? h->occ_init25[fid] : 1);
     if (g25 > nblocks) g25 = nblocks;
-    prof_begin(h, "k_qags_init<qk25>", st);
-    L.qags_init25(P, (int)g25, st);
-    prof_end(h, st);
-    if ((rc = launch_check(h, "k_qags_init<qk25>"))) return rc;
 
-    prof_begin(h, "k_qags_first", st);
-    L.qags_first(P, (int)g25, st);
-    prof_end(h, st);
-    if ((rc = launch_check(h, "k_qags_first"))) return rc;
-
+    // slabs of the two persistent kernels
     if (h->occ_loop[fid] < 0) h->occ_loop[fid] = L.occupancy_loop();
     const unsigned long long need = (P.max_evals - 17) / 50 + 1;  // qags.rs:98-99, nevals >= 17
-    const unsigned long long lim = reserve_cap(P.ws_capacity, need);
     if (need > (1ull << 26)) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
     const int cap = (int)need;  // list length never exceeds the reserve request
-    (void)lim;
     int grid = persistent_grid(h, h->occ_loop[fid], cap, 0, ABLOCK);
     if (grid < 1) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
     const long long ablocks = (P.n + ABLOCK - 1) / ABLOCK;
     if ((long long)grid > ablocks) grid = (int)ablocks;
-    if ((rc = ensure_slab(h, (unsigned long long)grid * ABLOCK, cap, 0, P.slab))) return rc;
-    prof_begin(h, "k_adaptive<QAGS>", st);
-    L.qags_loop(P, grid, st);
-    prof_end(h, st);
-    return launch_check(h, "k_adaptive<QAGS>");
+    SlabGeom slab[2];
+    for (int c = 0; c < 2; ++c)
+        if ((rc = ensure_slab(h, (unsigned long long)grid * ABLOCK, cap, 0, slab[c], c))) return rc;
+
+    // fork: chain 1 (qk25 pass and what follows it) runs on the side stream
+    GKQ_CUDA(h, cudaEventRecord(S.ev_fork, st));
+    GKQ_CUDA(h, cudaStreamWaitEvent(S.side, S.ev_fork, 0));
+    for (int c = 0; c < 2; ++c) {
+        cudaStream_t cs = c == 0 ? st : S.side;
+        Batch1D Q = P;
+        Q.chain = c;
+        Q.slab = slab[c];
+        if (c == 1) {
+            prof_begin(h, "k_qags_init<qk25>", cs);
+            L.qags_init25(Q, (int)g25, cs);
+            prof_end(h, cs);
+            if ((rc = launch_check(h, "k_qags_init<qk25>"))) return rc;
+        }
+        prof_begin(h, c == 0 ? "k_qags_first[0]" : "k_qags_first[1]", cs);
+        L.qags_first(Q, (int)g25, cs);
+        prof_end(h, cs);
+        if ((rc = launch_check(h, "k_qags_first"))) return rc;
+        prof_begin(h, c == 0 ? "k_adaptive<QAGS>[0]" : "k_adaptive<QAGS>[1]", cs);
+        L.qags_loop(Q, grid, cs);
+        prof_end(h, cs);
+        if ((rc = launch_check(h, "k_adaptive<QAGS>"))) return rc;
+    }
+    // join
+    GKQ_CUDA(h, cudaEventRecord(S.ev_join, S.side));
+    GKQ_CUDA(h, cudaStreamWaitEvent(st, S.ev_join, 0));
+    return GKQ_OK;
 }
 
 static int run_qagp(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, int npts_max,
@@ -572,11 +632,29 @@ static int run_qagp(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, int n
     return launch_check(h, "k_adaptive<QAGP>");
 }
 
+// The batch call proper, on scratch context h->cur.
+static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
+                               const double* a, const double* b, int64_t range_stride,
+                               const double* params, int64_t param_stride, const int64_t* pts_offsets,
+                               const double* pts, double* out_estimate, double* out_delta,
+                               uint32_t* out_nevals, uint32_t* out_status, void* stream);
+
 int gkq_integrate_batch(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
                         const double* a, const double* b, int64_t range_stride,
                         const double* params, int64_t param_stride, const int64_t* pts_offsets,
                         const double* pts, double* out_estimate, double* out_delta,
                         uint32_t* out_nevals, uint32_t* out_status, void* stream) {
+    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
+    h->cur = 0;
+    return integrate_batch_ctx(h, cfg, functor_id, n, a, b, range_stride, params, param_stride,
+                               pts_offsets, pts, out_estimate, out_delta, out_nevals, out_status, stream);
+}
+
+static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
+                               const double* a, const double* b, int64_t range_stride,
+                               const double* params, int64_t param_stride, const int64_t* pts_offsets,
+                               const double* pts, double* out_estimate, double* out_delta,
+                               uint32_t* out_nevals, uint32_t* out_status, void* stream) {
     if (!h) return GKQ_ERR_INVALID_ARGUMENT;
     if (!cfg) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "cfg is NULL");
     if (functor_id < 0 || functor_id >= F1_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown functor id");
@@ -618,16 +696,18 @@ int gkq_integrate_batch(gkq_handle_t h, const gkq_config* cfg, int functor_id, i
     P.out.delta = out_delta;
     P.out.nevals = out_nevals;
     P.out.status = out_status;
-    P.ctl = h->ctl;
-    P.abs0 = h->abs0;
-    P.list25 = h->list25;
-    P.listLoop = h->listLoop;
-    P.listLoop2 = h->listLoop2;
-    P.stage = h->stage6;
-    P.stage_ro1 = h->stage_ro1;
+    P.ctl = h->sc[h->cur].ctl;
+    P.abs0 = h->sc[h->cur].abs0;
+    P.list25 = h->sc[h->cur].list25;
+    for (int c = 0; c < 2; ++c) {
+        P.listLoop[c] = h->sc[h->cur].listLoop[c];
+        P.listLoop2[c] = h->sc[h->cur].listLoop2[c];
+    }
+    P.stage = h->sc[h->cur].stage6;
+    P.stage_ro1 = h->sc[h->cur].stage_ro1;
 
     if (h->profiling) prof_clear(h);
-    GKQ_CUDA(h, cudaMemsetAsync(h->ctl, 0, sizeof(Control), st));
+    GKQ_CUDA(h, cudaMemsetAsync(h->sc[h->cur].ctl, 0, sizeof(Control), st));
     const Launch1D& L = h->l1[functor_id];
     h->stats.batches += 1;
     h->stats.integrals += (uint64_t)n;
@@ -638,7 +718,7 @@ int gkq_integrate_batch(gkq_handle_t h, const gkq_config* cfg, int functor_id, i
             rc = run_qags(h, L, functor_id, P, st);
         } else {
             if ((rc = upload_shared_points(h, cfg->points, (size_t)cfg->npoints, st))) return rc;
-            P.pts = h->dev_pts;
+            P.pts = h->sc[h->cur].dev_pts;
             P.npts_shared = (int)cfg->npoints;
             rc = run_qagp(h, L, functor_id, P, (int)cfg->npoints, st);
         }
@@ -648,30 +728,32 @@ int gkq_integrate_batch(gkq_handle_t h, const gkq_config* cfg, int functor_id, i
         // CSR points: split for AUTO and find the largest point count (one small sync)
         const int grid = (int)((n + BLOCK - 1) / BLOCK);
         const int mode = cfg->algo == GKQ_ALGO_AUTO ? 0 : 1;
-        k_split_auto<<<grid, BLOCK, 0, st>>>(n, (const long long*)pts_offsets, h->listS, h->listP, h->ctl, mode);
+        k_split_auto<<<grid, BLOCK, 0, st>>>(n, (const long long*)pts_offsets, h->sc[h->cur].listS, h->sc[h->cur].listP, h->sc[h->cur].ctl, mode);
         if ((rc = launch_check(h, "k_split_auto"))) return rc;
-        GKQ_CUDA(h, cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
+        GKQ_CUDA(h, cudaMemcpyAsync(h->sc[h->cur].ctl_host, h->sc[h->cur].ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
         GKQ_CUDA(h, cudaStreamSynchronize(st));
-        const int npts_max = (int)h->ctl_host->pad[0];
+        const int npts_max = (int)h->sc[h->cur].ctl_host->max_pts;
         P.pts_offsets = (const long long*)pts_offsets;
         P.pts = pts;
         if (mode == 0) {
             Batch1D PS = P;
-            PS.worklist = h->listS;
-            PS.worklist_count = &h->ctl->countS;
-            if (h->ctl_host->countS > 0 && (rc = run_qags(h, L, functor_id, PS, st))) return rc;
+            PS.worklist = h->sc[h->cur].listS;
+            PS.worklist_count = &h->sc[h->cur].ctl->countS;
+            if (h->sc[h->cur].ctl_host->countS > 0 && (rc = run_qags(h, L, functor_id, PS, st))) return rc;
             Batch1D PP = P;
-            PP.worklist = h->listP;
-            PP.worklist_count = &h->ctl->countP;
-            if (h->ctl_host->countP > 0) rc = run_qagp(h, L, functor_id, PP, npts_max, st);
+            PP.worklist = h->sc[h->cur].listP;
+            PP.worklist_count = &h->sc[h->cur].ctl->countP;
+            if (h->sc[h->cur].ctl_host->countP > 0) rc = run_qagp(h, L, functor_id, PP, npts_max, st);
         } else {
             rc = run_qagp(h, L, functor_id, P, npts_max, st);
         }
     }
     if (rc) return rc;
-    // lazy read-back of the worklist sizes for gkq_get_stats
-    GKQ_CUDA(h, cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
-    h->ctl_pending = true;
+    // worklist sizes for gkq_get_stats: read back only in profiling mode (keeps the hot call lean)
+    if (h->profiling) {
+        GKQ_CUDA(h, cudaMemcpyAsync(h->sc[h->cur].ctl_host, h->sc[h->cur].ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
+        h->sc[h->cur].ctl_pending = true;
+    }
     return GKQ_OK;
 }
 
@@ -719,7 +801,9 @@ int gkq_functor_eval_batch(gkq_handle_t h, int functor_id, int64_t n, const doub
     return launch_check(h, "k_eval");
 }
 
-// Host-pointer entry: chunked, double-buffered H2D -> kernels -> D2H pipeline.
+// Host-pointer entry: chunked H2D -> kernels -> D2H pipeline.  Chunks alternate between the two
+// scratch contexts / compute streams so that the latency-bound tail kernels of one chunk overlap
+// the bulk kernels of the next; copies run on their own streams in both directions at once.
 int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
                              const double* a, const double* b, int64_t range_stride,
                              const double* params, int64_t param_stride,
@@ -738,19 +822,26 @@ int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_
     if (np > 0 && !params) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "params is NULL");
     const int np_batch = param_stride ? np : 0;  // per-integral parameter rows
 
-    // device staging layout for one chunk of C integrals (two buffers, ping-pong):
+    // device staging for one chunk of C integrals (ring of NBUF buffers):
     //   a[C] b[C] (when per-integral) | params[np][C] | est[C] delta[C] nevals[C] status[C]
-    const int64_t C = n < (1 << 18) ? n : (1 << 18);
+    constexpr int NBUF = 4;
+    int64_t CH = 1 << 17;
+    if (const char* env = getenv("GKQ_HOST_CHUNK")) {  // tuning knob (integrals per pipeline chunk)
+        long long v = atoll(env);
+        if (v >= 1024) CH = v;
+    }
+    const int64_t C = n < CH ? n : CH;
     const size_t in_doubles = (size_t)((range_stride ? 2 : 0) + np_batch) * (size_t)C;
-    const size_t chunk_bytes = in_doubles * 8 + (size_t)C * (8 + 8 + 4 + 4) + 256;
+    const size_t chunk_bytes = ((in_doubles * 8 + (size_t)C * (8 + 8 + 4 + 4) + 255) / 256) * 256;
     const size_t fixed_bytes = 64 * 8;  // shared range / shared params
     int rc;
     {
-        size_t want = 2 * chunk_bytes + fixed_bytes;
+        size_t want = NBUF * chunk_bytes + fixed_bytes;
         if (want > h->stage_bytes) {
             if (h->stage_dev) GKQ_CUDA(h, cudaFree(h->stage_dev));
             h->stage_dev = nullptr;
             h->stats.scratch_bytes -= h->stage_bytes;
+            h->stage_bytes = 0;
             GKQ_CUDA(h, cudaMalloc(&h->stage_dev, want));
             h->stage_bytes = want;
             h->stats.scratch_bytes += want;
@@ -766,11 +857,11 @@ int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_
     }
     if (!param_stride)
         for (int k = 0; k < np; ++k) fixed_host[2 + k] = params[k];
-    GKQ_CUDA(h, cudaMemcpyAsync(d_fixed, fixed_host, sizeof fixed_host, cudaMemcpyHostToDevice, h->s_compute));
-    GKQ_CUDA(h, cudaStreamSynchronize(h->s_compute));  // fixed_host is a stack buffer
+    GKQ_CUDA(h, cudaMemcpyAsync(d_fixed, fixed_host, sizeof fixed_host, cudaMemcpyHostToDevice, h->s_in));
+    GKQ_CUDA(h, cudaStreamSynchronize(h->s_in));  // fixed_host is a stack buffer
 
-    cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
-    for (int k = 0; k < 2; ++k) {
+    cudaEvent_t ev_in[NBUF], ev_done[NBUF], ev_out[NBUF];
+    for (int k = 0; k < NBUF; ++k) {
         GKQ_CUDA(h, cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
         GKQ_CUDA(h, cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
         GKQ_CUDA(h, cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
@@ -779,7 +870,9 @@ int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_
     int64_t chunk_idx = 0;
     for (int64_t off = 0; off < n && rc == GKQ_OK; off += C, ++chunk_idx) {
         const int64_t m = (n - off) < C ? (n - off) : C;
-        const int buf = (int)(chunk_idx & 1);
+        const int buf = (int)(chunk_idx % NBUF);
+        const int ctx = (int)(chunk_idx & 1);
+        cudaStream_t sc = ctx ? h->s_compute2 : h->s_compute;
         char* base = h->stage_dev + fixed_bytes + (size_t)buf * chunk_bytes;
         double* d_in = (double*)base;
         double* d_a = range_stride ? d_in : d_fixed;
@@ -790,8 +883,8 @@ int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_
         uint32_t* d_nev = (uint32_t*)(d_dlt + C);
         uint32_t* d_st = d_nev + C;
 
-        // the buffer is free once the D2H copies of chunk_idx-2 have completed
-        if (chunk_idx >= 2) GKQ_CUDA(h, cudaStreamWaitEvent(h->s_in, ev_out[buf], 0));
+        // the staging buffer is free once the D2H copies of chunk_idx - NBUF have completed
+        if (chunk_idx >= NBUF) GKQ_CUDA(h, cudaStreamWaitEvent(h->s_in, ev_out[buf], 0));
         if (range_stride) {
             GKQ_CUDA(h, cudaMemcpyAsync(d_a, a + off, (size_t)m * 8, cudaMemcpyHostToDevice, h->s_in));
             GKQ_CUDA(h, cudaMemcpyAsync(d_b, b + off, (size_t)m * 8, cudaMemcpyHostToDevice, h->s_in));
@@ -801,12 +894,12 @@ int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_
                                         (size_t)m * 8, cudaMemcpyHostToDevice, h->s_in));
         GKQ_CUDA(h, cudaEventRecord(ev_in[buf], h->s_in));
 
-        GKQ_CUDA(h, cudaStreamWaitEvent(h->s_compute, ev_in[buf], 0));
-        rc = gkq_integrate_batch(h, cfg, functor_id, m, d_a, d_b, range_stride, d_par,
-                                 param_stride ? C : 0, nullptr, nullptr, d_est, d_dlt, d_nev, d_st,
-                                 h->s_compute);
+        GKQ_CUDA(h, cudaStreamWaitEvent(sc, ev_in[buf], 0));
+        h->cur = ctx;
+        rc = integrate_batch_ctx(h, cfg, functor_id, m, d_a, d_b, range_stride, d_par,
+                                 param_stride ? C : 0, nullptr, nullptr, d_est, d_dlt, d_nev, d_st, sc);
         if (rc) break;
-        GKQ_CUDA(h, cudaEventRecord(ev_done[buf], h->s_compute));
+        GKQ_CUDA(h, cudaEventRecord(ev_done[buf], sc));
 
         GKQ_CUDA(h, cudaStreamWaitEvent(h->s_out, ev_done[buf], 0));
         GKQ_CUDA(h, cudaMemcpyAsync(out_estimate + off, d_est, (size_t)m * 8, cudaMemcpyDeviceToHost, h->s_out));
@@ -817,17 +910,17 @@ int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_
     }
     cudaError_t e1 = cudaStreamSynchronize(h->s_in);
     cudaError_t e2 = cudaStreamSynchronize(h->s_compute);
+    cudaError_t e4 = cudaStreamSynchronize(h->s_compute2);
     cudaError_t e3 = cudaStreamSynchronize(h->s_out);
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < NBUF; ++k) {
         cudaEventDestroy(ev_in[k]);
         cudaEventDestroy(ev_done[k]);
         cudaEventDestroy(ev_out[k]);
     }
+    h->cur = 0;
     if (rc) return rc;
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
-        return fail(h, GKQ_ERR_CUDA, std::string("host pipeline failed: ") +
-                                         cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
-    gkq_sync(h, h->s_compute);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess)
+        return fail(h, GKQ_ERR_CUDA, "host pipeline failed: a stream reported an error");
     return GKQ_OK;
 }
 
@@ -861,6 +954,7 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
 
     GKQ_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
+    h->cur = 0;
     if ((rc = ensure_batch_scratch(h, (size_t)n))) return rc;
 
     Batch2D P;
@@ -883,9 +977,9 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
     P.out.delta = out_delta;
     P.out.nevals = out_nevals;
     P.out.status = out_status;
-    P.ctl = h->ctl;
+    P.ctl = h->sc[h->cur].ctl;
     if (h->profiling) prof_clear(h);
-    GKQ_CUDA(h, cudaMemsetAsync(h->ctl, 0, sizeof(Control), st));
+    GKQ_CUDA(h, cudaMemsetAsync(h->sc[h->cur].ctl, 0, sizeof(Control), st));
     h->stats.batches += 1;
     h->stats.integrals += (uint64_t)n;
 
@@ -900,7 +994,7 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
             P.npts = npts_max;
             if (npts_max > 0) {
                 if ((rc = upload_shared_points(h, cfg->points, (size_t)(2 * npts_max), st))) return rc;
-                P.pts_xy = h->dev_pts;
+                P.pts_xy = h->sc[h->cur].dev_pts;
             }
         }
     } else if (cfg->algo == GKQ_ALGO_QAGS) {
@@ -908,17 +1002,17 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
     } else {
         const int grid = (int)((n + BLOCK - 1) / BLOCK);
         const int mode = cfg->algo == GKQ_ALGO_AUTO ? 0 : 1;
-        k_split_auto<<<grid, BLOCK, 0, st>>>(n, (const long long*)pts_offsets, h->listS, h->listP, h->ctl, mode);
+        k_split_auto<<<grid, BLOCK, 0, st>>>(n, (const long long*)pts_offsets, h->sc[h->cur].listS, h->sc[h->cur].listP, h->sc[h->cur].ctl, mode);
         if ((rc = launch_check(h, "k_split_auto"))) return rc;
-        GKQ_CUDA(h, cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
+        GKQ_CUDA(h, cudaMemcpyAsync(h->sc[h->cur].ctl_host, h->sc[h->cur].ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
         GKQ_CUDA(h, cudaStreamSynchronize(st));
-        npts_max = (int)h->ctl_host->pad[0];
+        npts_max = (int)h->sc[h->cur].ctl_host->max_pts;
         P.pts_offsets = (const long long*)pts_offsets;
         P.pts_xy = pts_xy;
         if (mode == 0) {
             split = true;
-            run_s = h->ctl_host->countS > 0;
-            run_p = h->ctl_host->countP > 0;
+            run_s = h->sc[h->cur].ctl_host->countS > 0;
+            run_p = h->sc[h->cur].ctl_host->countP > 0;
         } else {
             run_p = true;
         }
@@ -935,8 +1029,8 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
             Q.npts_max = 0;
         }
         if (split) {
-            Q.worklist = alg == 0 ? h->listS : h->listP;
-            Q.worklist_count = alg == 0 ? &h->ctl->countS : &h->ctl->countP;
+            Q.worklist = alg == 0 ? h->sc[h->cur].listS : h->sc[h->cur].listP;
+            Q.worklist_count = alg == 0 ? &h->sc[h->cur].ctl->countS : &h->sc[h->cur].ctl->countP;
         }
         const Launch2D& L = h->l2[functor2_id];
         if (h->occ_2d[functor2_id][alg] < 0) h->occ_2d[functor2_id][alg] = L.occupancy[alg]();

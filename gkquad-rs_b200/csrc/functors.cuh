@@ -12,6 +12,7 @@
 // (/root/reference/gkquad/benches/*.rs, tests/common/functions.rs).
 #pragma once
 #include "gk_common.cuh"
+#include "gk_math.cuh"
 
 namespace gkq {
 
@@ -30,37 +31,48 @@ struct FunctorInfo {
 enum F1Id : int {
     F1_SQUARE = 0, F1_RECIP_P, F1_LORENTZ_P, F1_EXPCOS_P, F1_GAUSS_P, F1_ABSPOW_P, F1_LOGABS_P,
     F1_F1, F1_F2, F1_F3, F1_F4, F1_F5, F1_F6, F1_EXP_P, F1_SQRT_SHIFT_P, F1_INV_ABS_SHIFT_P,
-    F1_COS_P, F1_COUNT
+    F1_COS_P, F1_SIN_P, F1_COUNT
 };
 
 // HEAVY = body calls transcendental libdevice routines: the rule loop is then only partly
 // unrolled to keep the instruction footprint inside the instruction cache.
 template <int ID> struct F1;
-#define GKQ_F1(ID, HEAVY_, BODY)                                   \
-    template <> struct F1<ID> {                                    \
-        static constexpr bool HEAVY = HEAVY_;                      \
-        double p[MAX_PARAMS];                                      \
-        GKQ_DEV double operator()(double x) const { BODY }         \
+// BODY computes f(x) with the math policy `m` (m.exp, m.cos, m.sin, m.log, m.pow):
+//   eval(x, FastMath&)  branch-free sample; clears m.ok when an argument leaves the fast range
+//   operator()(x)       always-valid sample (SafeMath)
+#define GKQ_F1(ID, HEAVY_, BODY)                                                 \
+    template <> struct F1<ID> {                                                  \
+        static constexpr bool HEAVY = HEAVY_;                                    \
+        double p[MAX_PARAMS];                                                    \
+        template <class M> GKQ_DEV double eval(double x, M& m) const {           \
+            (void)m;                                                             \
+            BODY                                                                 \
+        }                                                                        \
+        GKQ_DEV double operator()(double x) const {                              \
+            SafeMath m;                                                          \
+            return eval(x, m);                                                   \
+        }                                                                        \
     };
 GKQ_F1(F1_SQUARE, false, return x * x;)                                   // benches/single.rs:11
 GKQ_F1(F1_RECIP_P, false, return p[0] / x;)                               // benches/single.rs:20
 GKQ_F1(F1_LORENTZ_P, false, return 1.0 / (1.0 + p[0] * (x * x));)         // benches/single.rs:32
-GKQ_F1(F1_EXPCOS_P, true, return exp(-p[0] * x) * cos(p[1] * x);)         // S1 / S3
-GKQ_F1(F1_GAUSS_P, true, return exp(-p[0] * (x * x));)                    // I2
-GKQ_F1(F1_ABSPOW_P, true, return pow(fabs(x - p[0]), -p[1]);)             // P1
-GKQ_F1(F1_LOGABS_P, true, return log(fabs(x - p[0]));)                    // P2
-GKQ_F1(F1_F1, true, return pow(x, 2.6) * log(1. / x);)                    // functions.rs:3-5
-GKQ_F1(F1_F2, true, return pow(x, -0.9) * log(1. / x);)                   // functions.rs:8-10
-GKQ_F1(F1_F3, true, return cos(2.4622888266898326 * sin(x));)             // functions.rs:13-15 (2^1.3)
-GKQ_F1(F1_F4, true, return log(1. / x);)                                  // functions.rs:17-19
+GKQ_F1(F1_EXPCOS_P, true, return m.exp(-p[0] * x) * m.cos(p[1] * x);)         // S1 / S3
+GKQ_F1(F1_GAUSS_P, true, return m.exp(-p[0] * (x * x));)                    // I2
+GKQ_F1(F1_ABSPOW_P, true, return m.pow(fabs(x - p[0]), -p[1]);)             // P1
+GKQ_F1(F1_LOGABS_P, true, return m.log(fabs(x - p[0]));)                    // P2
+GKQ_F1(F1_F1, true, return m.pow(x, 2.6) * m.log(1. / x);)                    // functions.rs:3-5
+GKQ_F1(F1_F2, true, return m.pow(x, -0.9) * m.log(1. / x);)                   // functions.rs:8-10
+GKQ_F1(F1_F3, true, return m.cos(2.4622888266898326 * m.sin(x));)             // functions.rs:13-15 (2^1.3)
+GKQ_F1(F1_F4, true, return m.log(1. / x);)                                  // functions.rs:17-19
 GKQ_F1(F1_F5, true, double x2 = x * x;
-       return x2 * x * log(fabs((x2 - 1.) * (x2 - 2.)));)                 // functions.rs:22-25
+       return x2 * x * m.log(fabs((x2 - 1.) * (x2 - 2.)));)                 // functions.rs:22-25
 GKQ_F1(F1_F6, false, double x2 = x * x; double x3 = x2 * x;
        return 1.0 / (x3 - x2 + x - 1.);)                                  // functions.rs:27-31
-GKQ_F1(F1_EXP_P, true, return exp(p[0] * x);)
+GKQ_F1(F1_EXP_P, true, return m.exp(p[0] * x);)
 GKQ_F1(F1_SQRT_SHIFT_P, false, return sqrt(x - p[0]);)
 GKQ_F1(F1_INV_ABS_SHIFT_P, false, return 1.0 / fabs(x - p[0]);)
-GKQ_F1(F1_COS_P, true, return cos(p[0] * x);)
+GKQ_F1(F1_COS_P, true, return m.cos(p[0] * x);)
+GKQ_F1(F1_SIN_P, true, return m.sin(p[0] * x);)
 #undef GKQ_F1
 
 // ---- 2-D ------------------------------------------------------------------------------
@@ -69,18 +81,25 @@ enum F2Id : int {
     F2_D1_P, F2_COUNT
 };
 template <int ID> struct F2;
-#define GKQ_F2(ID, HEAVY_, BODY)                                          \
-    template <> struct F2<ID> {                                           \
-        static constexpr bool HEAVY = HEAVY_;                             \
-        double p[MAX_PARAMS];                                             \
-        GKQ_DEV double operator()(double x, double y) const { BODY }      \
+#define GKQ_F2(ID, HEAVY_, BODY)                                                      \
+    template <> struct F2<ID> {                                                       \
+        static constexpr bool HEAVY = HEAVY_;                                         \
+        double p[MAX_PARAMS];                                                         \
+        template <class M> GKQ_DEV double eval(double x, double y, M& m) const {      \
+            (void)m;                                                                  \
+            BODY                                                                      \
+        }                                                                             \
+        GKQ_DEV double operator()(double x, double y) const {                         \
+            SafeMath m;                                                               \
+            return eval(x, y, m);                                                     \
+        }                                                                             \
     };
 GKQ_F2(F2_XY, false, return x * y;)                                       // benches/double.rs:10
 GKQ_F2(F2_RECIP_XY_P, false, return p[0] / (x * y);)                      // benches/double.rs:19
 GKQ_F2(F2_RSQRT3, false, double denom = 1.0 + x * x + y * y;
        return 1.0 / (denom * sqrt(denom));)                               // benches/double.rs:31-33
 GKQ_F2(F2_G1, false, return 1.0 - x * y;)                                 // functions.rs:37-39
-GKQ_F2(F2_G2, true, return exp(y / x);)                                   // functions.rs:41-43
+GKQ_F2(F2_G2, true, return m.exp(y / x);)                                   // functions.rs:41-43
 GKQ_F2(F2_G3, false, return sqrt(0.25 - x * x - y * y);)                  // functions.rs:45-47
 GKQ_F2(F2_G4, false, double a = 1.0 + x + y; return 1.0 / (a * (a * a));) // functions.rs:49-51 powi(3)
 GKQ_F2(F2_GP1, false, return 1.0 / sqrt(fabs(x) + fabs(y));)              // functions.rs:54-56
@@ -131,7 +150,8 @@ struct YRange {
     X(F1_EXP_P, "exp_p", 1, 30.0)            \
     X(F1_SQRT_SHIFT_P, "sqrt_shift_p", 1, 2.0)       \
     X(F1_INV_ABS_SHIFT_P, "inv_abs_shift_p", 1, 2.0) \
-    X(F1_COS_P, "cos_p", 1, 26.0)
+    X(F1_COS_P, "cos_p", 1, 26.0)            \
+    X(F1_SIN_P, "sin_p", 1, 26.0)
 
 #define GKQ_F2_LIST(X)                       \
     X(F2_XY, "xy", 0, 1.0)                   \

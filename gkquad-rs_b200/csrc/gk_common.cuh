@@ -15,6 +15,10 @@ namespace gkq {
 
 #define GKQ_DEV __device__ __forceinline__
 
+}  // namespace gkq
+#include "gk_math.cuh"
+namespace gkq {
+
 constexpr double F64_EPSILON = 2.220446049250313e-16;        // core::f64::EPSILON
 constexpr double F64_MIN_POSITIVE = 2.2250738585072014e-308; // core::f64::MIN_POSITIVE
 constexpr double F64_MAX = 1.7976931348623157e308;           // core::f64::MAX
@@ -152,14 +156,31 @@ struct Wrapped {
         }
         return f(x);
     }
+    // Two samples at once.  The integrand bodies run branch-free (FastMath) in ONE basic block so
+    // that ptxas interleaves their dependent chains (DFMA latency is ~9 cycles, profiles/); the
+    // rare out-of-range argument re-evaluates both samples through the always-valid path.
+    GKQ_DEV void pair(double x1, double x2, double& f1, double& f2) const {
+        double c1 = 1., c2 = 1.;
+        if (transform) {
+            c1 = 1. / (1. - fabs(x1));
+            c2 = 1. / (1. - fabs(x2));
+            x1 = x1 * c1;
+            x2 = x2 * c2;
+        }
+        FastMath m;
+        f1 = f.eval(x1, m);
+        f2 = f.eval(x2, m);
+        if (!m.ok) {
+            f1 = f(x1);
+            f2 = f(x2);
+        }
+        if (transform) {
+            f1 = f1 * c1 * c1;
+            f2 = f2 * c2 * c2;
+        }
+    }
 };
 
-// The Gauss-Kronrod rule of single/qk/naive.rs:32-106 for ONE thread: the thread evaluates
-// all 2N+1 nodes itself and accumulates the Kronrod / Gauss / |f| sums and the asc pass in
-// the reference's order (j = 0..N-1 from the centre outwards), so results are bit-equal
-// to the CPU for IEEE-exact integrands.  UNROLL = how many node pairs are inlined per loop
-// trip (N = fully unrolled, values stay in registers; smaller = the 2N values live in
-// local memory, which is lane-interleaved and L1-resident).
 // Second half of the rule (single/qk/naive.rs:70-105): Kronrod / Gauss / |f| sums and the asc
 // pass over already evaluated samples, in the reference's order.
 template <int N>
@@ -211,8 +232,7 @@ GKQ_DEV QK qk_rule(const G& g, double a, double b) {
 #pragma unroll UNROLL
     for (int j = 0; j < N; ++j) {
         double abscissa = half_length * R::xgk(j);
-        fv1[j] = g(center - abscissa);
-        fv2[j] = g(center + abscissa);
+        g.pair(center - abscissa, center + abscissa, fv1[j], fv2[j]);
     }
     const double f_center = g(center);
     return qk_reduce<N>(fv1, fv2, f_center, a, b);

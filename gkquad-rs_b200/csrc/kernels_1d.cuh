@@ -34,15 +34,26 @@ constexpr int COOP_MAX_LIVE = GKQ_COOP_MAX_LIVE;
 #endif
 
 // Device-side control block of one batch call (zeroed by a memset node before the kernels).
+// The QAGS pipeline runs as two independent chains after the qk17 pass:
+//   chain 0: integrals whose qk17 error is far off (delta > 1024 tol) skip qk25 and go straight to
+//            bisection:                    qk17 -> first step -> persistent loop
+//   chain 1: the others take the qk25 pass first:  qk17 -> qk25 -> first step -> persistent loop
+// Each chain has its own worklists, counters and slab, so the two run on concurrent streams.
+struct ChainCtl {
+    unsigned long long countLoop;   // entries in listLoop[c]  (integrals entering the main loop)
+    unsigned long long countLoop2;  // entries in listLoop2[c] (unfinished after the first step)
+    unsigned long long headLoop;    // queue head of the chain's persistent kernel
+    unsigned long long pad;
+};
 struct Control {
-    unsigned long long count25;    // entries in list25  (integrals that need the qk25 pass)
-    unsigned long long countLoop;  // entries in listLoop (integrals entering the main loop)
-    unsigned long long headLoop;   // queue head of the persistent QAGS kernel
-    unsigned long long headP;      // queue head of the persistent QAGP kernel
-    unsigned long long countP;     // QAGP worklist size when built on the device (AUTO split)
-    unsigned long long countS;     // QAGS worklist size when built on the device (AUTO split)
-    unsigned long long pad[1];     // pad[0]: largest per-integral point count (CSR batches)
-    unsigned long long countLoop2; // integrals still unfinished after their first bisection step
+    ChainCtl chain[2];
+    unsigned long long count25;  // entries in list25 (integrals that need the qk25 pass)
+    unsigned long long headP;    // queue head of the persistent QAGP / nested kernels
+    unsigned long long countP;   // QAGP worklist size when built on the device (AUTO split)
+    unsigned long long countS;   // QAGS worklist size when built on the device (AUTO split)
+    unsigned long long max_pts;  // largest per-integral point count (CSR batches)
+    unsigned long long head2;    // second queue head (nested QAGS2 kernel)
+    unsigned long long pad[2];
 };
 
 struct Batch1D {
@@ -63,14 +74,15 @@ struct Batch1D {
     Control* ctl;
     double* abs0;               // [n] absvalue of the initial rule (qags.rs:315-376 returns it)
     unsigned int* list25;       // [n]
-    unsigned int* listLoop;     // [n]
-    unsigned int* listLoop2;    // [n] survivors of the first bisection step
+    unsigned int* listLoop[2];  // [n] per chain: integrals entering the main loop
+    unsigned int* listLoop2[2]; // [n] per chain: survivors of the first bisection step
+    int chain;                  // which chain this launch serves (k_qags_first / k_adaptive)
     double* stage;              // [6][n] state parked between k_qags_first and k_adaptive:
                                 //        e1, d1, e2, d2 (the two halves), area, errsum
     unsigned char* stage_ro1;   // [n] roundoff_type1 counter after the first step
     const unsigned int* worklist;        // optional subset of integrals (AUTO split) or nullptr
     const unsigned long long* worklist_count;  // device count for `worklist`
-    SlabGeom slab;
+    SlabGeom slab;  // of the chain being launched
 };
 
 template <class F>
@@ -116,7 +128,7 @@ struct RuleUnroll {
 // ---- QAGS initial passes -------------------------------------------------------------------
 // PASS 0: N = 8 (qk17) over the whole batch (or `worklist`); PASS 1: N = 12 (qk25) over list25.
 template <class F, int N, int NPARAMS>
-__global__ void __launch_bounds__(BLOCK) k_qags_init(const Batch1D P) {
+__global__ void __launch_bounds__(BLOCK, (N == 8) ? 4 : 3) k_qags_init(const Batch1D P) {
     constexpr int PASS = (N == 8) ? 0 : 1;
     long long total;
     if (PASS == 0)
@@ -168,7 +180,7 @@ __global__ void __launch_bounds__(BLOCK) k_qags_init(const Batch1D P) {
             }
         }
         if (PASS == 0) list_append(to25, (unsigned int)i, P.list25, &P.ctl->count25);
-        list_append(toLoop, (unsigned int)i, P.listLoop, &P.ctl->countLoop);
+        list_append(toLoop, (unsigned int)i, P.listLoop[PASS], &P.ctl->chain[PASS].countLoop);
     }
 }
 
@@ -181,13 +193,13 @@ __global__ void __launch_bounds__(BLOCK) k_qags_init(const Batch1D P) {
 // epsilon table = [result0, area], ktmin = 1: what qags.rs leaves behind after iteration 1).
 template <class F, int NPARAMS>
 __global__ void __launch_bounds__(BLOCK) k_qags_first(const Batch1D P) {
-    const long long total = (long long)P.ctl->countLoop;
+    const long long total = (long long)P.ctl->chain[P.chain].countLoop;
     for (long long k = (long long)blockIdx.x * BLOCK + threadIdx.x; k - threadIdx.x % 32 < total;
          k += (long long)gridDim.x * BLOCK) {
         bool survive = false;
         long long i = 0;
         if (k < total) {
-            i = (long long)P.listLoop[k];
+            i = (long long)P.listLoop[P.chain][k];
             Wrapped<F> g;
             double a, b;
             load_range(P, i, a, b, g.transform);
@@ -240,7 +252,7 @@ __global__ void __launch_bounds__(BLOCK) k_qags_first(const Batch1D P) {
                 }
             }
         }
-        list_append(survive, (unsigned int)i, P.listLoop2, &P.ctl->countLoop2);
+        list_append(survive, (unsigned int)i, P.listLoop2[P.chain], &P.ctl->chain[P.chain].countLoop2);
     }
 }
 
@@ -309,8 +321,8 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
     if (QAGP)
         total = P.worklist ? *P.worklist_count : (unsigned long long)P.n;
     else
-        total = P.ctl->countLoop2;
-    unsigned long long* head = QAGP ? &P.ctl->headP : &P.ctl->headLoop;
+        total = P.ctl->chain[P.chain].countLoop2;
+    unsigned long long* head = QAGP ? &P.ctl->headP : &P.ctl->chain[P.chain].headLoop;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * (ABLOCK / 32);
     const unsigned long long warp_id = t >> 5;
     // first fill: queue positions [0, first_span) are owned statically; later refills draw
@@ -381,7 +393,7 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
                     double a, b;
                     if (!QAGP) {
                         // resume after iteration 1 from what k_qags_first parked
-                        s.idx = (long long)P.listLoop2[my];
+                        s.idx = (long long)P.listLoop2[P.chain][my];
                         const long long i = s.idx;
                         load_range(P, i, a, b, s.transform);
                         load_functor(g.f, P, i, NPARAMS);

@@ -335,6 +335,7 @@ struct InnerF {
     F2T f;
     double x;
     GKQ_DEV double operator()(double y) const { return f(x, y); }
+    template <class M> GKQ_DEV double eval(double y, M& m) const { return f.eval(x, y, m); }
 };
 
 // The outer integrand of double/algorithm/qags.rs:66-87 / qagp.rs:108-131 with the infinite
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(BLOCK) k_nested(const Batch2D P) {
     Sin.cap = P.cap_inner;
 
     const unsigned long long total = P.worklist ? *P.worklist_count : (unsigned long long)P.n;
-    unsigned long long* head = QAGP ? &P.ctl->headP : &P.ctl->headLoop;
+    unsigned long long* head = QAGP ? &P.ctl->headP : &P.ctl->head2;
     for (;;) {
         const unsigned long long slot = atomicAdd(head, 1ull);
         if (slot >= total) break;

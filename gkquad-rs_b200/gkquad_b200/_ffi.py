@@ -38,7 +38,8 @@ class gkq_config(C.Structure):
 class gkq_stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("batches", C.c_uint64), ("integrals", C.c_uint64),
                 ("scratch_bytes", C.c_uint64), ("last_survivors_qk25", C.c_uint64),
-                ("last_survivors_loop", C.c_uint64), ("last_survivors_step2", C.c_uint64)]
+                ("last_survivors_loop", C.c_uint64), ("last_survivors_step2", C.c_uint64),
+                ("last_chain_loop", C.c_uint64 * 2), ("last_chain_step2", C.c_uint64 * 2)]
 
 
 # every symbol include/gkquad_b200.h declares (tests/test_abi.py checks the list against the header)

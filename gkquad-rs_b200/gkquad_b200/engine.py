@@ -302,7 +302,11 @@ class Engine:
     def stats(self) -> dict:
         s = _ffi.gkq_stats()
         self._check(self.L.gkq_get_stats(self.h, C.byref(s)))
-        return {k: int(getattr(s, k)) for k, _ in s._fields_}
+        out = {}
+        for k, _ in s._fields_:
+            v = getattr(s, k)
+            out[k] = int(v) if isinstance(v, int) else [int(x) for x in v]
+        return out
 
     def reset_stats(self):
         self._check(self.L.gkq_reset_stats(self.h))

@@ -201,9 +201,11 @@ typedef struct gkq_stats {
     uint64_t batches;           /* integrate calls                                         */
     uint64_t integrals;         /* integrals submitted                                     */
     uint64_t scratch_bytes;     /* device scratch currently owned by the handle            */
-    uint64_t last_survivors_qk25;  /* worklist sizes of the last QAGS batch, valid after    */
-    uint64_t last_survivors_loop;  /* gkq_sync (read back lazily): -> qk25 pass, -> loop    */
+    uint64_t last_survivors_qk25;  /* worklist sizes of the last QAGS batch run with profiling */
+    uint64_t last_survivors_loop;  /* on (gkq_set_profiling), valid after gkq_sync: -> qk25 pass, -> loop */
     uint64_t last_survivors_step2; /* integrals still unfinished after the first bisection  */
+    uint64_t last_chain_loop[2];   /* the same two counts per chain of the QAGS pipeline:   */
+    uint64_t last_chain_step2[2];  /* [0] straight from qk17, [1] through the qk25 pass      */
 } gkq_stats;
 int gkq_get_stats(gkq_handle_t h, gkq_stats* out);
 int gkq_reset_stats(gkq_handle_t h);

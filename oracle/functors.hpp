@@ -38,7 +38,8 @@ enum F1Id : int {
     F1_SQRT_SHIFT_P = 14,   // sqrt(x-p0): NaN left of p0  (NanValueEncountered paths)
     F1_INV_ABS_SHIFT_P = 15,  // 1/|x-p0|: +inf at a node  (appendix A, inf is not NaN)
     F1_COS_P = 16,      // cos(p0*x)                   budget-exhaustion case (section 0.4)
-    F1_COUNT = 17,
+    F1_SIN_P = 17,      // sin(p0*x)
+    F1_COUNT = 18,
 };
 
 static const FunctorInfo F1_TABLE[F1_COUNT] = {
@@ -48,6 +49,7 @@ static const FunctorInfo F1_TABLE[F1_COUNT] = {
     {F1_F3, "f3", 0},           {F1_F4, "f4", 0},             {F1_F5, "f5", 0},
     {F1_F6, "f6", 0},           {F1_EXP_P, "exp_p", 1},       {F1_SQRT_SHIFT_P, "sqrt_shift_p", 1},
     {F1_INV_ABS_SHIFT_P, "inv_abs_shift_p", 1},               {F1_COS_P, "cos_p", 1},
+    {F1_SIN_P, "sin_p", 1},
 };
 
 template <int ID>
@@ -75,6 +77,7 @@ GKQO_F1(F1_EXP_P, return std::exp(p[0] * x);)
 GKQO_F1(F1_SQRT_SHIFT_P, return std::sqrt(x - p[0]);)
 GKQO_F1(F1_INV_ABS_SHIFT_P, return 1.0 / std::fabs(x - p[0]);)
 GKQO_F1(F1_COS_P, return std::cos(p[0] * x);)
+GKQO_F1(F1_SIN_P, return std::sin(p[0] * x);)
 #undef GKQO_F1
 
 // ---- 2-D ----------------------------------------------------------------------------

@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     from gkquad_b200 import _ffi
     assert C.sizeof(_ffi.gkq_tolerance) == 24
     assert C.sizeof(_ffi.gkq_config) == 8 + 24 + 8 + 8 + 8 + 8
-    assert C.sizeof(_ffi.gkq_stats) == 7 * 8
+    assert C.sizeof(_ffi.gkq_stats) == 11 * 8
     cfg = _ffi.gkq_config()
     assert _ffi.lib().gkq_config_default(1, C.byref(cfg)) == 0
     assert (cfg.algo, cfg.tol.kind, cfg.tol.abs_tol, cfg.tol.rel_tol, cfg.max_evals) == (0, 2, 1.49e-8, 1.49e-8, 2000)
