@@ -1,0 +1,104 @@
+//! Raw bindings of include/gkquad_b200.h (ABI version 1).  UNCOMPILED in the build image.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_double, c_float, c_int, c_void};
+
+#[repr(C)]
+pub struct gkq_handle_s {
+    _private: [u8; 0],
+}
+pub type gkq_handle_t = *mut gkq_handle_s;
+
+pub const GKQ_ALGO_AUTO: i32 = 0;
+pub const GKQ_ALGO_QAGS: i32 = 1;
+pub const GKQ_ALGO_QAGP: i32 = 2;
+
+pub const GKQ_TOL_ABSOLUTE: i32 = 0;
+pub const GKQ_TOL_RELATIVE: i32 = 1;
+pub const GKQ_TOL_ABS_OR_REL: i32 = 2;
+pub const GKQ_TOL_ABS_AND_REL: i32 = 3;
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct gkq_tolerance {
+    pub kind: i32,
+    pub _pad: i32,
+    pub abs_tol: c_double,
+    pub rel_tol: c_double,
+}
+
+#[repr(C)]
+pub struct gkq_config {
+    pub algo: i32,
+    pub _pad: i32,
+    pub tol: gkq_tolerance,
+    pub max_evals: u64,
+    pub workspace_capacity: u64,
+    pub points: *const c_double,
+    pub npoints: i64,
+}
+
+#[repr(C)]
+#[derive(Default)]
+pub struct gkq_stats {
+    pub kernel_launches: u64,
+    pub batches: u64,
+    pub integrals: u64,
+    pub scratch_bytes: u64,
+    pub last_survivors_qk25: u64,
+    pub last_survivors_loop: u64,
+    pub last_survivors_step2: u64,
+    pub last_chain_loop: [u64; 2],
+    pub last_chain_step2: [u64; 2],
+}
+
+extern "C" {
+    pub fn gkq_abi_version() -> c_int;
+    pub fn gkq_config_default(dim: c_int, cfg: *mut gkq_config) -> c_int;
+    pub fn gkq_create(device: c_int, out: *mut gkq_handle_t) -> c_int;
+    pub fn gkq_destroy(h: gkq_handle_t) -> c_int;
+    pub fn gkq_last_error(h: gkq_handle_t) -> *const c_char;
+    pub fn gkq_functor_count(dim: c_int) -> c_int;
+    pub fn gkq_functor_info(dim: c_int, id: c_int, name: *mut *const c_char, nparams: *mut c_int,
+                            flops_per_eval: *mut c_double) -> c_int;
+    pub fn gkq_functor_lookup(dim: c_int, name: *const c_char) -> c_int;
+    pub fn gkq_integrate_batch(h: gkq_handle_t, cfg: *const gkq_config, functor_id: c_int, n: i64,
+                               a: *const c_double, b: *const c_double, range_stride: i64,
+                               params: *const c_double, param_stride: i64,
+                               pts_offsets: *const i64, pts: *const c_double,
+                               out_estimate: *mut c_double, out_delta: *mut c_double,
+                               out_nevals: *mut u32, out_status: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn gkq_integrate_batch_host(h: gkq_handle_t, cfg: *const gkq_config, functor_id: c_int, n: i64,
+                                    a: *const c_double, b: *const c_double, range_stride: i64,
+                                    params: *const c_double, param_stride: i64,
+                                    pts_offsets: *const i64, pts: *const c_double,
+                                    out_estimate: *mut c_double, out_delta: *mut c_double,
+                                    out_nevals: *mut u32, out_status: *mut u32) -> c_int;
+    pub fn gkq_integrate2_batch(h: gkq_handle_t, cfg: *const gkq_config, functor2_id: c_int,
+                                yrange_id: c_int, n: i64, x0: *const c_double, x1: *const c_double,
+                                range_stride: i64, fparams: *const c_double, fparam_stride: i64,
+                                yparams: *const c_double, yparam_stride: i64,
+                                pts_offsets: *const i64, pts_xy: *const c_double,
+                                out_estimate: *mut c_double, out_delta: *mut c_double,
+                                out_nevals: *mut u32, out_status: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn gkq_integrate2_batch_host(h: gkq_handle_t, cfg: *const gkq_config, functor2_id: c_int,
+                                     yrange_id: c_int, n: i64, x0: *const c_double, x1: *const c_double,
+                                     range_stride: i64, fparams: *const c_double, fparam_stride: i64,
+                                     yparams: *const c_double, yparam_stride: i64,
+                                     pts_offsets: *const i64, pts_xy: *const c_double,
+                                     out_estimate: *mut c_double, out_delta: *mut c_double,
+                                     out_nevals: *mut u32, out_status: *mut u32) -> c_int;
+    pub fn gkq_qk_batch(h: gkq_handle_t, rule: c_int, functor_id: c_int, n: i64, a: *const c_double,
+                        b: *const c_double, range_stride: i64, params: *const c_double,
+                        param_stride: i64, out4: *mut c_double, stream: *mut c_void) -> c_int;
+    pub fn gkq_functor_eval_batch(h: gkq_handle_t, functor_id: c_int, n: i64, x: *const c_double,
+                                  params: *const c_double, param_stride: i64, y: *mut c_double,
+                                  stream: *mut c_void) -> c_int;
+    pub fn gkq_sync(h: gkq_handle_t, stream: *mut c_void) -> c_int;
+    pub fn gkq_get_stats(h: gkq_handle_t, out: *mut gkq_stats) -> c_int;
+    pub fn gkq_reset_stats(h: gkq_handle_t) -> c_int;
+    pub fn gkq_set_profiling(h: gkq_handle_t, enable: c_int) -> c_int;
+    pub fn gkq_get_profile(h: gkq_handle_t, max_entries: c_int, names: *mut *const c_char,
+                           ms: *mut c_float) -> c_int;
+    pub fn gkq_measure_fp64_peak(h: gkq_handle_t, repeats: c_int, flops_per_s: *mut c_double,
+                                 ms: *mut c_double) -> c_int;
+}

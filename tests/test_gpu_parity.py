@@ -349,3 +349,14 @@ def test_api_mirror_on_gpu(eng):
     assert res.has_err() and res.err().name == "Divergent" and res.unwrap_unchecked().nevals == 550
     with pytest.raises(ValueError):
         res.unwrap()
+
+
+def test_cpp_mirror_reference_benches():
+    """The C++ host mirror (gkquad-rs_b200/cpp/gkquad_b200.hpp) reproduces the six reference bench
+    assertions (benches/single.rs, benches/double.rs) through gkq_integrate*_batch_host."""
+    import subprocess
+    exe = Path(__file__).resolve().parent.parent / "gkquad-rs_b200" / "cpp" / "example_benches"
+    assert exe.exists(), "build it: make -C gkquad-rs_b200"
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert "all reference bench assertions hold" in out.stdout
