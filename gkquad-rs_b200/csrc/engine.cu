@@ -93,6 +93,11 @@ struct gkq_handle_s {
         // chain 1 of the QAGS pipeline runs on its own stream, forked / joined with events
         cudaStream_t side = nullptr;
         cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+        // deferred-join mode: the latency-bound persistent kernels of a batch run on `tail` and
+        // overlap the bulk kernels of the next batch (which uses the other context)
+        cudaStream_t tail = nullptr;
+        cudaEvent_t ev_first0 = nullptr, ev_tail = nullptr;
+        bool tail_pending = false;
         double* stage6 = nullptr;           // [6][cap_n]
         unsigned char* stage_ro1 = nullptr;  // [cap_n]
         size_t stage6_elems = 0, stage_ro1_elems = 0;
@@ -117,6 +122,9 @@ struct gkq_handle_s {
     char* stage_dev = nullptr;
     size_t stage_pin_bytes = 0;
     char* stage_pin = nullptr;
+
+    bool deferred = false;     // gkq_set_deferred_join
+    unsigned call_index = 0;   // alternates the scratch context in deferred mode
 
     // optional per-kernel timing (gkq_set_profiling): one CUDA event pair per launch
     bool profiling = false;
@@ -382,6 +390,9 @@ int gkq_create(int device, gkq_handle_t* out) {
         ok = ok && cudaMalloc(&h->sc[c].ctl, sizeof(Control)) == cudaSuccess &&
              cudaMallocHost(&h->sc[c].ctl_host, sizeof(Control)) == cudaSuccess;
         if (ok) memset(h->sc[c].ctl_host, 0, sizeof(Control));
+        ok = ok && cudaStreamCreateWithFlags(&h->sc[c].tail, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->sc[c].ev_first0, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->sc[c].ev_tail, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaStreamCreateWithFlags(&h->sc[c].side, cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&h->sc[c].ev_fork, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&h->sc[c].ev_join, cudaEventDisableTiming) == cudaSuccess;
@@ -414,6 +425,9 @@ int gkq_destroy(gkq_handle_t h) {
             cudaFree(s.slab_w[k]);
         }
         if (s.side) cudaStreamDestroy(s.side);
+        if (s.tail) cudaStreamDestroy(s.tail);
+        if (s.ev_first0) cudaEventDestroy(s.ev_first0);
+        if (s.ev_tail) cudaEventDestroy(s.ev_tail);
         if (s.ev_fork) cudaEventDestroy(s.ev_fork);
         if (s.ev_join) cudaEventDestroy(s.ev_join);
         cudaFree(s.stage6);
@@ -467,10 +481,38 @@ int gkq_functor_lookup(int dim, const char* name) {
     return GKQ_ERR_INVALID_ARGUMENT;
 }
 
+int gkq_set_deferred_join(gkq_handle_t h, int enable) {
+    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
+    if (!enable && h->deferred) {
+        for (int c = 0; c < 2; ++c)
+            if (h->sc[c].tail_pending) {
+                GKQ_CUDA(h, cudaEventSynchronize(h->sc[c].ev_tail));
+                h->sc[c].tail_pending = false;
+            }
+    }
+    h->deferred = enable != 0;
+    return GKQ_OK;
+}
+
+int gkq_join(gkq_handle_t h, void* stream) {
+    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
+    // (the pending flags stay set: the next batch on that scratch context still has to order
+    // its own stream behind the remainder; waiting twice on an event is harmless)
+    for (int c = 0; c < 2; ++c)
+        if (h->sc[c].tail_pending)
+            GKQ_CUDA(h, cudaStreamWaitEvent((cudaStream_t)stream, h->sc[c].ev_tail, 0));
+    return GKQ_OK;
+}
+
 int gkq_sync(gkq_handle_t h, void* stream) {
     if (!h) return GKQ_ERR_INVALID_ARGUMENT;
     GKQ_CUDA(h, cudaSetDevice(h->device));
+    {
+        int rcj = gkq_join(h, stream);
+        if (rcj) return rcj;
+    }
     GKQ_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+    h->sc[0].tail_pending = h->sc[1].tail_pending = false;
     h->cur = 0;
     if (h->sc[h->cur].ctl_pending) {
         h->stats.last_survivors_qk25 = h->sc[h->cur].ctl_host->count25;
@@ -584,32 +626,56 @@ static int run_qags(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, cudaS
     for (int c = 0; c < 2; ++c)
         if ((rc = ensure_slab(h, (unsigned long long)grid * ABLOCK, cap, 0, slab[c], c))) return rc;
 
-    // fork: chain 1 (qk25 pass and what follows it) runs on the side stream
-    GKQ_CUDA(h, cudaEventRecord(S.ev_fork, st));
-    GKQ_CUDA(h, cudaStreamWaitEvent(S.side, S.ev_fork, 0));
+    // fork: chain 1 (qk25 pass and what follows it) runs on the side stream.  In profiling mode
+    // everything stays on one stream so that the per-kernel event brackets are clean.
+    const bool serial = h->profiling;
+    const bool defer = h->deferred && !h->profiling;
+    if (!serial) {
+        GKQ_CUDA(h, cudaEventRecord(S.ev_fork, st));
+        GKQ_CUDA(h, cudaStreamWaitEvent(S.side, S.ev_fork, 0));
+    }
+    Batch1D Q[2];
     for (int c = 0; c < 2; ++c) {
-        cudaStream_t cs = c == 0 ? st : S.side;
-        Batch1D Q = P;
-        Q.chain = c;
-        Q.slab = slab[c];
+        cudaStream_t cs = (c == 0 || serial) ? st : S.side;
+        Q[c] = P;
+        Q[c].chain = c;
+        Q[c].slab = slab[c];
         if (c == 1) {
             prof_begin(h, "k_qags_init<qk25>", cs);
-            L.qags_init25(Q, (int)g25, cs);
+            L.qags_init25(Q[c], (int)g25, cs);
             prof_end(h, cs);
             if ((rc = launch_check(h, "k_qags_init<qk25>"))) return rc;
         }
         prof_begin(h, c == 0 ? "k_qags_first[0]" : "k_qags_first[1]", cs);
-        L.qags_first(Q, (int)g25, cs);
+        L.qags_first(Q[c], (int)g25, cs);
         prof_end(h, cs);
         if ((rc = launch_check(h, "k_qags_first"))) return rc;
+        if (defer) {
+            if (c == 0) GKQ_CUDA(h, cudaEventRecord(S.ev_first0, st));
+            continue;  // the persistent kernels are launched below, on the tail stream
+        }
         prof_begin(h, c == 0 ? "k_adaptive<QAGS>[0]" : "k_adaptive<QAGS>[1]", cs);
-        L.qags_loop(Q, grid, cs);
+        L.qags_loop(Q[c], grid, cs);
         prof_end(h, cs);
         if ((rc = launch_check(h, "k_adaptive<QAGS>"))) return rc;
     }
-    // join
-    GKQ_CUDA(h, cudaEventRecord(S.ev_join, S.side));
-    GKQ_CUDA(h, cudaStreamWaitEvent(st, S.ev_join, 0));
+    // join the bulk of chain 1 back into the caller's stream
+    if (!serial) {
+        GKQ_CUDA(h, cudaEventRecord(S.ev_join, S.side));
+        GKQ_CUDA(h, cudaStreamWaitEvent(st, S.ev_join, 0));
+    }
+    if (defer) {
+        // latency-bound remainder: a few integrals walking many bisection steps.  It runs on the
+        // context's tail stream and overlaps whatever the caller enqueues next; gkq_join / gkq_sync
+        // (or the next batch that needs this scratch context) waits for it.
+        for (int c = 0; c < 2; ++c) {
+            GKQ_CUDA(h, cudaStreamWaitEvent(S.tail, c == 0 ? S.ev_first0 : S.ev_join, 0));
+            L.qags_loop(Q[c], grid, S.tail);
+            if ((rc = launch_check(h, "k_adaptive<QAGS>"))) return rc;
+        }
+        GKQ_CUDA(h, cudaEventRecord(S.ev_tail, S.tail));
+        S.tail_pending = true;
+    }
     return GKQ_OK;
 }
 
@@ -646,8 +712,13 @@ int gkq_integrate_batch(gkq_handle_t h, const gkq_config* cfg, int functor_id, i
                         uint32_t* out_nevals, uint32_t* out_status, void* stream) {
     if (!h) return GKQ_ERR_INVALID_ARGUMENT;
     h->cur = 0;
-    return integrate_batch_ctx(h, cfg, functor_id, n, a, b, range_stride, params, param_stride,
-                               pts_offsets, pts, out_estimate, out_delta, out_nevals, out_status, stream);
+    if (h->deferred) {
+        h->cur = (int)(h->call_index++ & 1u);
+    }
+    int rc = integrate_batch_ctx(h, cfg, functor_id, n, a, b, range_stride, params, param_stride,
+                                 pts_offsets, pts, out_estimate, out_delta, out_nevals, out_status, stream);
+    h->cur = 0;
+    return rc;
 }
 
 static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
@@ -677,6 +748,11 @@ static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functo
 
     GKQ_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (h->sc[h->cur].tail_pending) {
+        // the deferred remainder of the batch that last used this scratch context must be over
+        GKQ_CUDA(h, cudaStreamWaitEvent(st, h->sc[h->cur].ev_tail, 0));
+        h->sc[h->cur].tail_pending = false;
+    }
     if ((rc = ensure_batch_scratch(h, (size_t)n))) return rc;
 
     Batch1D P;
@@ -896,12 +972,16 @@ int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_
 
         GKQ_CUDA(h, cudaStreamWaitEvent(sc, ev_in[buf], 0));
         h->cur = ctx;
+        const bool was_deferred = h->deferred;
+        h->deferred = true;  // chunks are independent batches: their remainders overlap the next chunk
         rc = integrate_batch_ctx(h, cfg, functor_id, m, d_a, d_b, range_stride, d_par,
                                  param_stride ? C : 0, nullptr, nullptr, d_est, d_dlt, d_nev, d_st, sc);
+        h->deferred = was_deferred;
         if (rc) break;
         GKQ_CUDA(h, cudaEventRecord(ev_done[buf], sc));
 
         GKQ_CUDA(h, cudaStreamWaitEvent(h->s_out, ev_done[buf], 0));
+        if (h->sc[ctx].tail_pending) GKQ_CUDA(h, cudaStreamWaitEvent(h->s_out, h->sc[ctx].ev_tail, 0));
         GKQ_CUDA(h, cudaMemcpyAsync(out_estimate + off, d_est, (size_t)m * 8, cudaMemcpyDeviceToHost, h->s_out));
         GKQ_CUDA(h, cudaMemcpyAsync(out_delta + off, d_dlt, (size_t)m * 8, cudaMemcpyDeviceToHost, h->s_out));
         GKQ_CUDA(h, cudaMemcpyAsync(out_nevals + off, d_nev, (size_t)m * 4, cudaMemcpyDeviceToHost, h->s_out));
@@ -912,6 +992,7 @@ int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_
     cudaError_t e2 = cudaStreamSynchronize(h->s_compute);
     cudaError_t e4 = cudaStreamSynchronize(h->s_compute2);
     cudaError_t e3 = cudaStreamSynchronize(h->s_out);
+    h->sc[0].tail_pending = h->sc[1].tail_pending = false;  // s_out waited for every remainder
     for (int k = 0; k < NBUF; ++k) {
         cudaEventDestroy(ev_in[k]);
         cudaEventDestroy(ev_done[k]);

@@ -48,7 +48,7 @@ SYMBOLS = [
     "gkq_functor_count", "gkq_functor_info", "gkq_functor_lookup", "gkq_integrate_batch",
     "gkq_integrate_batch_host", "gkq_integrate2_batch", "gkq_integrate2_batch_host", "gkq_qk_batch",
     "gkq_functor_eval_batch",
-    "gkq_sync", "gkq_get_stats", "gkq_reset_stats", "gkq_set_profiling", "gkq_get_profile",
+    "gkq_set_deferred_join", "gkq_join", "gkq_sync", "gkq_get_stats", "gkq_reset_stats", "gkq_set_profiling", "gkq_get_profile",
     "gkq_measure_fp64_peak",
 ]
 
@@ -86,6 +86,8 @@ def lib():
     L.gkq_integrate2_batch_host.argtypes = batch2
     L.gkq_qk_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int64, dp, dp, C.c_int64, dp, C.c_int64, dp, vp]
     L.gkq_functor_eval_batch.argtypes = [vp, C.c_int, C.c_int64, dp, dp, C.c_int64, dp, vp]
+    L.gkq_set_deferred_join.argtypes = [vp, C.c_int]
+    L.gkq_join.argtypes = [vp, vp]
     L.gkq_sync.argtypes = [vp, vp]
     L.gkq_get_stats.argtypes = [vp, C.POINTER(gkq_stats)]
     L.gkq_reset_stats.argtypes = [vp]

@@ -296,6 +296,14 @@ class Engine:
         return BatchResult(est, dlt, nev, st)
 
     # ---- accounting -------------------------------------------------------------------------
+    def set_deferred_join(self, on: bool):
+        """Throughput pipelining of independent batches (see gkq_set_deferred_join): results of a
+        batch are complete only after join() / sync()."""
+        self._check(self.L.gkq_set_deferred_join(self.h, 1 if on else 0))
+
+    def join(self):
+        self._check(self.L.gkq_join(self.h, self._stream()))
+
     def sync(self):
         self._check(self.L.gkq_sync(self.h, self._stream()))
 

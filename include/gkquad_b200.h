@@ -193,6 +193,18 @@ int gkq_qk_batch(gkq_handle_t h, int rule, int functor_id, int64_t n, const doub
 int gkq_functor_eval_batch(gkq_handle_t h, int functor_id, int64_t n, const double* x,
                            const double* params, int64_t param_stride, double* y, void* stream);
 
+/* Deferred-join mode (throughput pipelining of independent batches).  By default a batch call is
+ * fully ordered on `stream`.  With deferred join enabled, gkq_integrate_batch still enqueues every
+ * bulk kernel on `stream`, but the latency-bound remainder of a QAGS batch (the persistent kernels
+ * that walk the few integrals needing many bisection steps) runs on a handle-owned stream and
+ * overlaps whatever is enqueued next -- typically the bulk of the NEXT batch, which uses the
+ * handle's second scratch context (two batches in flight).  The outputs of a batch are complete
+ * only after gkq_join(h, stream) (makes `stream` wait for all outstanding remainders) or gkq_sync.
+ * The reference has no counterpart (it is synchronous); an Integrator-level sweep over many
+ * parameter batches is where this applies. */
+int gkq_set_deferred_join(gkq_handle_t h, int enable);
+int gkq_join(gkq_handle_t h, void* stream);
+
 /* ---- stream helpers / accounting --------------------------------------------------------- */
 int gkq_sync(gkq_handle_t h, void* stream);
 

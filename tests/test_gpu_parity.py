@@ -360,3 +360,25 @@ def test_cpp_mirror_reference_benches():
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr + out.stdout
     assert "all reference bench assertions hold" in out.stdout
+
+
+def test_deferred_join_pipelining(eng):
+    """gkq_set_deferred_join: back-to-back independent batches (remainders overlapping the next
+    batch's bulk, alternating scratch contexts) give exactly the results of ordered calls."""
+    import torch
+    from gkquad_b200.workloads import WORKLOADS
+    W = WORKLOADS["S3"]  # long tails: many integrals need 3..14 bisection steps
+    n = 200_000
+    ps = [torch.as_tensor(W.make_params(k * n, n), device="cuda:0") for k in range(5)]
+    ref = [eng.integrate_batch(W.functor, 0.0, 1.0, p, algo=ALGO["QAGS"], tol=W.tol, n=n).numpy() for p in ps]
+    eng.set_deferred_join(True)
+    try:
+        outs = [eng.integrate_batch(W.functor, 0.0, 1.0, p, algo=ALGO["QAGS"], tol=W.tol, n=n) for p in ps]
+        eng.join()
+        torch.cuda.synchronize()
+        got = [o.numpy() for o in outs]
+    finally:
+        eng.set_deferred_join(False)
+    for g, r in zip(got, ref):
+        assert np.array_equal(g.estimate, r.estimate) and np.array_equal(g.delta, r.delta)
+        assert np.array_equal(g.nevals, r.nevals) and np.array_equal(g.status, r.status)
