@@ -239,7 +239,10 @@ def _main(args, real_stdout):
         ints = packed[2 * n:].view(torch.int32)
         out = (packed[:n], packed[n:2 * n], ints[:n], ints[n:])
         gathered = torch.empty(world * 3 * n, dtype=torch.float64, device=dev) if world > 1 else None
-        sets.append(dict(p_host=p_host, p_dev=torch.as_tensor(p_host, device=dev), kw=kw, packed=packed,
+        p_dev = torch.as_tensor(p_host, device=dev)
+        # the call is marshalled once (an Integrator owns integrand + config and is run many times)
+        plan = eng.plan_batch(W.functor, W.a, W.b, p_dev, out=out, **kw)
+        sets.append(dict(p_host=p_host, p_dev=p_dev, kw=kw, packed=packed, plan=plan,
                          out=out, gathered=gathered, done=None))
     p_host = sets[0]["p_host"]
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
@@ -250,7 +253,7 @@ def _main(args, real_stdout):
         S = sets[k % NSETS]
         if S["done"] is not None:  # the gather that last read this buffer must be over
             torch.cuda.current_stream().wait_event(S["done"])
-        eng.integrate_batch(W.functor, W.a, W.b, S["p_dev"], out=S["out"], **S["kw"])
+        S["plan"].run()
         if world > 1:
             ev = torch.cuda.Event()
             ev.record()
@@ -373,13 +376,14 @@ def _main(args, real_stdout):
         if W.points and W.points != "param0":
             kwh["points"] = W.points
         if W.points != "param0":
+            hplan = eng.plan_batch(W.functor, W.a, W.b, ph.numpy(), **kwh)
             for _ in range(3):
-                eng.integrate_batch(W.functor, W.a, W.b, ph.numpy(), **kwh)
+                hplan.run()
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
             for _ in range(args.steps):
-                eng.integrate_batch(W.functor, W.a, W.b, ph.numpy(), **kwh)
+                hplan.run()
             dt = (time.perf_counter() - t0) / args.steps
             tt = torch.tensor([dt], dtype=torch.float64, device=dev)
             if world > 1:

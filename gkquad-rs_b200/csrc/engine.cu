@@ -1,6 +1,15 @@
 // engine.cu -- handle, device scratch, dispatch and the C ABI of libgkquad_b200.so
 // (include/gkquad_b200.h).  No torch, no oracle, no CPU fallback: without a CUDA device
 // gkq_create fails and nothing can be computed.
+//
+// Orchestration of one QAGS batch:
+//   bulk      k_qags_init<qk17> -> { k_qags_first[0] } || { k_qags_init<qk25> -> k_qags_first[1] }
+//             flat, stateless, throughput-bound kernels; the few integrals that are still
+//             unfinished after their first bisection step leave as self-contained STRAGGLER
+//             RECORDS in a handle-owned buffer;
+//   remainder one launch of the persistent kernel k_adaptive<.., QAGS> finishes the records --
+//             immediately (ordered mode), at gkq_join (deferred mode: the remainders of many
+//             batches share one launch), or once at the end of a host-pipeline call.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -42,7 +51,6 @@ __global__ void __launch_bounds__(BLOCK) k_split_auto(long long n, const long lo
         list_append(valid && cnt == 0, (unsigned int)i, listS, &ctl->countS);
         list_append(valid && cnt != 0, (unsigned int)i, listP, &ctl->countP);
     }
-    // max points per integral -> pad[0]
     unsigned long long m = (unsigned long long)(cnt > 0 ? cnt : 0);
     for (int o = 16; o > 0; o >>= 1) {
         unsigned long long other = __shfl_xor_sync(0xffffffffu, m, o);
@@ -76,55 +84,70 @@ struct gkq_handle_s {
     size_t total_mem = 0;
     std::string err;
     gkq_stats stats{};
+    bool deferred = false;  // gkq_set_deferred_join
 
-    // Two independent scratch contexts: the device entry uses context 0; the host entry alternates
-    // so that the latency-bound tail kernels of one chunk overlap the bulk kernels of the next.
+    // Bulk scratch: two contexts, so the host pipeline can run chunks on two compute streams.
     struct Scratch {
-    Control* ctl = nullptr;       // device
-        Control* ctl_host = nullptr;  // pinned mirror for lazy read-back
+        Control* ctl = nullptr;       // device
+        Control* ctl_host = nullptr;  // pinned mirror (profiling read-back, CSR split)
         bool ctl_pending = false;
-
-        // per-batch scratch, grown on demand
         size_t cap_n = 0;
         double* abs0 = nullptr;
         unsigned int *list25 = nullptr, *listS = nullptr, *listP = nullptr;
         unsigned int* listLoop[2] = {nullptr, nullptr};
-        unsigned int* listLoop2[2] = {nullptr, nullptr};
-        // chain 1 of the QAGS pipeline runs on its own stream, forked / joined with events
-        cudaStream_t side = nullptr;
+        cudaStream_t side = nullptr;  // chain 1 of the QAGS bulk
         cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-        // deferred-join mode: the latency-bound persistent kernels of a batch run on `tail` and
-        // overlap the bulk kernels of the next batch (which uses the other context)
-        cudaStream_t tail = nullptr;
-        cudaEvent_t ev_first0 = nullptr, ev_tail = nullptr;
-        bool tail_pending = false;
-        double* stage6 = nullptr;           // [6][cap_n]
-        unsigned char* stage_ro1 = nullptr;  // [cap_n]
-        size_t stage6_elems = 0, stage_ro1_elems = 0;
-
-        size_t slab_d_elems[2] = {0, 0}, slab_w_elems[2] = {0, 0};
-        double* slab_d[2] = {nullptr, nullptr};
-        int* slab_w[2] = {nullptr, nullptr};
-
-        size_t dev_pts_cap = 0;
-        double* dev_pts = nullptr;     // shared points (device copy)
-        double* host_pts = nullptr;    // pinned staging for the shared points
-        size_t host_pts_cap = 0;
-        size_t pts_count = 0;
-
+        // slab of the persistent QAGP / nested kernels
+        size_t slab_d_elems = 0, slab_w_elems = 0;
+        double* slab_d = nullptr;
+        int* slab_w = nullptr;
+        // shared points (device copy + pinned staging)
+        size_t dev_pts_cap = 0, host_pts_cap = 0, pts_count = 0;
+        double* dev_pts = nullptr;
+        double* host_pts = nullptr;
     };
     Scratch sc[2];
     int cur = 0;
 
-    // host-entry staging (gkq_integrate_batch_host)
-    cudaStream_t s_in = nullptr, s_compute = nullptr, s_compute2 = nullptr, s_out = nullptr;
+    // Straggler records: two buffers, so that the remainder of one group of batches can run while
+    // the next batches already append to the other buffer.
+    static constexpr int MAX_CALLS = 64;
+    struct RecBuf {
+        StragglerRec* recs = nullptr;
+        size_t cap = 0;
+        RecCtl* rctl = nullptr;
+        RecCtl* rctl_host = nullptr;      // pinned
+        Outputs* call_outs = nullptr;     // device [MAX_CALLS]
+        Outputs* call_outs_pin = nullptr;  // pinned mirror
+        int ncalls = 0;                   // calls that appended since the last flush
+        size_t n_bound = 0;               // upper bound of the records they may have appended
+        int fid = -1;                     // configuration the pending records were produced under
+        Tol tol{};
+        unsigned long long max_evals = 0, ws_capacity = 0;
+        cudaEvent_t ev_bulk = nullptr;    // after the last bulk kernel that appended
+        cudaEvent_t ev_tail = nullptr;    // after the flush
+        bool tail_pending = false;
+        // slab of the persistent QAGS kernel
+        size_t slab_d_elems = 0, slab_w_elems = 0;
+        double* slab_d = nullptr;
+        int* slab_w = nullptr;
+        // patch arrays (host pipeline): [cap] idx | est | dlt | nev | st, device + pinned
+        char* patch_dev = nullptr;
+        char* patch_pin = nullptr;
+        size_t patch_cap = 0;
+    };
+    RecBuf rb[2];
+    int rb_cur = 0;
+
+    // host-entry pipeline (gkq_integrate_batch_host)
+    static constexpr int MAX_CHUNKS = 64;
+    cudaStream_t s_in = nullptr, s_compute = nullptr, s_compute2 = nullptr, s_out = nullptr, s_out2 = nullptr;
+    cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_done[MAX_CHUNKS] = {};
+    cudaEvent_t ev_c2 = nullptr;
+    bool host_records_primed = false;  // the host pipeline has reset the record counters itself
     size_t stage_bytes = 0;
     char* stage_dev = nullptr;
-    size_t stage_pin_bytes = 0;
-    char* stage_pin = nullptr;
-
-    bool deferred = false;     // gkq_set_deferred_join
-    unsigned call_index = 0;   // alternates the scratch context in deferred mode
+    double* fixed_pin = nullptr;  // pinned copy of the shared (stride-0) range / parameters
 
     // optional per-kernel timing (gkq_set_profiling): one CUDA event pair per launch
     bool profiling = false;
@@ -204,48 +227,41 @@ int grow(gkq_handle_t h, T*& p, size_t& have, size_t want) {
 }
 
 int ensure_batch_scratch(gkq_handle_t h, size_t n) {
-    if (n <= h->sc[h->cur].cap_n) return 0;
-    size_t dummy;
-    size_t w = n + n / 8 + 1024;
-    auto re = [&](auto*& p) -> int {
-        using T = std::remove_reference_t<decltype(*p)>;
-        size_t have = h->sc[h->cur].cap_n;
-        T* q = p;
-        dummy = have;
-        int rc = grow(h, q, dummy, w);
-        p = q;
-        return rc;
-    };
+    gkq_handle_s::Scratch& S = h->sc[h->cur];
+    if (n <= S.cap_n) return 0;
+    const size_t w = n + n / 8 + 1024;
     int rc;
-    if ((rc = re(h->sc[h->cur].abs0))) return rc;
-    if ((rc = re(h->sc[h->cur].list25))) return rc;
+    size_t have;
+    have = S.cap_n; if ((rc = grow(h, S.abs0, have, w))) return rc;
+    have = S.cap_n; if ((rc = grow(h, S.list25, have, w))) return rc;
+    have = S.cap_n; if ((rc = grow(h, S.listS, have, w))) return rc;
+    have = S.cap_n; if ((rc = grow(h, S.listP, have, w))) return rc;
     for (int c = 0; c < 2; ++c) {
-        if ((rc = re(h->sc[h->cur].listLoop[c]))) return rc;
-        if ((rc = re(h->sc[h->cur].listLoop2[c]))) return rc;
+        have = S.cap_n;
+        if ((rc = grow(h, S.listLoop[c], have, w))) return rc;
     }
-    if ((rc = grow(h, h->sc[h->cur].stage6, h->sc[h->cur].stage6_elems, 6 * w))) return rc;
-    if ((rc = grow(h, h->sc[h->cur].stage_ro1, h->sc[h->cur].stage_ro1_elems, w))) return rc;
-    if ((rc = re(h->sc[h->cur].listS))) return rc;
-    if ((rc = re(h->sc[h->cur].listP))) return rc;
-    h->sc[h->cur].cap_n = w;  // every grow() call allocated >= w elements
+    S.cap_n = w;  // every grow() allocated >= w elements
     return 0;
 }
 
-// Per-thread slabs for `threads` persistent threads with `cap` interval slots each (one slab
-// per chain of the QAGS pipeline; every other kernel uses slab 0).
-int ensure_slab(gkq_handle_t h, unsigned long long threads, int cap, int npts_max, SlabGeom& g, int which = 0) {
-    gkq_handle_s::Scratch& s = h->sc[h->cur];
+int slab_geom(gkq_handle_t h, double*& sd, size_t& sd_n, int*& sw, size_t& sw_n, unsigned long long threads,
+              int cap, int npts_max, SlabGeom& g) {
     const unsigned long long nd = slab_doubles(cap, npts_max) * threads;
     const unsigned long long nw = slab_ints(cap) * threads;
     int rc;
-    if ((rc = grow(h, s.slab_d[which], s.slab_d_elems[which], (size_t)nd))) return rc;
-    if ((rc = grow(h, s.slab_w[which], s.slab_w_elems[which], (size_t)nw))) return rc;
-    g.dbase = s.slab_d[which];
-    g.wbase = s.slab_w[which];
+    if ((rc = grow(h, sd, sd_n, (size_t)nd))) return rc;
+    if ((rc = grow(h, sw, sw_n, (size_t)nw))) return rc;
+    g.dbase = sd;
+    g.wbase = sw;
     g.stride = threads;
     g.cap = cap;
     g.npts_max = npts_max;
     return 0;
+}
+// slab of the persistent QAGP / nested kernels (bulk scratch context)
+int ensure_slab(gkq_handle_t h, unsigned long long threads, int cap, int npts_max, SlabGeom& g) {
+    gkq_handle_s::Scratch& S = h->sc[h->cur];
+    return slab_geom(h, S.slab_d, S.slab_d_elems, S.slab_w, S.slab_w_elems, threads, cap, npts_max, g);
 }
 
 int check_tol(gkq_handle_t h, const gkq_tolerance& t) {
@@ -334,6 +350,118 @@ void prof_clear(gkq_handle_t h) {
     h->prof.clear();
 }
 
+// ---- straggler records ------------------------------------------------------------------------
+inline size_t patch_bytes(size_t cap) { return cap * (8 + 8 + 8 + 4 + 4); }
+inline PatchView patch_view(char* base, size_t cap) {
+    PatchView v;
+    v.idx = (unsigned long long*)base;
+    v.est = (double*)(v.idx + cap);
+    v.dlt = v.est + cap;
+    v.nev = (unsigned int*)(v.dlt + cap);
+    v.st = v.nev + cap;
+    return v;
+}
+
+// Finish the pending records of the current buffer with one launch of the persistent QAGS kernel
+// on `stream` and switch to the other buffer.  patch = true: results go to the buffer's patch.
+int flush_records(gkq_handle_t h, cudaStream_t stream, bool patch) {
+    gkq_handle_s::RecBuf& R = h->rb[h->rb_cur];
+    if (R.ncalls == 0) return GKQ_OK;
+    int rc;
+    const int fid = R.fid;
+    const Launch1D& L = h->l1[fid];
+    if (h->occ_loop[fid] < 0) h->occ_loop[fid] = L.occupancy_loop();
+    const unsigned long long need = (R.max_evals - 17) / 50 + 1;  // qags.rs:98-99, nevals >= 17
+    if (need > (1ull << 26)) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
+    const int cap = (int)need;  // the list never outgrows the reserve request
+    int grid = persistent_grid(h, h->occ_loop[fid], cap, 0, ABLOCK);
+    if (grid < 1) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
+    const long long ablocks = ((long long)R.n_bound + ABLOCK - 1) / ABLOCK;
+    if ((long long)grid > ablocks) grid = (int)(ablocks > 0 ? ablocks : 1);
+    Batch1D Q;
+    memset(&Q, 0, sizeof Q);
+    if ((rc = slab_geom(h, R.slab_d, R.slab_d_elems, R.slab_w, R.slab_w_elems, (unsigned long long)grid * ABLOCK,
+                        cap, 0, Q.slab)))
+        return rc;
+    Q.tol = R.tol;
+    Q.max_evals = R.max_evals;
+    Q.ws_capacity = R.ws_capacity;
+    Q.recs = R.recs;
+    Q.rctl = R.rctl;
+    Q.call_outs = R.call_outs;
+    Q.ctl = h->sc[0].ctl;  // unused by the QAGS instance
+    if (patch)
+        Q.patch = patch_view(R.patch_dev, R.patch_cap);
+    else
+        GKQ_CUDA(h, cudaStreamWaitEvent(stream, R.ev_bulk, 0));
+    prof_begin(h, "k_adaptive<QAGS>", stream);
+    L.qags_loop(Q, grid, stream);
+    prof_end(h, stream);
+    if ((rc = launch_check(h, "k_adaptive<QAGS>"))) return rc;
+    if (h->profiling)
+        GKQ_CUDA(h, cudaMemcpyAsync(R.rctl_host, R.rctl, sizeof(RecCtl), cudaMemcpyDeviceToHost, stream));
+    GKQ_CUDA(h, cudaEventRecord(R.ev_tail, stream));
+    R.tail_pending = true;
+    R.ncalls = 0;
+    R.n_bound = 0;
+    h->rb_cur ^= 1;
+    return GKQ_OK;
+}
+
+// Prepare the current record buffer for a call that may append up to n records under the given
+// configuration; flushes first when the pending records are incompatible or would not fit.
+int records_begin(gkq_handle_t h, cudaStream_t st, int fid, const Batch1D& P, size_t n, bool patch,
+                  unsigned int& slot) {
+    int rc;
+    {
+        gkq_handle_s::RecBuf& R = h->rb[h->rb_cur];
+        const bool same = R.fid == fid && R.tol.kind == P.tol.kind && R.tol.abs_tol == P.tol.abs_tol &&
+                          R.tol.rel_tol == P.tol.rel_tol && R.max_evals == P.max_evals &&
+                          R.ws_capacity == P.ws_capacity;
+        if (R.ncalls > 0 && (!same || (!patch && R.ncalls >= gkq_handle_s::MAX_CALLS) || R.n_bound + n > R.cap))
+            if ((rc = flush_records(h, st, patch))) return rc;
+    }
+    gkq_handle_s::RecBuf& R = h->rb[h->rb_cur];
+    if (R.ncalls == 0) {
+        // fresh buffer: its previous remainder must be over, then reset the counters
+        if (R.tail_pending) {
+            GKQ_CUDA(h, cudaStreamWaitEvent(st, R.ev_tail, 0));
+            R.tail_pending = false;
+        }
+        // deferred mode batches the remainders of up to 8 calls into one launch (every integral of
+        // a call may become a record, so room for 8 n records is kept: 144 B each)
+        const size_t want = (h->deferred && !patch && !h->profiling) ? 8 * n : n;
+        if (want > R.cap) {
+            GKQ_CUDA(h, cudaStreamSynchronize(st));  // nothing may still read the old buffer
+            if ((rc = grow(h, R.recs, R.cap, want))) return rc;
+            // grow the idle twin buffer now as well (keeps allocations out of steady state)
+            gkq_handle_s::RecBuf& O = h->rb[h->rb_cur ^ 1];
+            if (O.ncalls == 0 && !O.tail_pending && want > O.cap)
+                if ((rc = grow(h, O.recs, O.cap, want))) return rc;
+        }
+        if (!h->host_records_primed) GKQ_CUDA(h, cudaMemsetAsync(R.rctl, 0, sizeof(RecCtl), st));
+        R.fid = fid;
+        R.tol = P.tol;
+        R.max_evals = P.max_evals;
+        R.ws_capacity = P.ws_capacity;
+    }
+    if (patch && R.patch_cap < R.cap) {
+        if (R.patch_dev) GKQ_CUDA(h, cudaFree(R.patch_dev));
+        if (R.patch_pin) GKQ_CUDA(h, cudaFreeHost(R.patch_pin));
+        R.patch_dev = R.patch_pin = nullptr;
+        GKQ_CUDA(h, cudaMalloc(&R.patch_dev, patch_bytes(R.cap)));
+        GKQ_CUDA(h, cudaMallocHost(&R.patch_pin, patch_bytes(R.cap)));
+        R.patch_cap = R.cap;
+        h->stats.scratch_bytes += patch_bytes(R.cap);
+    }
+    slot = (unsigned int)R.ncalls;
+    if (!patch) {  // (patched results never look the owning call up)
+        R.call_outs_pin[slot] = P.out;
+        GKQ_CUDA(h, cudaMemcpyAsync(R.call_outs + slot, R.call_outs_pin + slot, sizeof(Outputs), cudaMemcpyHostToDevice, st));
+    }
+    return GKQ_OK;
+}
+
 }  // namespace
 
 // ---- C ABI -----------------------------------------------------------------------------------
@@ -386,22 +514,38 @@ int gkq_create(int device, gkq_handle_t* out) {
     FillL1<0>::go(h);
     FillL2<0>::go(h);
     bool ok = true;
+    auto ev = [&](cudaEvent_t* e_) { ok = ok && cudaEventCreateWithFlags(e_, cudaEventDisableTiming) == cudaSuccess; };
+    auto strm = [&](cudaStream_t* s_) { ok = ok && cudaStreamCreateWithFlags(s_, cudaStreamNonBlocking) == cudaSuccess; };
     for (int c = 0; c < 2; ++c) {
-        ok = ok && cudaMalloc(&h->sc[c].ctl, sizeof(Control)) == cudaSuccess &&
-             cudaMallocHost(&h->sc[c].ctl_host, sizeof(Control)) == cudaSuccess;
-        if (ok) memset(h->sc[c].ctl_host, 0, sizeof(Control));
-        ok = ok && cudaStreamCreateWithFlags(&h->sc[c].tail, cudaStreamNonBlocking) == cudaSuccess &&
-             cudaEventCreateWithFlags(&h->sc[c].ev_first0, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&h->sc[c].ev_tail, cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaStreamCreateWithFlags(&h->sc[c].side, cudaStreamNonBlocking) == cudaSuccess &&
-             cudaEventCreateWithFlags(&h->sc[c].ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&h->sc[c].ev_join, cudaEventDisableTiming) == cudaSuccess;
+        gkq_handle_s::Scratch& S = h->sc[c];
+        ok = ok && cudaMalloc(&S.ctl, sizeof(Control)) == cudaSuccess &&
+             cudaMallocHost(&S.ctl_host, sizeof(Control)) == cudaSuccess;
+        if (ok) memset(S.ctl_host, 0, sizeof(Control));
+        strm(&S.side);
+        ev(&S.ev_fork);
+        ev(&S.ev_join);
+        gkq_handle_s::RecBuf& R = h->rb[c];
+        ok = ok && cudaMalloc(&R.rctl, sizeof(RecCtl)) == cudaSuccess &&
+             cudaMallocHost(&R.rctl_host, sizeof(RecCtl)) == cudaSuccess &&
+             cudaMalloc(&R.call_outs, sizeof(Outputs) * gkq_handle_s::MAX_CALLS) == cudaSuccess &&
+             cudaMallocHost(&R.call_outs_pin, sizeof(Outputs) * gkq_handle_s::MAX_CALLS) == cudaSuccess;
+        if (ok) memset(R.rctl_host, 0, sizeof(RecCtl));
+        ev(&R.ev_bulk);
+        ev(&R.ev_tail);
     }
-    if (!ok || cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->s_compute2, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess) {
-        delete h;
+    strm(&h->s_in);
+    strm(&h->s_compute);
+    strm(&h->s_compute2);
+    strm(&h->s_out);
+    strm(&h->s_out2);
+    ev(&h->ev_c2);
+    for (int k = 0; k < gkq_handle_s::MAX_CHUNKS; ++k) {
+        ev(&h->ev_in[k]);
+        ev(&h->ev_done[k]);
+    }
+    ok = ok && cudaMallocHost(&h->fixed_pin, 64 * sizeof(double)) == cudaSuccess;
+    if (!ok) {
+        gkq_destroy(h);
         return fail(nullptr, GKQ_ERR_CUDA, "handle allocation failed");
     }
     *out = h;
@@ -418,33 +562,41 @@ int gkq_destroy(gkq_handle_t h) {
         cudaFreeHost(s.ctl_host);
         cudaFree(s.abs0);
         cudaFree(s.list25);
-        for (int k = 0; k < 2; ++k) {
-            cudaFree(s.listLoop[k]);
-            cudaFree(s.listLoop2[k]);
-            cudaFree(s.slab_d[k]);
-            cudaFree(s.slab_w[k]);
-        }
-        if (s.side) cudaStreamDestroy(s.side);
-        if (s.tail) cudaStreamDestroy(s.tail);
-        if (s.ev_first0) cudaEventDestroy(s.ev_first0);
-        if (s.ev_tail) cudaEventDestroy(s.ev_tail);
-        if (s.ev_fork) cudaEventDestroy(s.ev_fork);
-        if (s.ev_join) cudaEventDestroy(s.ev_join);
-        cudaFree(s.stage6);
-        cudaFree(s.stage_ro1);
         cudaFree(s.listS);
         cudaFree(s.listP);
+        cudaFree(s.listLoop[0]);
+        cudaFree(s.listLoop[1]);
+        cudaFree(s.slab_d);
+        cudaFree(s.slab_w);
         cudaFree(s.dev_pts);
         cudaFreeHost(s.host_pts);
+        if (s.side) cudaStreamDestroy(s.side);
+        if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+        if (s.ev_join) cudaEventDestroy(s.ev_join);
+        gkq_handle_s::RecBuf& R = h->rb[c];
+        cudaFree(R.recs);
+        cudaFree(R.rctl);
+        cudaFreeHost(R.rctl_host);
+        cudaFree(R.call_outs);
+        cudaFreeHost(R.call_outs_pin);
+        cudaFree(R.slab_d);
+        cudaFree(R.slab_w);
+        cudaFree(R.patch_dev);
+        cudaFreeHost(R.patch_pin);
+        if (R.ev_bulk) cudaEventDestroy(R.ev_bulk);
+        if (R.ev_tail) cudaEventDestroy(R.ev_tail);
     }
     cudaFree(h->stage_dev);
-    cudaFreeHost(h->stage_pin);
+    cudaFreeHost(h->fixed_pin);
+    for (int k = 0; k < gkq_handle_s::MAX_CHUNKS; ++k) {
+        if (h->ev_in[k]) cudaEventDestroy(h->ev_in[k]);
+        if (h->ev_done[k]) cudaEventDestroy(h->ev_done[k]);
+    }
+    if (h->ev_c2) cudaEventDestroy(h->ev_c2);
     prof_clear(h);
-    for (auto ev : h->prof_pool) cudaEventDestroy(ev);
-    if (h->s_in) cudaStreamDestroy(h->s_in);
-    if (h->s_compute) cudaStreamDestroy(h->s_compute);
-    if (h->s_compute2) cudaStreamDestroy(h->s_compute2);
-    if (h->s_out) cudaStreamDestroy(h->s_out);
+    for (auto e : h->prof_pool) cudaEventDestroy(e);
+    for (cudaStream_t s : {h->s_in, h->s_compute, h->s_compute2, h->s_out, h->s_out2})
+        if (s) cudaStreamDestroy(s);
     delete h;
     return GKQ_OK;
 }
@@ -481,49 +633,46 @@ int gkq_functor_lookup(int dim, const char* name) {
     return GKQ_ERR_INVALID_ARGUMENT;
 }
 
+int gkq_join(gkq_handle_t h, void* stream) {
+    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
+    GKQ_CUDA(h, cudaSetDevice(h->device));
+    int rc = flush_records(h, (cudaStream_t)stream, false);
+    if (rc) return rc;
+    // remainders flushed earlier on other streams: order `stream` behind them too (the flags stay
+    // set: the buffer's next user still has to order its own stream; waiting twice is harmless)
+    for (int c = 0; c < 2; ++c)
+        if (h->rb[c].tail_pending) GKQ_CUDA(h, cudaStreamWaitEvent((cudaStream_t)stream, h->rb[c].ev_tail, 0));
+    return GKQ_OK;
+}
+
 int gkq_set_deferred_join(gkq_handle_t h, int enable) {
     if (!h) return GKQ_ERR_INVALID_ARGUMENT;
     if (!enable && h->deferred) {
-        for (int c = 0; c < 2; ++c)
-            if (h->sc[c].tail_pending) {
-                GKQ_CUDA(h, cudaEventSynchronize(h->sc[c].ev_tail));
-                h->sc[c].tail_pending = false;
-            }
+        // leaving deferred mode: nothing may stay pending
+        int rc = gkq_join(h, nullptr);
+        if (rc) return rc;
+        GKQ_CUDA(h, cudaStreamSynchronize(nullptr));
+        h->rb[0].tail_pending = h->rb[1].tail_pending = false;
     }
     h->deferred = enable != 0;
     return GKQ_OK;
 }
 
-int gkq_join(gkq_handle_t h, void* stream) {
-    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
-    // (the pending flags stay set: the next batch on that scratch context still has to order
-    // its own stream behind the remainder; waiting twice on an event is harmless)
-    for (int c = 0; c < 2; ++c)
-        if (h->sc[c].tail_pending)
-            GKQ_CUDA(h, cudaStreamWaitEvent((cudaStream_t)stream, h->sc[c].ev_tail, 0));
-    return GKQ_OK;
-}
-
 int gkq_sync(gkq_handle_t h, void* stream) {
     if (!h) return GKQ_ERR_INVALID_ARGUMENT;
-    GKQ_CUDA(h, cudaSetDevice(h->device));
-    {
-        int rcj = gkq_join(h, stream);
-        if (rcj) return rcj;
-    }
+    int rc = gkq_join(h, stream);
+    if (rc) return rc;
     GKQ_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
-    h->sc[0].tail_pending = h->sc[1].tail_pending = false;
-    h->cur = 0;
-    if (h->sc[h->cur].ctl_pending) {
-        h->stats.last_survivors_qk25 = h->sc[h->cur].ctl_host->count25;
-        const Control* c = h->sc[h->cur].ctl_host;
+    h->rb[0].tail_pending = h->rb[1].tail_pending = false;
+    gkq_handle_s::Scratch& S = h->sc[0];
+    if (S.ctl_pending) {
+        const Control* c = S.ctl_host;
+        h->stats.last_survivors_qk25 = c->count25;
         h->stats.last_survivors_loop = c->chain[0].countLoop + c->chain[1].countLoop;
-        h->stats.last_survivors_step2 = c->chain[0].countLoop2 + c->chain[1].countLoop2;
-        for (int k = 0; k < 2; ++k) {
-            h->stats.last_chain_loop[k] = c->chain[k].countLoop;
-            h->stats.last_chain_step2[k] = c->chain[k].countLoop2;
-        }
-        h->sc[h->cur].ctl_pending = false;
+        for (int k = 0; k < 2; ++k) h->stats.last_chain_loop[k] = c->chain[k].countLoop;
+        // records of the last profiled batch (profiling flushes after every call)
+        h->stats.last_survivors_step2 = h->rb[h->rb_cur ^ 1].rctl_host->count;
+        S.ctl_pending = false;
     }
     return GKQ_OK;
 }
@@ -575,7 +724,7 @@ int gkq_measure_fp64_peak(gkq_handle_t h, int repeats, double* flops_per_s, doub
     double best = 1e30;
     for (int r = 0; r < repeats + 1; ++r) {  // first trip is a warm-up
         GKQ_CUDA(h, cudaEventRecord(e0, 0));
-        k_dfma_peak<<<grid, BLOCK>>>((double*)h->sc[h->cur].ctl, iters, 1.0 + r);
+        k_dfma_peak<<<grid, BLOCK>>>((double*)h->sc[1].ctl, iters, 1.0 + r);
         GKQ_CUDA(h, cudaEventRecord(e1, 0));
         GKQ_CUDA(h, cudaEventSynchronize(e1));
         float ms = 0;
@@ -593,8 +742,9 @@ int gkq_measure_fp64_peak(gkq_handle_t h, int repeats, double* flops_per_s, doub
 }
 
 // ---- 1-D ----------------------------------------------------------------------------------------
-static int run_qags(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, cudaStream_t st) {
-    // P.worklist / worklist_count may select a subset (AUTO split); n is the upper bound
+// Bulk kernels of one QAGS batch on `st` (chain 1 forks to the context's side stream).  Appends
+// straggler records to the current record buffer; `patch`: host-pipeline mode.
+static int run_qags_bulk(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, cudaStream_t st, bool patch) {
     int rc;
     gkq_handle_s::Scratch& S = h->sc[h->cur];
     if (P.max_evals < 17) {  // qags.rs:86-88 -- only reachable without a worklist split
@@ -603,6 +753,13 @@ static int run_qags(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, cudaS
         k_fill_result<<<grid, BLOCK, 0, st>>>(P.n, P.out, 0.0, F64_MAX, 0u, ST_INSUFFICIENT_ITERATION);
         return launch_check(h, "k_fill_result");
     }
+    unsigned int slot = 0;
+    if ((rc = records_begin(h, st, fid, P, (size_t)P.n, patch, slot))) return rc;
+    gkq_handle_s::RecBuf& R = h->rb[h->rb_cur];
+    P.recs = R.recs;
+    P.rctl = R.rctl;
+    P.call_slot = slot;
+
     const long long nblocks = (P.n + BLOCK - 1) / BLOCK;
     prof_begin(h, "k_qags_init<qk17>", st);
     L.qags_init17(P, (int)nblocks, st);
@@ -613,69 +770,35 @@ static int run_qags(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, cudaS
     long long g25 = (long long)h->sm_count * (h->occ_init25[fid] > 0 ? h->occ_init25[fid] : 1);
     if (g25 > nblocks) g25 = nblocks;
 
-    // slabs of the two persistent kernels
-    if (h->occ_loop[fid] < 0) h->occ_loop[fid] = L.occupancy_loop();
-    const unsigned long long need = (P.max_evals - 17) / 50 + 1;  // qags.rs:98-99, nevals >= 17
-    if (need > (1ull << 26)) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
-    const int cap = (int)need;  // list length never exceeds the reserve request
-    int grid = persistent_grid(h, h->occ_loop[fid], cap, 0, ABLOCK);
-    if (grid < 1) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
-    const long long ablocks = (P.n + ABLOCK - 1) / ABLOCK;
-    if ((long long)grid > ablocks) grid = (int)ablocks;
-    SlabGeom slab[2];
-    for (int c = 0; c < 2; ++c)
-        if ((rc = ensure_slab(h, (unsigned long long)grid * ABLOCK, cap, 0, slab[c], c))) return rc;
-
-    // fork: chain 1 (qk25 pass and what follows it) runs on the side stream.  In profiling mode
+    // fork: chain 1 (qk25 pass + its first steps) runs on the side stream.  In profiling mode
     // everything stays on one stream so that the per-kernel event brackets are clean.
-    const bool serial = h->profiling;
-    const bool defer = h->deferred && !h->profiling;
+    const bool serial = h->profiling || patch;  // (host pipeline: chunks already overlap on two streams)
     if (!serial) {
         GKQ_CUDA(h, cudaEventRecord(S.ev_fork, st));
         GKQ_CUDA(h, cudaStreamWaitEvent(S.side, S.ev_fork, 0));
     }
-    Batch1D Q[2];
     for (int c = 0; c < 2; ++c) {
         cudaStream_t cs = (c == 0 || serial) ? st : S.side;
-        Q[c] = P;
-        Q[c].chain = c;
-        Q[c].slab = slab[c];
+        Batch1D Q = P;
+        Q.chain = c;
         if (c == 1) {
             prof_begin(h, "k_qags_init<qk25>", cs);
-            L.qags_init25(Q[c], (int)g25, cs);
+            L.qags_init25(Q, (int)g25, cs);
             prof_end(h, cs);
             if ((rc = launch_check(h, "k_qags_init<qk25>"))) return rc;
         }
         prof_begin(h, c == 0 ? "k_qags_first[0]" : "k_qags_first[1]", cs);
-        L.qags_first(Q[c], (int)g25, cs);
+        L.qags_first(Q, (int)g25, cs);
         prof_end(h, cs);
         if ((rc = launch_check(h, "k_qags_first"))) return rc;
-        if (defer) {
-            if (c == 0) GKQ_CUDA(h, cudaEventRecord(S.ev_first0, st));
-            continue;  // the persistent kernels are launched below, on the tail stream
-        }
-        prof_begin(h, c == 0 ? "k_adaptive<QAGS>[0]" : "k_adaptive<QAGS>[1]", cs);
-        L.qags_loop(Q[c], grid, cs);
-        prof_end(h, cs);
-        if ((rc = launch_check(h, "k_adaptive<QAGS>"))) return rc;
     }
-    // join the bulk of chain 1 back into the caller's stream
     if (!serial) {
         GKQ_CUDA(h, cudaEventRecord(S.ev_join, S.side));
         GKQ_CUDA(h, cudaStreamWaitEvent(st, S.ev_join, 0));
     }
-    if (defer) {
-        // latency-bound remainder: a few integrals walking many bisection steps.  It runs on the
-        // context's tail stream and overlaps whatever the caller enqueues next; gkq_join / gkq_sync
-        // (or the next batch that needs this scratch context) waits for it.
-        for (int c = 0; c < 2; ++c) {
-            GKQ_CUDA(h, cudaStreamWaitEvent(S.tail, c == 0 ? S.ev_first0 : S.ev_join, 0));
-            L.qags_loop(Q[c], grid, S.tail);
-            if ((rc = launch_check(h, "k_adaptive<QAGS>"))) return rc;
-        }
-        GKQ_CUDA(h, cudaEventRecord(S.ev_tail, S.tail));
-        S.tail_pending = true;
-    }
+    R.ncalls += 1;
+    R.n_bound += (size_t)P.n;
+    if (!patch) GKQ_CUDA(h, cudaEventRecord(R.ev_bulk, st));  // (the host pipeline orders its own flush)
     return GKQ_OK;
 }
 
@@ -698,34 +821,13 @@ static int run_qagp(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, int n
     return launch_check(h, "k_adaptive<QAGP>");
 }
 
-// The batch call proper, on scratch context h->cur.
+// The batch call proper, on bulk scratch context h->cur.  patch / idx_offset: host pipeline.
 static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
                                const double* a, const double* b, int64_t range_stride,
                                const double* params, int64_t param_stride, const int64_t* pts_offsets,
                                const double* pts, double* out_estimate, double* out_delta,
-                               uint32_t* out_nevals, uint32_t* out_status, void* stream);
-
-int gkq_integrate_batch(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
-                        const double* a, const double* b, int64_t range_stride,
-                        const double* params, int64_t param_stride, const int64_t* pts_offsets,
-                        const double* pts, double* out_estimate, double* out_delta,
-                        uint32_t* out_nevals, uint32_t* out_status, void* stream) {
-    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
-    h->cur = 0;
-    if (h->deferred) {
-        h->cur = (int)(h->call_index++ & 1u);
-    }
-    int rc = integrate_batch_ctx(h, cfg, functor_id, n, a, b, range_stride, params, param_stride,
-                                 pts_offsets, pts, out_estimate, out_delta, out_nevals, out_status, stream);
-    h->cur = 0;
-    return rc;
-}
-
-static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
-                               const double* a, const double* b, int64_t range_stride,
-                               const double* params, int64_t param_stride, const int64_t* pts_offsets,
-                               const double* pts, double* out_estimate, double* out_delta,
-                               uint32_t* out_nevals, uint32_t* out_status, void* stream) {
+                               uint32_t* out_nevals, uint32_t* out_status, void* stream, bool patch,
+                               unsigned long long idx_offset, Control* ctl_zeroed = nullptr) {
     if (!h) return GKQ_ERR_INVALID_ARGUMENT;
     if (!cfg) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "cfg is NULL");
     if (functor_id < 0 || functor_id >= F1_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown functor id");
@@ -748,11 +850,7 @@ static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functo
 
     GKQ_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (h->sc[h->cur].tail_pending) {
-        // the deferred remainder of the batch that last used this scratch context must be over
-        GKQ_CUDA(h, cudaStreamWaitEvent(st, h->sc[h->cur].ev_tail, 0));
-        h->sc[h->cur].tail_pending = false;
-    }
+    gkq_handle_s::Scratch& S = h->sc[h->cur];
     if ((rc = ensure_batch_scratch(h, (size_t)n))) return rc;
 
     Batch1D P;
@@ -772,65 +870,85 @@ static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functo
     P.out.delta = out_delta;
     P.out.nevals = out_nevals;
     P.out.status = out_status;
-    P.ctl = h->sc[h->cur].ctl;
-    P.abs0 = h->sc[h->cur].abs0;
-    P.list25 = h->sc[h->cur].list25;
-    for (int c = 0; c < 2; ++c) {
-        P.listLoop[c] = h->sc[h->cur].listLoop[c];
-        P.listLoop2[c] = h->sc[h->cur].listLoop2[c];
-    }
-    P.stage = h->sc[h->cur].stage6;
-    P.stage_ro1 = h->sc[h->cur].stage_ro1;
+    P.ctl = ctl_zeroed ? ctl_zeroed : S.ctl;
+    P.abs0 = S.abs0;
+    P.list25 = S.list25;
+    P.listLoop[0] = S.listLoop[0];
+    P.listLoop[1] = S.listLoop[1];
+    P.idx_offset = idx_offset;
 
     if (h->profiling) prof_clear(h);
-    GKQ_CUDA(h, cudaMemsetAsync(h->sc[h->cur].ctl, 0, sizeof(Control), st));
+    if (!ctl_zeroed) GKQ_CUDA(h, cudaMemsetAsync(S.ctl, 0, sizeof(Control), st));
     const Launch1D& L = h->l1[functor_id];
     h->stats.batches += 1;
     h->stats.integrals += (uint64_t)n;
 
+    bool did_qags = false;
     if (!pts_offsets) {
         const bool use_qags = cfg->algo == GKQ_ALGO_QAGS || (cfg->algo == GKQ_ALGO_AUTO && cfg->npoints == 0);
         if (use_qags) {
-            rc = run_qags(h, L, functor_id, P, st);
+            rc = run_qags_bulk(h, L, functor_id, P, st, patch);
+            did_qags = true;
         } else {
             if ((rc = upload_shared_points(h, cfg->points, (size_t)cfg->npoints, st))) return rc;
-            P.pts = h->sc[h->cur].dev_pts;
+            P.pts = S.dev_pts;
             P.npts_shared = (int)cfg->npoints;
             rc = run_qagp(h, L, functor_id, P, (int)cfg->npoints, st);
         }
     } else if (cfg->algo == GKQ_ALGO_QAGS) {
-        rc = run_qags(h, L, functor_id, P, st);  // explicit QAGS ignores points
+        rc = run_qags_bulk(h, L, functor_id, P, st, patch);  // explicit QAGS ignores points
+        did_qags = true;
     } else {
         // CSR points: split for AUTO and find the largest point count (one small sync)
         const int grid = (int)((n + BLOCK - 1) / BLOCK);
         const int mode = cfg->algo == GKQ_ALGO_AUTO ? 0 : 1;
-        k_split_auto<<<grid, BLOCK, 0, st>>>(n, (const long long*)pts_offsets, h->sc[h->cur].listS, h->sc[h->cur].listP, h->sc[h->cur].ctl, mode);
+        k_split_auto<<<grid, BLOCK, 0, st>>>(n, (const long long*)pts_offsets, S.listS, S.listP, S.ctl, mode);
         if ((rc = launch_check(h, "k_split_auto"))) return rc;
-        GKQ_CUDA(h, cudaMemcpyAsync(h->sc[h->cur].ctl_host, h->sc[h->cur].ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
+        GKQ_CUDA(h, cudaMemcpyAsync(S.ctl_host, S.ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
         GKQ_CUDA(h, cudaStreamSynchronize(st));
-        const int npts_max = (int)h->sc[h->cur].ctl_host->max_pts;
+        const int npts_max = (int)S.ctl_host->max_pts;
         P.pts_offsets = (const long long*)pts_offsets;
         P.pts = pts;
         if (mode == 0) {
-            Batch1D PS = P;
-            PS.worklist = h->sc[h->cur].listS;
-            PS.worklist_count = &h->sc[h->cur].ctl->countS;
-            if (h->sc[h->cur].ctl_host->countS > 0 && (rc = run_qags(h, L, functor_id, PS, st))) return rc;
-            Batch1D PP = P;
-            PP.worklist = h->sc[h->cur].listP;
-            PP.worklist_count = &h->sc[h->cur].ctl->countP;
-            if (h->sc[h->cur].ctl_host->countP > 0) rc = run_qagp(h, L, functor_id, PP, npts_max, st);
+            if (S.ctl_host->countS > 0) {
+                Batch1D PS = P;
+                PS.worklist = S.listS;
+                PS.worklist_count = &S.ctl->countS;
+                if ((rc = run_qags_bulk(h, L, functor_id, PS, st, patch))) return rc;
+                did_qags = true;
+            }
+            if (S.ctl_host->countP > 0) {
+                Batch1D PP = P;
+                PP.worklist = S.listP;
+                PP.worklist_count = &S.ctl->countP;
+                rc = run_qagp(h, L, functor_id, PP, npts_max, st);
+            }
         } else {
             rc = run_qagp(h, L, functor_id, P, npts_max, st);
         }
     }
     if (rc) return rc;
+    // ordered mode (the default): finish the stragglers of this batch right away on its stream
+    if (did_qags && !patch && (!h->deferred || h->profiling))
+        if ((rc = flush_records(h, st, false))) return rc;
     // worklist sizes for gkq_get_stats: read back only in profiling mode (keeps the hot call lean)
     if (h->profiling) {
-        GKQ_CUDA(h, cudaMemcpyAsync(h->sc[h->cur].ctl_host, h->sc[h->cur].ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
-        h->sc[h->cur].ctl_pending = true;
+        GKQ_CUDA(h, cudaMemcpyAsync(S.ctl_host, S.ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
+        S.ctl_pending = true;
     }
     return GKQ_OK;
+}
+
+int gkq_integrate_batch(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
+                        const double* a, const double* b, int64_t range_stride,
+                        const double* params, int64_t param_stride, const int64_t* pts_offsets,
+                        const double* pts, double* out_estimate, double* out_delta,
+                        uint32_t* out_nevals, uint32_t* out_status, void* stream) {
+    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
+    h->cur = 0;
+    return integrate_batch_ctx(h, cfg, functor_id, n, a, b, range_stride, params, param_stride,
+                               pts_offsets, pts, out_estimate, out_delta, out_nevals, out_status, stream,
+                               false, 0ull);
 }
 
 int gkq_qk_batch(gkq_handle_t h, int rule, int functor_id, int64_t n, const double* a,
@@ -877,14 +995,20 @@ int gkq_functor_eval_batch(gkq_handle_t h, int functor_id, int64_t n, const doub
     return launch_check(h, "k_eval");
 }
 
-// Host-pointer entry: chunked H2D -> kernels -> D2H pipeline.  Chunks alternate between the two
-// scratch contexts / compute streams so that the latency-bound tail kernels of one chunk overlap
-// the bulk kernels of the next; copies run on their own streams in both directions at once.
+// Host-pointer entry: H2D -> bulk kernels -> D2H pipeline over chunks of the batch.
+//   * the whole batch is staged on the device (40 B per integral), so all H2D copies are enqueued
+//     first and run back to back; chunk sizes ramp up (32k, 64k, ... 256k) so the first results
+//     leave early and later copies are large;
+//   * chunks alternate between two compute streams / bulk scratch contexts and two D2H streams;
+//     the bulk results of a chunk leave as soon as its bulk kernels end;
+//   * the stragglers of ALL chunks are finished by ONE launch of the persistent kernel at the end;
+//     their results reach the host as a compact patch that the CPU applies.
 int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
                              const double* a, const double* b, int64_t range_stride,
                              const double* params, int64_t param_stride,
                              const int64_t* pts_offsets, const double* pts, double* out_estimate,
                              double* out_delta, uint32_t* out_nevals, uint32_t* out_status) {
+    (void)pts;
     if (!h) return GKQ_ERR_INVALID_ARGUMENT;
     if (!cfg) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "cfg is NULL");
     if (functor_id < 0 || functor_id >= F1_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown functor id");
@@ -897,111 +1021,206 @@ int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_
     const int np = F1_TABLE[functor_id].nparams;
     if (np > 0 && !params) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "params is NULL");
     const int np_batch = param_stride ? np : 0;  // per-integral parameter rows
+    int rc;
+    // records pending from deferred device-entry calls are finished first (they own the buffers)
+    if (h->rb[0].ncalls || h->rb[1].ncalls || h->rb[0].tail_pending || h->rb[1].tail_pending) {
+        if ((rc = gkq_join(h, h->s_compute))) return rc;
+        GKQ_CUDA(h, cudaStreamSynchronize(h->s_compute));
+        h->rb[0].tail_pending = h->rb[1].tail_pending = false;
+    }
 
-    // device staging for one chunk of C integrals (ring of NBUF buffers):
-    //   a[C] b[C] (when per-integral) | params[np][C] | est[C] delta[C] nevals[C] status[C]
-    constexpr int NBUF = 4;
-    int64_t CH = 1 << 17;
-    if (const char* env = getenv("GKQ_HOST_CHUNK")) {  // tuning knob (integrals per pipeline chunk)
+    // chunk schedule
+    constexpr int MAXC = gkq_handle_s::MAX_CHUNKS;
+    int64_t CH = 1 << 18, C0 = 1 << 16;
+    if (const char* env = getenv("GKQ_HOST_CHUNK")) {  // tuning knobs (integrals per chunk)
         long long v = atoll(env);
         if (v >= 1024) CH = v;
     }
-    const int64_t C = n < CH ? n : CH;
-    const size_t in_doubles = (size_t)((range_stride ? 2 : 0) + np_batch) * (size_t)C;
-    const size_t chunk_bytes = ((in_doubles * 8 + (size_t)C * (8 + 8 + 4 + 4) + 255) / 256) * 256;
-    const size_t fixed_bytes = 64 * 8;  // shared range / shared params
-    int rc;
-    {
-        size_t want = NBUF * chunk_bytes + fixed_bytes;
-        if (want > h->stage_bytes) {
-            if (h->stage_dev) GKQ_CUDA(h, cudaFree(h->stage_dev));
-            h->stage_dev = nullptr;
-            h->stats.scratch_bytes -= h->stage_bytes;
-            h->stage_bytes = 0;
-            GKQ_CUDA(h, cudaMalloc(&h->stage_dev, want));
-            h->stage_bytes = want;
-            h->stats.scratch_bytes += want;
-        }
+    if (const char* env = getenv("GKQ_HOST_CHUNK0")) {
+        long long v = atoll(env);
+        if (v >= 1024) C0 = v;
     }
-    // shared (stride-0) inputs live at the front of the staging area
+    if (C0 > CH) C0 = CH;
+    while ((n + CH - 1) / CH + 8 > MAXC) CH *= 2;
+    int64_t c_off[MAXC], c_len[MAXC];
+    int nchunks = 0;
+    for (int64_t off = 0, next = C0; off < n; ++nchunks) {
+        const int64_t m = (n - off) < next ? (n - off) : next;
+        c_off[nchunks] = off;
+        c_len[nchunks] = m;
+        off += m;
+        next = next * 2 > CH ? CH : next * 2;
+    }
+
+    // device staging of the whole batch: [64 shared doubles | nchunks Control blocks |
+    //   a[n] b[n] (when per-integral) | params[np][n] | est[n] | delta[n] | nevals[n] | status[n]]
+    const size_t N = (size_t)n;
+    const size_t fixed_bytes = 64 * 8, ctl_bytes = sizeof(Control) * MAXC;
+    const size_t in_doubles = (size_t)((range_stride ? 2 : 0) + np_batch) * N;
+    const size_t want = fixed_bytes + ctl_bytes + in_doubles * 8 + N * 24 + 256;
+    if (want > h->stage_bytes) {
+        if (h->stage_dev) GKQ_CUDA(h, cudaFree(h->stage_dev));
+        h->stage_dev = nullptr;
+        h->stats.scratch_bytes -= h->stage_bytes;
+        h->stage_bytes = 0;
+        GKQ_CUDA(h, cudaMalloc(&h->stage_dev, want));
+        h->stage_bytes = want;
+        h->stats.scratch_bytes += want;
+    }
     double* d_fixed = (double*)h->stage_dev;
-    double fixed_host[64];
-    memset(fixed_host, 0, sizeof fixed_host);
+    Control* d_ctl = (Control*)(h->stage_dev + fixed_bytes);
+    double* d_in = (double*)(h->stage_dev + fixed_bytes + ctl_bytes);
+    double* d_a = range_stride ? d_in : d_fixed;
+    double* d_b = range_stride ? d_in + N : d_fixed + 1;
+    double* d_par = param_stride ? d_in + (range_stride ? 2 * N : 0) : d_fixed + 2;
+    double* d_est = d_in + in_doubles;
+    double* d_dlt = d_est + N;
+    uint32_t* d_nev = (uint32_t*)(d_dlt + N);
+    uint32_t* d_st = d_nev + N;
+
+    // GKQ_HOST_TRACE=1: per-chunk timeline (timing events) printed to stderr -- tuning aid
+    const bool trace = getenv("GKQ_HOST_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t s) {
+        if (!trace) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, s);
+        tev.push_back(ev);
+    };
+    mark(h->s_in);
+
+    // ---- phase 1: every H2D copy, back to back on the copy-in stream --------------------------
+    // shared (stride-0) inputs go through a pinned bounce buffer (the previous host call has
+    // fully synchronised, so it is free)
+    memset(h->fixed_pin, 0, 64 * sizeof(double));
     if (!range_stride) {
-        fixed_host[0] = a[0];
-        fixed_host[1] = b[0];
+        h->fixed_pin[0] = a[0];
+        h->fixed_pin[1] = b[0];
     }
     if (!param_stride)
-        for (int k = 0; k < np; ++k) fixed_host[2 + k] = params[k];
-    GKQ_CUDA(h, cudaMemcpyAsync(d_fixed, fixed_host, sizeof fixed_host, cudaMemcpyHostToDevice, h->s_in));
-    GKQ_CUDA(h, cudaStreamSynchronize(h->s_in));  // fixed_host is a stack buffer
-
-    cudaEvent_t ev_in[NBUF], ev_done[NBUF], ev_out[NBUF];
-    for (int k = 0; k < NBUF; ++k) {
-        GKQ_CUDA(h, cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
-        GKQ_CUDA(h, cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
-        GKQ_CUDA(h, cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
+        for (int k = 0; k < np; ++k) h->fixed_pin[2 + k] = params[k];
+    GKQ_CUDA(h, cudaMemcpyAsync(d_fixed, h->fixed_pin, 64 * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
+    GKQ_CUDA(h, cudaMemsetAsync(d_ctl, 0, sizeof(Control) * (size_t)nchunks, h->s_in));
+    const bool is_qags = cfg->algo == GKQ_ALGO_QAGS || (cfg->algo == GKQ_ALGO_AUTO && cfg->npoints == 0);
+    const int rbi = h->rb_cur;
+    if (is_qags) {
+        // the whole call appends to ONE record buffer, reset here (before any chunk can append)
+        gkq_handle_s::RecBuf& R0 = h->rb[rbi];
+        if (N > R0.cap)
+            if ((rc = grow(h, R0.recs, R0.cap, N))) return rc;
+        GKQ_CUDA(h, cudaMemsetAsync(R0.rctl, 0, sizeof(RecCtl), h->s_in));
     }
-    rc = GKQ_OK;
-    int64_t chunk_idx = 0;
-    for (int64_t off = 0; off < n && rc == GKQ_OK; off += C, ++chunk_idx) {
-        const int64_t m = (n - off) < C ? (n - off) : C;
-        const int buf = (int)(chunk_idx % NBUF);
-        const int ctx = (int)(chunk_idx & 1);
-        cudaStream_t sc = ctx ? h->s_compute2 : h->s_compute;
-        char* base = h->stage_dev + fixed_bytes + (size_t)buf * chunk_bytes;
-        double* d_in = (double*)base;
-        double* d_a = range_stride ? d_in : d_fixed;
-        double* d_b = range_stride ? d_in + C : d_fixed + 1;
-        double* d_par = param_stride ? d_in + (range_stride ? 2 * C : 0) : d_fixed + 2;
-        double* d_est = (double*)(base + in_doubles * 8);
-        double* d_dlt = d_est + C;
-        uint32_t* d_nev = (uint32_t*)(d_dlt + C);
-        uint32_t* d_st = d_nev + C;
-
-        // the staging buffer is free once the D2H copies of chunk_idx - NBUF have completed
-        if (chunk_idx >= NBUF) GKQ_CUDA(h, cudaStreamWaitEvent(h->s_in, ev_out[buf], 0));
+    for (int c = 0; c < nchunks; ++c) {
+        const int64_t off = c_off[c], m = c_len[c];
+        mark(h->s_in);
         if (range_stride) {
-            GKQ_CUDA(h, cudaMemcpyAsync(d_a, a + off, (size_t)m * 8, cudaMemcpyHostToDevice, h->s_in));
-            GKQ_CUDA(h, cudaMemcpyAsync(d_b, b + off, (size_t)m * 8, cudaMemcpyHostToDevice, h->s_in));
+            GKQ_CUDA(h, cudaMemcpyAsync(d_a + off, a + off, (size_t)m * 8, cudaMemcpyHostToDevice, h->s_in));
+            GKQ_CUDA(h, cudaMemcpyAsync(d_b + off, b + off, (size_t)m * 8, cudaMemcpyHostToDevice, h->s_in));
         }
         for (int k = 0; k < np_batch; ++k)
-            GKQ_CUDA(h, cudaMemcpyAsync(d_par + (size_t)k * C, params + (size_t)k * param_stride + off,
+            GKQ_CUDA(h, cudaMemcpyAsync(d_par + (size_t)k * N + off, params + (size_t)k * param_stride + off,
                                         (size_t)m * 8, cudaMemcpyHostToDevice, h->s_in));
-        GKQ_CUDA(h, cudaEventRecord(ev_in[buf], h->s_in));
+        GKQ_CUDA(h, cudaEventRecord(h->ev_in[c], h->s_in));
+        mark(h->s_in);
+    }
 
-        GKQ_CUDA(h, cudaStreamWaitEvent(sc, ev_in[buf], 0));
+    // ---- phase 2: bulk kernels + result copies, chunk by chunk ------------------------------------
+    rc = GKQ_OK;
+    h->host_records_primed = is_qags;  // records_begin must not reset the counters again
+    for (int c = 0; c < nchunks && rc == GKQ_OK; ++c) {
+        const int64_t off = c_off[c], m = c_len[c];
+        const int ctx = c & 1;
+        cudaStream_t sc = ctx ? h->s_compute2 : h->s_compute;
+        cudaStream_t so = ctx ? h->s_out2 : h->s_out;
+        GKQ_CUDA(h, cudaStreamWaitEvent(sc, h->ev_in[c], 0));
+        mark(sc);
         h->cur = ctx;
-        const bool was_deferred = h->deferred;
-        h->deferred = true;  // chunks are independent batches: their remainders overlap the next chunk
-        rc = integrate_batch_ctx(h, cfg, functor_id, m, d_a, d_b, range_stride, d_par,
-                                 param_stride ? C : 0, nullptr, nullptr, d_est, d_dlt, d_nev, d_st, sc);
-        h->deferred = was_deferred;
+        rc = integrate_batch_ctx(h, cfg, functor_id, m, range_stride ? d_a + off : d_a,
+                                 range_stride ? d_b + off : d_b, range_stride,
+                                 param_stride ? d_par + off : d_par, param_stride ? (int64_t)N : 0, nullptr,
+                                 nullptr, d_est + off, d_dlt + off, d_nev + off, d_st + off, sc,
+                                 /*patch=*/true, (unsigned long long)off, d_ctl + c);
         if (rc) break;
-        GKQ_CUDA(h, cudaEventRecord(ev_done[buf], sc));
+        GKQ_CUDA(h, cudaEventRecord(h->ev_done[c], sc));
+        mark(sc);
+        // the bulk results leave right away
+        GKQ_CUDA(h, cudaStreamWaitEvent(so, h->ev_done[c], 0));
+        mark(so);
+        GKQ_CUDA(h, cudaMemcpyAsync(out_estimate + off, d_est + off, (size_t)m * 8, cudaMemcpyDeviceToHost, so));
+        GKQ_CUDA(h, cudaMemcpyAsync(out_delta + off, d_dlt + off, (size_t)m * 8, cudaMemcpyDeviceToHost, so));
+        GKQ_CUDA(h, cudaMemcpyAsync(out_nevals + off, d_nev + off, (size_t)m * 4, cudaMemcpyDeviceToHost, so));
+        GKQ_CUDA(h, cudaMemcpyAsync(out_status + off, d_st + off, (size_t)m * 4, cudaMemcpyDeviceToHost, so));
+        mark(so);
+    }
+    h->host_records_primed = false;
+    h->cur = 0;
 
-        GKQ_CUDA(h, cudaStreamWaitEvent(h->s_out, ev_done[buf], 0));
-        if (h->sc[ctx].tail_pending) GKQ_CUDA(h, cudaStreamWaitEvent(h->s_out, h->sc[ctx].ev_tail, 0));
-        GKQ_CUDA(h, cudaMemcpyAsync(out_estimate + off, d_est, (size_t)m * 8, cudaMemcpyDeviceToHost, h->s_out));
-        GKQ_CUDA(h, cudaMemcpyAsync(out_delta + off, d_dlt, (size_t)m * 8, cudaMemcpyDeviceToHost, h->s_out));
-        GKQ_CUDA(h, cudaMemcpyAsync(out_nevals + off, d_nev, (size_t)m * 4, cudaMemcpyDeviceToHost, h->s_out));
-        GKQ_CUDA(h, cudaMemcpyAsync(out_status + off, d_st, (size_t)m * 4, cudaMemcpyDeviceToHost, h->s_out));
-        GKQ_CUDA(h, cudaEventRecord(ev_out[buf], h->s_out));
+    // ---- phase 3: the stragglers of every chunk: one launch, results into the patch ---------------
+    unsigned long long nrec = 0;
+    gkq_handle_s::RecBuf& R = h->rb[rbi];
+    const bool have_records = rc == GKQ_OK && is_qags && h->rb_cur == rbi && R.ncalls > 0;
+    if (have_records) {
+        GKQ_CUDA(h, cudaEventRecord(h->ev_c2, h->s_compute2));
+        GKQ_CUDA(h, cudaStreamWaitEvent(h->s_compute, h->ev_c2, 0));
+        if ((rc = flush_records(h, h->s_compute, true)) == GKQ_OK) {
+            GKQ_CUDA(h, cudaMemcpyAsync(R.rctl_host, R.rctl, sizeof(RecCtl), cudaMemcpyDeviceToHost, h->s_compute));
+            // most batches leave a handful of stragglers: fetch a first slice together with the count
+            const size_t first = R.patch_cap < 4096 ? R.patch_cap : 4096;
+            PatchView dv = patch_view(R.patch_dev, R.patch_cap), hv = patch_view(R.patch_pin, R.patch_cap);
+            auto fetch = [&](size_t lo, size_t cnt) -> cudaError_t {
+                cudaError_t e;
+                if ((e = cudaMemcpyAsync(hv.idx + lo, dv.idx + lo, cnt * 8, cudaMemcpyDeviceToHost, h->s_compute))) return e;
+                if ((e = cudaMemcpyAsync(hv.est + lo, dv.est + lo, cnt * 8, cudaMemcpyDeviceToHost, h->s_compute))) return e;
+                if ((e = cudaMemcpyAsync(hv.dlt + lo, dv.dlt + lo, cnt * 8, cudaMemcpyDeviceToHost, h->s_compute))) return e;
+                if ((e = cudaMemcpyAsync(hv.nev + lo, dv.nev + lo, cnt * 4, cudaMemcpyDeviceToHost, h->s_compute))) return e;
+                return cudaMemcpyAsync(hv.st + lo, dv.st + lo, cnt * 4, cudaMemcpyDeviceToHost, h->s_compute);
+            };
+            GKQ_CUDA(h, fetch(0, first));
+            GKQ_CUDA(h, cudaStreamSynchronize(h->s_compute));
+            nrec = R.rctl_host->count;
+            if (nrec > first) {
+                GKQ_CUDA(h, fetch(first, (size_t)nrec - first));
+                GKQ_CUDA(h, cudaStreamSynchronize(h->s_compute));
+            }
+            R.tail_pending = false;
+        }
     }
     cudaError_t e1 = cudaStreamSynchronize(h->s_in);
     cudaError_t e2 = cudaStreamSynchronize(h->s_compute);
     cudaError_t e4 = cudaStreamSynchronize(h->s_compute2);
     cudaError_t e3 = cudaStreamSynchronize(h->s_out);
-    h->sc[0].tail_pending = h->sc[1].tail_pending = false;  // s_out waited for every remainder
-    for (int k = 0; k < NBUF; ++k) {
-        cudaEventDestroy(ev_in[k]);
-        cudaEventDestroy(ev_done[k]);
-        cudaEventDestroy(ev_out[k]);
-    }
-    h->cur = 0;
+    if (e3 == cudaSuccess) e3 = cudaStreamSynchronize(h->s_out2);
     if (rc) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess)
         return fail(h, GKQ_ERR_CUDA, "host pipeline failed: a stream reported an error");
+    if (have_records) {
+        PatchView hv = patch_view(R.patch_pin, R.patch_cap);
+        for (unsigned long long k = 0; k < nrec; ++k) {
+            const unsigned long long i = hv.idx[k];
+            out_estimate[i] = hv.est[k];
+            out_delta[i] = hv.dlt[k];
+            out_nevals[i] = hv.nev[k];
+            out_status[i] = hv.st[k];
+        }
+    }
+    if (trace && !tev.empty()) {
+        // events: [0] start; per chunk h2d_begin, h2d_end (phase 1); then per chunk compute_begin,
+        // compute_end, d2h_begin, d2h_end (phase 2)
+        auto us = [&](size_t k) {
+            float t = 0;
+            cudaEventElapsedTime(&t, tev[0], tev[k]);
+            return t * 1e3f;
+        };
+        for (int c = 0; c < nchunks; ++c) {
+            const size_t p1 = 1 + 2 * (size_t)c, p2 = 1 + 2 * (size_t)nchunks + 4 * (size_t)c;
+            if (p2 + 3 >= tev.size()) break;
+            fprintf(stderr, "chunk %d (%lld): h2d %.0f-%.0f  compute %.0f-%.0f  d2h %.0f-%.0f us\n", c,
+                    (long long)c_len[c], us(p1), us(p1 + 1), us(p2), us(p2 + 1), us(p2 + 2), us(p2 + 3));
+        }
+        fprintf(stderr, "stragglers patched on the host: %llu\n", nrec);
+        for (auto ev : tev) cudaEventDestroy(ev);
+    }
     return GKQ_OK;
 }
 
@@ -1036,6 +1255,7 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
     GKQ_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     h->cur = 0;
+    gkq_handle_s::Scratch& S = h->sc[0];
     if ((rc = ensure_batch_scratch(h, (size_t)n))) return rc;
 
     Batch2D P;
@@ -1058,9 +1278,9 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
     P.out.delta = out_delta;
     P.out.nevals = out_nevals;
     P.out.status = out_status;
-    P.ctl = h->sc[h->cur].ctl;
+    P.ctl = S.ctl;
     if (h->profiling) prof_clear(h);
-    GKQ_CUDA(h, cudaMemsetAsync(h->sc[h->cur].ctl, 0, sizeof(Control), st));
+    GKQ_CUDA(h, cudaMemsetAsync(S.ctl, 0, sizeof(Control), st));
     h->stats.batches += 1;
     h->stats.integrals += (uint64_t)n;
 
@@ -1075,7 +1295,7 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
             P.npts = npts_max;
             if (npts_max > 0) {
                 if ((rc = upload_shared_points(h, cfg->points, (size_t)(2 * npts_max), st))) return rc;
-                P.pts_xy = h->sc[h->cur].dev_pts;
+                P.pts_xy = S.dev_pts;
             }
         }
     } else if (cfg->algo == GKQ_ALGO_QAGS) {
@@ -1083,17 +1303,17 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
     } else {
         const int grid = (int)((n + BLOCK - 1) / BLOCK);
         const int mode = cfg->algo == GKQ_ALGO_AUTO ? 0 : 1;
-        k_split_auto<<<grid, BLOCK, 0, st>>>(n, (const long long*)pts_offsets, h->sc[h->cur].listS, h->sc[h->cur].listP, h->sc[h->cur].ctl, mode);
+        k_split_auto<<<grid, BLOCK, 0, st>>>(n, (const long long*)pts_offsets, S.listS, S.listP, S.ctl, mode);
         if ((rc = launch_check(h, "k_split_auto"))) return rc;
-        GKQ_CUDA(h, cudaMemcpyAsync(h->sc[h->cur].ctl_host, h->sc[h->cur].ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
+        GKQ_CUDA(h, cudaMemcpyAsync(S.ctl_host, S.ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
         GKQ_CUDA(h, cudaStreamSynchronize(st));
-        npts_max = (int)h->sc[h->cur].ctl_host->max_pts;
+        npts_max = (int)S.ctl_host->max_pts;
         P.pts_offsets = (const long long*)pts_offsets;
         P.pts_xy = pts_xy;
         if (mode == 0) {
             split = true;
-            run_s = h->sc[h->cur].ctl_host->countS > 0;
-            run_p = h->sc[h->cur].ctl_host->countP > 0;
+            run_s = S.ctl_host->countS > 0;
+            run_p = S.ctl_host->countP > 0;
         } else {
             run_p = true;
         }
@@ -1110,8 +1330,8 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
             Q.npts_max = 0;
         }
         if (split) {
-            Q.worklist = alg == 0 ? h->sc[h->cur].listS : h->sc[h->cur].listP;
-            Q.worklist_count = alg == 0 ? &h->sc[h->cur].ctl->countS : &h->sc[h->cur].ctl->countP;
+            Q.worklist = alg == 0 ? S.listS : S.listP;
+            Q.worklist_count = alg == 0 ? &S.ctl->countS : &S.ctl->countP;
         }
         const Launch2D& L = h->l2[functor2_id];
         if (h->occ_2d[functor2_id][alg] < 0) h->occ_2d[functor2_id][alg] = L.occupancy[alg]();

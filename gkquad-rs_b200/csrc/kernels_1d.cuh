@@ -41,9 +41,7 @@ constexpr int COOP_MAX_LIVE = GKQ_COOP_MAX_LIVE;
 // Each chain has its own worklists, counters and slab, so the two run on concurrent streams.
 struct ChainCtl {
     unsigned long long countLoop;   // entries in listLoop[c]  (integrals entering the main loop)
-    unsigned long long countLoop2;  // entries in listLoop2[c] (unfinished after the first step)
-    unsigned long long headLoop;    // queue head of the chain's persistent kernel
-    unsigned long long pad;
+    unsigned long long pad[3];
 };
 struct Control {
     ChainCtl chain[2];
@@ -56,6 +54,58 @@ struct Control {
     unsigned long long pad[2];
 };
 
+// An integral that is still unfinished after its first bisection step: a self-contained record
+// (inputs + the state qags.rs leaves behind after iteration 1).  Records of one or many batches
+// accumulate in a handle-owned buffer and are finished by ONE launch of the persistent kernel
+// -- right away (ordered mode), at gkq_join (deferred mode: the remainders of many batches
+// share a launch), or at the end of a host-pipeline call.
+struct alignas(16) StragglerRec {
+    double a, b;                   // range as given (the kernel re-applies the infinite-range map)
+    double p[MAX_PARAMS];
+    double est0, delta0, abs0;     // result0 of the initial passes
+    double e1, d1, e2, d2;         // the two halves of the first bisection
+    double area, errsum;
+    unsigned long long idx;        // position in the owning call's output arrays
+    unsigned int nevals;           // evaluations so far (result0 + 50)
+    unsigned int ro1;              // roundoff_type1 after the first step
+    unsigned int call;             // slot of the owning call in the outputs table
+    unsigned int pad_;
+};
+struct RecCtl {
+    unsigned long long count;  // records appended
+    unsigned long long head;   // queue head of the persistent kernel that finishes them
+    unsigned long long pad[2];
+};
+// Where finished stragglers go: the owning call's output arrays (device entry), or a compact
+// patch that the host applies (host pipeline).
+struct PatchView {
+    unsigned long long* idx;
+    double* est;
+    double* dlt;
+    unsigned int* nev;
+    unsigned int* st;
+};
+
+// Sink of the QAGS persistent kernel: slot = record index.
+struct RecordSink {
+    const StragglerRec* recs;
+    const Outputs* call_outs;
+    PatchView patch;
+    GKQ_DEV void put(long long slot, double est, double dlt, uint32_t nev, uint32_t st) const {
+        const StragglerRec& r = recs[slot];
+        if (patch.idx) {
+            patch.idx[slot] = r.idx;
+            patch.est[slot] = est;
+            patch.dlt[slot] = dlt;
+            patch.nev[slot] = nev;
+            patch.st[slot] = st;
+        } else {
+            write_result(call_outs[r.call], (long long)r.idx, est, dlt, nev, st);
+        }
+    }
+};
+template <bool QAGP> struct SinkFor { using type = GlobalSink; };
+template <> struct SinkFor<false> { using type = RecordSink; };
 struct Batch1D {
     long long n;
     const double* a;
@@ -75,15 +125,25 @@ struct Batch1D {
     double* abs0;               // [n] absvalue of the initial rule (qags.rs:315-376 returns it)
     unsigned int* list25;       // [n]
     unsigned int* listLoop[2];  // [n] per chain: integrals entering the main loop
-    unsigned int* listLoop2[2]; // [n] per chain: survivors of the first bisection step
-    int chain;                  // which chain this launch serves (k_qags_first / k_adaptive)
-    double* stage;              // [6][n] state parked between k_qags_first and k_adaptive:
-                                //        e1, d1, e2, d2 (the two halves), area, errsum
-    unsigned char* stage_ro1;   // [n] roundoff_type1 counter after the first step
+    int chain;                  // which chain this launch serves (k_qags_first)
+    // straggler records (written by k_qags_first, finished by k_adaptive<.., false>)
+    StragglerRec* recs;
+    RecCtl* rctl;
+    unsigned int call_slot;         // slot of this call in `call_outs`
+    unsigned long long idx_offset;  // added to the integral index stored in a record (host pipeline chunks)
+    const Outputs* call_outs;       // [slots] output arrays of the calls that own the records
+    PatchView patch;                // patch.idx != nullptr: finished stragglers go to the patch
     const unsigned int* worklist;        // optional subset of integrals (AUTO split) or nullptr
     const unsigned long long* worklist_count;  // device count for `worklist`
     SlabGeom slab;  // of the chain being launched
 };
+
+GKQ_DEV void init_sink(GlobalSink& s, const Batch1D& P) { s.O = P.out; }
+GKQ_DEV void init_sink(RecordSink& s, const Batch1D& P) {
+    s.recs = P.recs;
+    s.call_outs = P.call_outs;
+    s.patch = P.patch;
+}
 
 template <class F>
 GKQ_DEV void load_functor(F& f, const Batch1D& P, long long i, int nparams) {
@@ -198,6 +258,7 @@ __global__ void __launch_bounds__(BLOCK) k_qags_first(const Batch1D P) {
          k += (long long)gridDim.x * BLOCK) {
         bool survive = false;
         long long i = 0;
+        StragglerRec rec;
         if (k < total) {
             i = (long long)P.listLoop[P.chain][k];
             Wrapped<F> g;
@@ -240,19 +301,38 @@ __global__ void __launch_bounds__(BLOCK) k_qags_first(const Batch1D P) {
                         write_result(P.out, i, (0.0 + E0) + E1, errsum, nevals, error);
                     } else {
                         survive = true;
-                        P.stage[i] = q1.estimate;
-                        P.stage[P.n + i] = q1.delta;
-                        P.stage[2 * P.n + i] = q2.estimate;
-                        P.stage[3 * P.n + i] = q2.delta;
-                        P.stage[4 * P.n + i] = area;
-                        P.stage[5 * P.n + i] = errsum;
-                        P.stage_ro1[i] = (unsigned char)ro1;
-                        P.out.nevals[i] = nevals;
+                        rec.a = P.a[i * P.range_stride];
+                        rec.b = P.b[i * P.range_stride];
+#pragma unroll
+                        for (int q = 0; q < MAX_PARAMS; ++q) rec.p[q] = g.f.p[q];
+                        rec.est0 = est0;
+                        rec.delta0 = delta0;
+                        rec.abs0 = P.abs0[i];
+                        rec.e1 = q1.estimate;
+                        rec.d1 = q1.delta;
+                        rec.e2 = q2.estimate;
+                        rec.d2 = q2.delta;
+                        rec.area = area;
+                        rec.errsum = errsum;
+                        rec.idx = P.idx_offset + (unsigned long long)i;
+                        rec.nevals = nevals;
+                        rec.ro1 = (unsigned int)ro1;
+                        rec.call = P.call_slot;
+                        rec.pad_ = 0;
                     }
                 }
             }
         }
-        list_append(survive, (unsigned int)i, P.listLoop2[P.chain], &P.ctl->chain[P.chain].countLoop2);
+        // warp-aggregated append of the record
+        const unsigned mask = __ballot_sync(0xffffffffu, survive);
+        if (survive) {
+            const int lane = threadIdx.x & 31;
+            const int leader = __ffs(mask) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(&P.rctl->count, (unsigned long long)__popc(mask));
+            base = __shfl_sync(mask, base, leader);
+            P.recs[base + __popc(mask & ((1u << lane) - 1u))] = rec;
+        }
     }
 }
 
@@ -321,8 +401,8 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
     if (QAGP)
         total = P.worklist ? *P.worklist_count : (unsigned long long)P.n;
     else
-        total = P.ctl->chain[P.chain].countLoop2;
-    unsigned long long* head = QAGP ? &P.ctl->headP : &P.ctl->chain[P.chain].headLoop;
+        total = P.rctl->count;
+    unsigned long long* head = QAGP ? &P.ctl->headP : &P.rctl->head;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * (ABLOCK / 32);
     const unsigned long long warp_id = t >> 5;
     // first fill: queue positions [0, first_span) are owned statically; later refills draw
@@ -336,8 +416,10 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
     Lane& s = s_lanes[threadIdx.x];
     s.active = false;
     s.idx = 0;
-    GlobalSink sink;
-    sink.O = P.out;
+    // QAGP lanes write the batch outputs directly; QAGS lanes finish straggler records and write
+    // to the owning call's outputs or to the host-pipeline patch (s.idx = record slot)
+    typename SinkFor<QAGP>::type sink;
+    init_sink(sink, P);
     Wrapped<F> g;
     g.transform = false;
     bool exhausted = false;
@@ -392,22 +474,28 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
                     lane_reset_common(s);
                     double a, b;
                     if (!QAGP) {
-                        // resume after iteration 1 from what k_qags_first parked
-                        s.idx = (long long)P.listLoop2[P.chain][my];
-                        const long long i = s.idx;
-                        load_range(P, i, a, b, s.transform);
-                        load_functor(g.f, P, i, NPARAMS);
+                        // resume after iteration 1 from the straggler record
+                        const StragglerRec& r = P.recs[my];
+                        s.idx = (long long)my;
+                        a = r.a;
+                        b = r.b;
+                        s.transform = !is_finite(a) || !is_finite(b);
+                        if (s.transform) {
+                            a = transform_point(a);
+                            b = transform_point(b);
+                        }
+#pragma unroll
+                        for (int q = 0; q < MAX_PARAMS; ++q) g.f.p[q] = r.p[q];
                         g.transform = s.transform;
-                        s.est0 = P.out.estimate[i];  // result0 (still parked in the outputs)
-                        s.delta0 = P.out.delta[i];
-                        s.abs0 = P.abs0[i];
-                        s.nevals = P.out.nevals[i];  // nevals of result0 + 50
+                        s.est0 = r.est0;
+                        s.delta0 = r.delta0;
+                        s.abs0 = r.abs0;
+                        s.nevals = r.nevals;  // nevals of result0 + 50
                         const uint32_t nev0 = s.nevals - 50u;
                         // ws.reserve((max_evals - nevals) / 50 + 1)   qags.rs:98-99
                         s.max_iters = (P.max_evals - nev0) / 50;
                         s.limit = (int)reserve_cap(P.ws_capacity, s.max_iters + 1);
-                        const double e1 = P.stage[i], d1 = P.stage[P.n + i];
-                        const double e2 = P.stage[2 * P.n + i], d2 = P.stage[3 * P.n + i];
+                        const double e1 = r.e1, d1 = r.d1, e2 = r.e2, d2 = r.d2;
                         const double center = (a + b) * 0.5;
                         if (d2 > d1) {  // workspace.rs:145-151
                             ws_push(S, s, center, b, e2, d2, 1);
@@ -417,9 +505,9 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
                             ws_push(S, s, center, b, e2, d2, 1);
                         }
                         s.maxlevel = 1;
-                        s.area = P.stage[4 * P.n + i];
-                        s.errsum = P.stage[5 * P.n + i];
-                        s.ro1 = (int)P.stage_ro1[i];
+                        s.area = r.area;
+                        s.errsum = r.errsum;
+                        s.ro1 = (int)r.ro1;
                         tab_append(S, s, s.est0);
                         tab_append(S, s, s.area);
                         s.ktmin = 1;

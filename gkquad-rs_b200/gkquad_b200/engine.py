@@ -23,6 +23,26 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
+class BatchPlan:
+    """A marshalled batch call (see Engine.plan_batch): run() crosses the C ABI and nothing else."""
+
+    __slots__ = ("eng", "fn", "args", "device_entry", "result", "_keep")
+
+    def __init__(self, eng, fn, args, device_entry, result, keep):
+        self.eng, self.fn, self.args, self.device_entry, self.result, self._keep = eng, fn, args, device_entry, result, keep
+
+    def run(self, stream=None):
+        """Device entry: enqueue on `stream` (a raw cudaStream_t handle; default: torch's current
+        stream).  Host entry: blocking.  Returns the BatchResult the plan writes into."""
+        if self.device_entry:
+            rc = self.fn(*self.args, self.eng._stream() if stream is None else stream)
+        else:
+            rc = self.fn(*self.args)
+        if rc != 0:
+            self.eng._check(rc)
+        return self.result
+
+
 class Engine:
     """Owns a gkq_handle_t (device scratch, worklists, slabs).  Not thread-safe; calls are
     ordered on the CUDA stream that is current when they are made."""
@@ -91,15 +111,22 @@ class Engine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     # ---- 1-D ------------------------------------------------------------------------------
-    def integrate_batch(self, functor, a, b, params=None, *, algo=ALGO_AUTO, tol=None, max_evals=2000,
-                        points=None, pts_offsets=None, pts=None, workspace_capacity=0, n=None, out=None):
-        """n independent integrals of `functor` (registry name or id).
+    def integrate_batch(self, functor, a, b, params=None, **kw):
+        """n independent integrals of `functor`; see plan_batch for the arguments.  Returns
+        BatchResult (numpy arrays or torch tensors, like the inputs)."""
+        return self.plan_batch(functor, a, b, params, **kw).run()
+
+    def plan_batch(self, functor, a, b, params=None, *, algo=ALGO_AUTO, tol=None, max_evals=2000,
+                   points=None, pts_offsets=None, pts=None, workspace_capacity=0, n=None, out=None):
+        """Validate and marshal one batch call once; BatchPlan.run() then only crosses the C ABI
+        (the counterpart of an Integrator that owns its integrand and config and is run many times).
+        n independent integrals of `functor` (registry name or id).
 
         a, b: scalars (one shared range; `n` or a params batch defines the size) or arrays [n].
         params: None, a sequence of scalars (shared), or an array [nparams, n] (SoA).
         Arrays may be numpy (host entry: staged through pinned/pageable copies by the library) or
         torch CUDA float64 tensors (device entry: asynchronous on the current stream).
-        Returns BatchResult (numpy arrays or torch tensors accordingly)."""
+        out = (estimate, delta, nevals, status) to write into caller-owned arrays."""
         fid, fname, npar, _ = self.functor(1, functor)
         tol = tol or Tolerance.default()
         on_dev = any(_is_torch(x) for x in (a, b, params) if x is not None)
@@ -163,22 +190,19 @@ class Engine:
                 st = xp.empty(n, dtype=xp.int32, device=dev)
             else:
                 est, dlt, nev, st = out
-            self._check(self.L.gkq_integrate_batch(
-                self.h, C.byref(cfg), fid, n, self._ptr(aa), self._ptr(bb), rs, self._ptr(pp), ps,
-                self._ptr(po), self._ptr(pv), self._ptr(est), self._ptr(dlt), self._ptr(nev),
-                self._ptr(st), self._stream()))
             r = BatchResult(est, dlt, nev, st)
-            r._keep = (aa, bb, pp, po, pv, cfg)
-            return r
+            args = (self.h, C.byref(cfg), fid, n, self._ptr(aa), self._ptr(bb), rs, self._ptr(pp), ps,
+                    self._ptr(po), self._ptr(pv), self._ptr(est), self._ptr(dlt), self._ptr(nev), self._ptr(st))
+            return BatchPlan(self, self.L.gkq_integrate_batch, args, True, r, (aa, bb, pp, po, pv, cfg))
         if out is None:
             est, dlt = np.empty(n), np.empty(n)
             nev, st = np.empty(n, dtype=np.uint32), np.empty(n, dtype=np.uint32)
         else:
             est, dlt, nev, st = out
-        self._check(self.L.gkq_integrate_batch_host(
-            self.h, C.byref(cfg), fid, n, self._ptr(aa), self._ptr(bb), rs, self._ptr(pp), ps,
-            self._ptr(po), self._ptr(pv), self._ptr(est), self._ptr(dlt), self._ptr(nev), self._ptr(st)))
-        return BatchResult(est, dlt, nev, st)
+        r = BatchResult(est, dlt, nev, st)
+        args = (self.h, C.byref(cfg), fid, n, self._ptr(aa), self._ptr(bb), rs, self._ptr(pp), ps,
+                self._ptr(po), self._ptr(pv), self._ptr(est), self._ptr(dlt), self._ptr(nev), self._ptr(st))
+        return BatchPlan(self, self.L.gkq_integrate_batch_host, args, False, r, (aa, bb, pp, po, pv, cfg))
 
     def qk_batch(self, rule: int, functor, a, b, params=None):
         """single::qk17 / qk25 for a batch (device tensors in, [4, n] tensor out)."""
