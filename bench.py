@@ -220,60 +220,73 @@ def _main(args, real_stdout):
     eng = gk.Engine(local_rank)
     from gkquad_b200 import distributed as D
 
-    # NSETS independent batches are cycled through so that a step never finds its inputs or
-    # outputs in the 126 MB L2 (6 x (16 MB in + 24 MB out) = 240 MB): "inputs larger than L2".
-    NSETS = 6
+    # 2 groups x G independent batches are cycled through, so that a step never finds its inputs or
+    # outputs in the 126 MB L2 (8 x (16 MB in + 24 MB out) = 320 MB): "inputs larger than L2".
+    # For N > 1 the results of a group are gathered with ONE all_gather (24 B/integral, packed) on a
+    # side stream while the other group is being computed.
+    G, NGROUPS = 4, 2
+    NSETS = G * NGROUPS
+    groups = []
     sets = []
-    for s in range(NSETS):
-        p_host, idx = shard_params(W, n, rank, world, offset=s * n * world)
-        kw = dict(algo=algo, tol=W.tol, max_evals=W.max_evals, n=n)
-        if W.points and W.points != "param0":
-            kw["points"] = W.points
-        elif W.points == "param0":
-            from gkquad_b200.workloads import csr_points_from_param0
-            off, pts = csr_points_from_param0(p_host)
-            kw["pts_offsets"] = torch.as_tensor(off, device=dev)
-            kw["pts"] = torch.as_tensor(pts, device=dev)
-        # results are written straight into the packed gather buffer: est | delta | nevals,status
-        packed = torch.zeros(3 * n, dtype=torch.float64, device=dev)
-        ints = packed[2 * n:].view(torch.int32)
-        out = (packed[:n], packed[n:2 * n], ints[:n], ints[n:])
-        gathered = torch.empty(world * 3 * n, dtype=torch.float64, device=dev) if world > 1 else None
-        p_dev = torch.as_tensor(p_host, device=dev)
-        # the call is marshalled once (an Integrator owns integrand + config and is run many times)
-        plan = eng.plan_batch(W.functor, W.a, W.b, p_dev, out=out, **kw)
-        sets.append(dict(p_host=p_host, p_dev=p_dev, kw=kw, packed=packed, plan=plan,
-                         out=out, gathered=gathered, done=None))
+    for gi in range(NGROUPS):
+        packed = torch.zeros(G, 3 * n, dtype=torch.float64, device=dev)
+        gathered = torch.empty(world, G, 3 * n, dtype=torch.float64, device=dev) if world > 1 else None
+        groups.append(dict(packed=packed, gathered=gathered, done=None))
+        for si in range(G):
+            s = gi * G + si
+            p_host, idx = shard_params(W, n, rank, world, offset=s * n * world)
+            kw = dict(algo=algo, tol=W.tol, max_evals=W.max_evals, n=n)
+            if W.points and W.points != "param0":
+                kw["points"] = W.points
+            elif W.points == "param0":
+                from gkquad_b200.workloads import csr_points_from_param0
+                off, pts = csr_points_from_param0(p_host)
+                kw["pts_offsets"] = torch.as_tensor(off, device=dev)
+                kw["pts"] = torch.as_tensor(pts, device=dev)
+            # results are written straight into the packed gather buffer: est | delta | nevals,status
+            row = packed[si]
+            ints = row[2 * n:].view(torch.int32)
+            out = (row[:n], row[n:2 * n], ints[:n], ints[n:])
+            p_dev = torch.as_tensor(p_host, device=dev)
+            # the call is marshalled once (an Integrator owns integrand + config and is run many times)
+            plan = eng.plan_batch(W.functor, W.a, W.b, p_dev, out=out, **kw)
+            sets.append(dict(p_host=p_host, p_dev=p_dev, kw=kw, plan=plan, out=out, group=gi))
     p_host = sets[0]["p_host"]
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
 
     def step(k):
-        """One pass of the hot path over one batch; for N > 1 the single result gather (NCCL
-        all_gather of the packed 24 B/integral) runs on its own stream and overlaps the next step."""
-        S = sets[k % NSETS]
-        if S["done"] is not None:  # the gather that last read this buffer must be over
-            torch.cuda.current_stream().wait_event(S["done"])
+        """One pass of the hot path over one batch.  For N > 1 every G-th step hands its group to the
+        side stream: finish the group's stragglers (join) and all_gather the packed results, while
+        the next group is computed."""
+        s = k % NSETS
+        S = sets[s]
+        Gp = groups[S["group"]]
+        if s % G == 0 and Gp["done"] is not None:  # the gather that last read this group must be over
+            torch.cuda.current_stream().wait_event(Gp["done"])
         S["plan"].run()
-        if world > 1:
+        if world > 1 and s % G == G - 1:
             ev = torch.cuda.Event()
             ev.record()
             comm.wait_event(ev)
             with torch.cuda.stream(comm):
-                eng.join()  # the gather also waits for the deferred remainder of this batch
-                dist.all_gather_into_tensor(S["gathered"], S["packed"])
-                S["done"] = torch.cuda.Event()
-                S["done"].record()
+                eng.join()  # the gather also waits for the deferred remainders of the group
+                dist.all_gather_into_tensor(Gp["gathered"], Gp["packed"])
+                Gp["done"] = torch.cuda.Event()
+                Gp["done"].record()
 
     def join():
         eng.join()  # outstanding deferred remainders
         if world > 1:
             torch.cuda.current_stream().wait_stream(comm)
 
-    # throughput pipelining of independent batches: the latency-bound remainder of batch k overlaps
-    # the bulk kernels of batch k+1 (two batches in flight); every step is complete before e1
+    # throughput pipelining of independent batches: the latency-bound remainders of several batches
+    # are finished by one launch (deferred join); every step is complete before the end event
     eng.set_deferred_join(True)
 
-    for k in range(max(NSETS, args.warmup, 3)):
+    steps = args.steps
+    if world > 1 and steps % G:
+        steps += G - steps % G  # whole groups, so that every timed step is gathered inside the region
+    for k in range(max(2 * NSETS, args.warmup, 3)):
         step(k)
     join()
     torch.cuda.synchronize()
@@ -288,7 +301,7 @@ def _main(args, real_stdout):
         dist.barrier()
     torch.cuda.synchronize()
     e0.record()
-    for k in range(args.steps):
+    for k in range(steps):
         step(k)
     join()
     e1.record()
@@ -305,7 +318,7 @@ def _main(args, real_stdout):
         dist.all_reduce(conv_local, op=dist.ReduceOp.SUM)
     total_ms = float(t.item())
     converged = float(conv_local.item())
-    ms_per_step = total_ms / args.steps
+    ms_per_step = total_ms / steps
     value = converged / (ms_per_step * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
     eng.set_deferred_join(False)
@@ -414,16 +427,18 @@ def _main(args, real_stdout):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{W.name}: {W.description}; {W.algo}, {W.tol}, max_evals {W.max_evals}",
                        "batch_per_gpu": n, "global_batch": n * world,
                        "parallelism": f"shard{world}" + ("+nccl_all_gather" if world > 1 else ""),
-                       "l2": "6 independent batches cycled (240 MB of inputs+outputs > 126 MB L2); no flush needed",
-                       "pipeline": "deferred join: the remainder (persistent tail kernels) of step k overlaps the "
-                                   "bulk of step k+1, two batches in flight; all K steps complete inside the timed region",
-                       "gather": "all_gather of 24 B/integral on a side stream, overlapping the next step" if world > 1 else "none (N=1)",
+                       "l2": "8 independent batches cycled (320 MB of inputs+outputs > 126 MB L2); no flush needed",
+                       "pipeline": "deferred join: the stragglers (integrals needing > 1 bisection step) of up to 8 "
+                                   "steps are finished by one launch of the persistent kernel; all K steps "
+                                   "complete inside the timed region",
+                       "gather": ("one all_gather of 24 B/integral per group of 4 steps, on a side stream, "
+                                  "overlapping the next group") if world > 1 else "none (N=1)",
                        "converged_fraction": converged / (n * world),
                        "mean_nevals": float(nev_h.mean())},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
