@@ -40,11 +40,14 @@ template <int ID> struct F1;
 // BODY computes f(x) with the math policy `m` (m.exp, m.cos, m.sin, m.log, m.pow):
 //   eval(x, FastMath&)  branch-free sample; clears m.ok when an argument leaves the fast range
 //   operator()(x)       always-valid sample (SafeMath)
-#define GKQ_F1(ID, HEAVY_, BODY)                                                 \
+//   GKQ_F1P: the body only uses + - * / and m.exp / m.cos / m.sin, so it also instantiates on the
+//   two-lane type D2 and a node pair is evaluated with interleaved chains (PAIRWISE).
+#define GKQ_F1_IMPL(ID, HEAVY_, PAIR_, BODY)                                     \
     template <> struct F1<ID> {                                                  \
         static constexpr bool HEAVY = HEAVY_;                                    \
+        static constexpr bool PAIRWISE = PAIR_;                                  \
         double p[MAX_PARAMS];                                                    \
-        template <class M> GKQ_DEV double eval(double x, M& m) const {           \
+        template <class T, class M> GKQ_DEV T eval(T x, M& m) const {            \
             (void)m;                                                             \
             BODY                                                                 \
         }                                                                        \
@@ -53,27 +56,31 @@ template <int ID> struct F1;
             return eval(x, m);                                                   \
         }                                                                        \
     };
+#define GKQ_F1(ID, HEAVY_, BODY) GKQ_F1_IMPL(ID, HEAVY_, false, BODY)
+#define GKQ_F1P(ID, HEAVY_, BODY) GKQ_F1_IMPL(ID, HEAVY_, true, BODY)
 GKQ_F1(F1_SQUARE, false, return x * x;)                                   // benches/single.rs:11
 GKQ_F1(F1_RECIP_P, false, return p[0] / x;)                               // benches/single.rs:20
 GKQ_F1(F1_LORENTZ_P, false, return 1.0 / (1.0 + p[0] * (x * x));)         // benches/single.rs:32
-GKQ_F1(F1_EXPCOS_P, true, return m.exp(-p[0] * x) * m.cos(p[1] * x);)         // S1 / S3
-GKQ_F1(F1_GAUSS_P, true, return m.exp(-p[0] * (x * x));)                    // I2
+GKQ_F1P(F1_EXPCOS_P, true, return m.exp(-p[0] * x) * m.cos(p[1] * x);)         // S1 / S3
+GKQ_F1P(F1_GAUSS_P, true, return m.exp(-p[0] * (x * x));)                    // I2
 GKQ_F1(F1_ABSPOW_P, true, return m.pow(fabs(x - p[0]), -p[1]);)             // P1
 GKQ_F1(F1_LOGABS_P, true, return m.log(fabs(x - p[0]));)                    // P2
 GKQ_F1(F1_F1, true, return m.pow(x, 2.6) * m.log(1. / x);)                    // functions.rs:3-5
 GKQ_F1(F1_F2, true, return m.pow(x, -0.9) * m.log(1. / x);)                   // functions.rs:8-10
-GKQ_F1(F1_F3, true, return m.cos(2.4622888266898326 * m.sin(x));)             // functions.rs:13-15 (2^1.3)
+GKQ_F1P(F1_F3, true, return m.cos(2.4622888266898326 * m.sin(x));)             // functions.rs:13-15 (2^1.3)
 GKQ_F1(F1_F4, true, return m.log(1. / x);)                                  // functions.rs:17-19
 GKQ_F1(F1_F5, true, double x2 = x * x;
        return x2 * x * m.log(fabs((x2 - 1.) * (x2 - 2.)));)                 // functions.rs:22-25
 GKQ_F1(F1_F6, false, double x2 = x * x; double x3 = x2 * x;
        return 1.0 / (x3 - x2 + x - 1.);)                                  // functions.rs:27-31
-GKQ_F1(F1_EXP_P, true, return m.exp(p[0] * x);)
+GKQ_F1P(F1_EXP_P, true, return m.exp(p[0] * x);)
 GKQ_F1(F1_SQRT_SHIFT_P, false, return sqrt(x - p[0]);)
 GKQ_F1(F1_INV_ABS_SHIFT_P, false, return 1.0 / fabs(x - p[0]);)
-GKQ_F1(F1_COS_P, true, return m.cos(p[0] * x);)
-GKQ_F1(F1_SIN_P, true, return m.sin(p[0] * x);)
+GKQ_F1P(F1_COS_P, true, return m.cos(p[0] * x);)
+GKQ_F1P(F1_SIN_P, true, return m.sin(p[0] * x);)
 #undef GKQ_F1
+#undef GKQ_F1P
+#undef GKQ_F1_IMPL
 
 // ---- 2-D ------------------------------------------------------------------------------
 enum F2Id : int {
@@ -84,6 +91,7 @@ template <int ID> struct F2;
 #define GKQ_F2(ID, HEAVY_, BODY)                                                      \
     template <> struct F2<ID> {                                                       \
         static constexpr bool HEAVY = HEAVY_;                                         \
+        static constexpr bool PAIRWISE = false;                                       \
         double p[MAX_PARAMS];                                                         \
         template <class M> GKQ_DEV double eval(double x, double y, M& m) const {      \
             (void)m;                                                                  \

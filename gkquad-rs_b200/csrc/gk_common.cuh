@@ -168,8 +168,14 @@ struct Wrapped {
             x2 = x2 * c2;
         }
         FastMath m;
-        f1 = f.eval(x1, m);
-        f2 = f.eval(x2, m);
+        if constexpr (F::PAIRWISE) {
+            const D2 r = f.eval(D2{x1, x2}, m);  // both samples through the same statements (ILP 2)
+            f1 = r.a;
+            f2 = r.b;
+        } else {
+            f1 = f.eval(x1, m);
+            f2 = f.eval(x2, m);
+        }
         if (!m.ok) {
             f1 = f(x1);
             f2 = f(x2);

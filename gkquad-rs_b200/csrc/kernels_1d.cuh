@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(BLOCK, (N == 8) ? 4 : 3) k_qags_init(const Bat
 // from the state this kernel parks (list = the two halves ordered by error, order = [0, 1],
 // epsilon table = [result0, area], ktmin = 1: what qags.rs leaves behind after iteration 1).
 template <class F, int NPARAMS>
-__global__ void __launch_bounds__(BLOCK) k_qags_first(const Batch1D P) {
+__global__ void __launch_bounds__(BLOCK, 3) k_qags_first(const Batch1D P) {
     const long long total = (long long)P.ctl->chain[P.chain].countLoop;
     for (long long k = (long long)blockIdx.x * BLOCK + threadIdx.x; k - threadIdx.x % 32 < total;
          k += (long long)gridDim.x * BLOCK) {

@@ -334,6 +334,7 @@ template <class F2T>
 struct InnerF {
     F2T f;
     double x;
+    static constexpr bool PAIRWISE = false;
     GKQ_DEV double operator()(double y) const { return f(x, y); }
     template <class M> GKQ_DEV double eval(double y, M& m) const { return f.eval(x, y, m); }
 };
