@@ -162,6 +162,7 @@ struct gkq_handle_s {
     int occ_loop[F1_COUNT], occ_qagp[F1_COUNT], occ_init25[F1_COUNT];
     Launch2D l2[F2_COUNT];
     int occ_2d[F2_COUNT][2];
+    int occ_2dw[F2_COUNT][2];
 };
 
 namespace {
@@ -202,6 +203,7 @@ struct FillL2 {
     static void go(gkq_handle_s* h) {
         h->l2[ID] = make_launch2d<ID>();
         h->occ_2d[ID][0] = h->occ_2d[ID][1] = -1;
+        h->occ_2dw[ID][0] = h->occ_2dw[ID][1] = -1;
         FillL2<ID + 1>::go(h);
     }
 };
@@ -1334,23 +1336,41 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
             Q.worklist_count = alg == 0 ? &S.ctl->countS : &S.ctl->countP;
         }
         const Launch2D& L = h->l2[functor2_id];
-        if (h->occ_2d[functor2_id][alg] < 0) h->occ_2d[functor2_id][alg] = L.occupancy[alg]();
+        if (h->occ_2d[functor2_id][alg] < 0) {
+            h->occ_2d[functor2_id][alg] = L.occupancy[alg]();
+            h->occ_2dw[functor2_id][alg] = L.occupancy_warp[alg]();
+        }
         // list lengths: outer <= npts+1 + (max_evals/17)/50 + 1, inner <= npts+1 + max_evals/50 + 1
         const unsigned long long outer_need = (unsigned long long)Q.npts_max + 2ull + (cfg->max_evals / 17ull) / 50ull;
         const unsigned long long inner_need = (unsigned long long)Q.npts_max + 2ull + cfg->max_evals / 50ull;
         if (inner_need > (1ull << 24)) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
         const int cap_total = (int)(outer_need + inner_need);
-        const long long nblocks = (n + BLOCK - 1) / BLOCK;
-        int grid = persistent_grid(h, h->occ_2d[functor2_id][alg], cap_total, 2 * (Q.npts_max + 2) + 110);
+        // Thread per outer integral while the batch alone fills the machine; below that a warp
+        // per outer integral, its lanes sharing the inner integrals of each outer rule.
+        const long long resident = (long long)h->sm_count * h->occ_2d[functor2_id][alg] * BLOCK;
+        bool warp_mode = n * 4 < resident;
+        if (const char* env = getenv("GKQ_NESTED_MODE")) {  // test / tuning knob: 1 = thread, 2 = warp
+            if (atoi(env) == 1) warp_mode = false;
+            if (atoi(env) == 2) warp_mode = true;
+        }
+        const int blk = warp_mode ? NBLOCK : BLOCK;
+        const long long nblocks = warp_mode ? (n + NBLOCK / 32 - 1) / (NBLOCK / 32) : (n + BLOCK - 1) / BLOCK;
+        int grid = persistent_grid(h, warp_mode ? h->occ_2dw[functor2_id][alg] : h->occ_2d[functor2_id][alg],
+                                   cap_total, 2 * (Q.npts_max + 2) + 110, blk);
         if (grid < 1) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
         if ((long long)grid > nblocks) grid = (int)nblocks;
         SlabGeom g;
-        if ((rc = ensure_slab(h, (unsigned long long)grid * BLOCK, cap_total, 2 * (Q.npts_max + 2) + 110, g))) return rc;
+        if ((rc = ensure_slab(h, (unsigned long long)grid * blk, cap_total, 2 * (Q.npts_max + 2) + 110, g))) return rc;
         Q.slab = g;
         Q.cap_outer = (int)outer_need;
         Q.cap_inner = (int)inner_need;
-        prof_begin(h, alg == 0 ? "k_nested<QAGS2>" : "k_nested<QAGP2>", st);
-        L.run[alg](Q, grid, st);
+        const char* kname = warp_mode ? (alg == 0 ? "k_nested_warp<QAGS2>" : "k_nested_warp<QAGP2>")
+                                      : (alg == 0 ? "k_nested<QAGS2>" : "k_nested<QAGP2>");
+        prof_begin(h, kname, st);
+        if (warp_mode)
+            L.run_warp[alg](Q, grid, st);
+        else
+            L.run[alg](Q, grid, st);
         prof_end(h, st);
         if ((rc = launch_check(h, alg == 0 ? "k_nested<QAGS2>" : "k_nested<QAGP2>"))) return rc;
     }

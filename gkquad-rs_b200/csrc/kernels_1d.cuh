@@ -341,14 +341,14 @@ __global__ void __launch_bounds__(BLOCK, 3) k_qags_first(const Batch1D P) {
 // returns nint = len - 1.  The insertion sort is util.rs:178-211 with a strict comparator in
 // range direction.
 GKQ_DEV int make_sorted_points(const Slab& S, double begin, double end, const double* pts, int npts,
-                               bool transform) {
+                               bool transform, int pts_stride = 1) {
     const bool ascending = begin < end;
     const double mn = ascending ? begin : end;
     const double mx = ascending ? end : begin;
     // pts2[0] = begin, pts2[1..] = user points (transformed when the range is infinite)
     S.PTS(0) = begin;
     for (int k = 0; k < npts; ++k) {
-        double v = pts[k];
+        double v = pts[(long long)k * pts_stride];
         S.PTS(1 + k) = transform ? transform_point(v) : v;
     }
     // insert_sort(&mut pts2[1..])

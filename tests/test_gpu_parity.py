@@ -331,6 +331,45 @@ def test_double_dynamic_ranges(eng):
         compare(g, ref, _tol(tol), exact=True, label=f)
 
 
+@pytest.mark.parametrize("mode", ["1", "2"], ids=["thread_per_outer", "warp_per_outer"])
+def test_double_budget_exhaustion(eng, mode, monkeypatch):
+    """The running evaluation budget, the first-error latch and the persistent inner workspace of the
+    nest (double/algorithm/qags.rs:60-93, qagp.rs:108-137) under budgets that run out at every stage;
+    both device mappings (GKQ_NESTED_MODE) must agree bit for bit with the oracle."""
+    import torch
+    from gkquad_b200.workloads import WORKLOADS
+    from gpu_common import compare
+    from oracle import oracle as O
+    monkeypatch.setenv("GKQ_NESTED_MODE", mode)
+    W = WORKLOADS["D1"]
+    n = 24
+    p = W.make_params(0, n)
+    off = np.arange(n + 1, dtype=np.int64)
+    pxy = np.ascontiguousarray(p.T)
+    seen = set()
+    for me in (0, 16, 49, 50, 120, 700, 1250, 1300, 2600, 5000, 12000, 30000, 60000, 85000, 92000):
+        for tol in (("rel", 1e-6), ("abs", 1e-9)):
+            ref = O.integrate2_batch(ALGO["QAGP"], W.functor, W.yrange, W.a, W.b, fparams=p, yparams=W.yparams,
+                                     points=pxy, pts_offsets=off, tol=tol, max_evals=me, n=n)
+            g = eng.integrate2_batch(W.functor, W.yrange, W.a, W.b, fparams=p, yparams=W.yparams,
+                                     algo=ALGO["QAGP"], tol=_tol(tol), max_evals=me, pts_offsets=off, pts_xy=pxy, n=n)
+            compare(g, ref, _tol(tol), exact=True, label=f"D1 max_evals={me}")
+            seen |= set(np.unique(ref["status"]).tolist())
+    assert 1 in seen  # InsufficientIteration was exercised
+    cases = [("g1", "const", 0.0, 1.0, [0.0, 1.0], ALGO["QAGS"], []),
+             ("g2", "zero_to_x", 0.1, 1.0, [], ALGO["QAGS"], []),
+             ("gp1", "const", -1.0, 1.0, [-1.0, 1.0], ALGO["QAGS"], []),
+             ("gp3", "const", -1.0, 2.0, [-1.0, 1.0], ALGO["QAGP"], [(0.0, 0.0)]),
+             ("gp1", "const", -1.0, math.inf, [-math.inf, 2.0], ALGO["QAGP"], [(0.0, 0.0), (1.0, 1.0)])]
+    for f, yr, x0, x1, yq, algo, pts in cases:
+        for me in (10, 17, 288, 289, 290, 700, 1100, 3000, 9000, 25000):
+            for tol in (("rel", 1e-9), ("abs", 1e-13)):
+                ref = O.integrate2_batch(algo, f, yr, x0, x1, yparams=yq, points=pts, tol=tol, max_evals=me, n=1)
+                g = eng.integrate2_batch(f, yr, x0, x1, yparams=yq, algo=algo, tol=_tol(tol), max_evals=me,
+                                         points=pts, n=1)
+                compare(g, ref, _tol(tol), exact=f != "g2", label=f"{f} max_evals={me}")
+
+
 def test_api_mirror_on_gpu(eng):
     """The host-side mirror of gkquad's API (single::integral, Integrator builder, integral2)."""
     from gkquad_b200 import Tolerance, double, single
