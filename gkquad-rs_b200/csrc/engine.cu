@@ -1338,25 +1338,32 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
         const Launch2D& L = h->l2[functor2_id];
         if (h->occ_2d[functor2_id][alg] < 0) {
             h->occ_2d[functor2_id][alg] = L.occupancy[alg]();
-            h->occ_2dw[functor2_id][alg] = L.occupancy_warp[alg]();
+            h->occ_2dw[functor2_id][alg] = L.occupancy_pool[alg]();
         }
         // list lengths: outer <= npts+1 + (max_evals/17)/50 + 1, inner <= npts+1 + max_evals/50 + 1
         const unsigned long long outer_need = (unsigned long long)Q.npts_max + 2ull + (cfg->max_evals / 17ull) / 50ull;
         const unsigned long long inner_need = (unsigned long long)Q.npts_max + 2ull + cfg->max_evals / 50ull;
         if (inner_need > (1ull << 24)) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
         const int cap_total = (int)(outer_need + inner_need);
-        // Thread per outer integral while the batch alone fills the machine; below that a warp
-        // per outer integral, its lanes sharing the inner integrals of each outer rule.
-        const long long resident = (long long)h->sm_count * h->occ_2d[functor2_id][alg] * BLOCK;
-        bool warp_mode = n * 4 < resident;
-        if (const char* env = getenv("GKQ_NESTED_MODE")) {  // test / tuning knob: 1 = thread, 2 = warp
-            if (atoi(env) == 1) warp_mode = false;
-            if (atoi(env) == 2) warp_mode = true;
+        // k_nested_pool: warps own a few outer integrals each and share their inner integrals
+        // among the lanes; k_nested (a thread per outer integral) is kept as the reference mapping.
+        bool pool_mode = true;
+        if (const char* env = getenv("GKQ_NESTED_MODE")) {  // test / tuning knob: 1 = thread, 2 = pool
+            if (atoi(env) == 1) pool_mode = false;
         }
-        const int blk = warp_mode ? NBLOCK : BLOCK;
-        const long long nblocks = warp_mode ? (n + NBLOCK / 32 - 1) / (NBLOCK / 32) : (n + BLOCK - 1) / BLOCK;
-        int grid = persistent_grid(h, warp_mode ? h->occ_2dw[functor2_id][alg] : h->occ_2d[functor2_id][alg],
+        const int blk = pool_mode ? PB : BLOCK;
+        int grid = persistent_grid(h, pool_mode ? h->occ_2dw[functor2_id][alg] : h->occ_2d[functor2_id][alg],
                                    cap_total, 2 * (Q.npts_max + 2) + 110, blk);
+        long long nblocks = (n + BLOCK - 1) / BLOCK;
+        if (pool_mode && grid >= 1) {
+            // outer integrals per warp: as few as still keep every warp of the grid busy
+            const long long warps = (long long)grid * (PB / 32);
+            long long r = (n + warps - 1) / warps;
+            if (r < 1) r = 1;
+            if (r > POOL_R) r = POOL_R;
+            Q.pool_r = (int)r;
+            nblocks = (n + r * (PB / 32) - 1) / (r * (PB / 32));
+        }
         if (grid < 1) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
         if ((long long)grid > nblocks) grid = (int)nblocks;
         SlabGeom g;
@@ -1364,11 +1371,11 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
         Q.slab = g;
         Q.cap_outer = (int)outer_need;
         Q.cap_inner = (int)inner_need;
-        const char* kname = warp_mode ? (alg == 0 ? "k_nested_warp<QAGS2>" : "k_nested_warp<QAGP2>")
+        const char* kname = pool_mode ? (alg == 0 ? "k_nested_pool<QAGS2>" : "k_nested_pool<QAGP2>")
                                       : (alg == 0 ? "k_nested<QAGS2>" : "k_nested<QAGP2>");
         prof_begin(h, kname, st);
-        if (warp_mode)
-            L.run_warp[alg](Q, grid, st);
+        if (pool_mode)
+            L.run_pool[alg](Q, grid, st);
         else
             L.run[alg](Q, grid, st);
         prof_end(h, st);

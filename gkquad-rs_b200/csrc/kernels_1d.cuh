@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(BLOCK, 3) k_qags_first(const Batch1D P) {
 // returns nint = len - 1.  The insertion sort is util.rs:178-211 with a strict comparator in
 // range direction.
 GKQ_DEV int make_sorted_points(const Slab& S, double begin, double end, const double* pts, int npts,
-                               bool transform, int pts_stride = 1) {
+                               bool transform, int pts_stride = 1, bool pre_transform = false) {
     const bool ascending = begin < end;
     const double mn = ascending ? begin : end;
     const double mx = ascending ? end : begin;
@@ -349,6 +349,7 @@ GKQ_DEV int make_sorted_points(const Slab& S, double begin, double end, const do
     S.PTS(0) = begin;
     for (int k = 0; k < npts; ++k) {
         double v = pts[(long long)k * pts_stride];
+        if (pre_transform) v = transform_point(v);  // double/algorithm/qagp.rs:98-106
         S.PTS(1 + k) = transform ? transform_point(v) : v;
     }
     // insert_sort(&mut pts2[1..])

@@ -21,6 +21,12 @@
 
 namespace gkq {
 
+// Node pairs inlined per trip of the rule loops inside the nested kernels.  Lanes / warps of these
+// kernels sit in different phases of different inner integrals, so the instruction stream jumps
+// between the rule and the bookkeeping code all the time: what counts is that the whole trip fits
+// the 32 KB instruction cache (ncu: `no_instruction` was the top stall with fully unrolled rules).
+constexpr int NESTED_UNROLL = 1;
+
 struct Res {
     double est, dlt;
     uint32_t nev, st;
@@ -360,6 +366,7 @@ struct Batch2D {
     Control* ctl;
     SlabGeom slab;
     int cap_outer, cap_inner;
+    int pool_r;  // k_nested_pool: outer integrals per warp (<= POOL_R)
 };
 
 // f(x, .) as a 1-D integrand of y
@@ -406,10 +413,10 @@ struct OuterIntegrand {
         if (QAGP) {
             const double* p = pts_xy;
             auto user_pt = [p](int k) { return p[2 * k + 1]; };  // every y of the 2-D points
-            return seq_qagp<RM_PURE, RuleUnroll<F2T, 12>::value>(g, y0, y1, ytr, user_pt, npts, tol,
+            return seq_qagp<RM_PURE, NESTED_UNROLL>(g, y0, y1, ytr, user_pt, npts, tol,
                                                                  budget, cap, Sin);
         }
-        return seq_qags<RM_PURE, RuleUnroll<F2T, 12>::value>(g, y0, y1, tol, budget, cap, Sin);
+        return seq_qags<RM_PURE, NESTED_UNROLL>(g, y0, y1, tol, budget, cap, Sin);
     }
     // config1.max_evals = if error.is_some() { 0 } else { config.max_evals - nevals }
     // (if an inner QAGP call overshot the budget by its last 50 samples the reference's
@@ -518,518 +525,34 @@ __global__ void __launch_bounds__(BLOCK) k_nested(const Batch2D P) {
     }
 }
 
-// ---- warp-cooperative nest ---------------------------------------------------------------
-// One WARP owns one outer integral.  The outer algorithm runs redundantly and in lockstep in all
-// 32 lanes (identical state; each lane keeps its own copy of the outer list in its slab region,
-// which makes the list traffic one coalesced line per access), and whenever it needs a rule --
-// 17 or 25 inner integrals, or the 50 of a bisection step -- the lanes work those inner
-// integrals off IN PARALLEL: every lane is a small state machine that owns one inner integral
-// at a time (initial passes / break-point seeding / bisection loop, the same phases as
-// k_adaptive), takes the next one of the group when its own terminates, and all lanes meet
-// once per trip in the same sampling code (2 x 25 integrand samples), so the warp stays
-// converged however different the inner iteration counts are.  The values are then shared with
-// shuffles and every lane reduces them in the reference's order: the outer arithmetic is
-// bit-identical.
-//
-// What the reference serialises between inner calls is only the running budget (max_evals =
-// total - evaluations so far), the first-error latch and the capacity of the re-used inner
-// workspace.  The inner integrals of a group therefore run with the budget at the START of the
-// group (an upper bound of their true budgets) and the group is committed with a prefix sum
-// when that provably did not matter: an inner call that spent `nev` evaluations never looks at
-// its budget B or its list capacity as long as B >= 2 nev + 200 (+ 100 per break-point window):
-// its iteration count stays below max_iters = (B - nev0) / 50 and its list shorter than
-// limit / 2, the only places where qags.rs / qagp.rs / workspace.rs read them.  The first time
-// this cannot be shown -- the budget is nearly exhausted -- the warp switches, for the rest of
-// that outer integral, to the exact path: all lanes walk the inner calls one after the other
-// like k_nested does.
-struct TaskBoard {  // results of the inner integrals of one group (per warp, shared memory)
-    double est[64];
-    uint32_t nev[64], st[64], rsv[64];  // rsv = RSV_* << 28 | rsv_n
-};
-struct BoardSink {
-    TaskBoard* tb;
-    GKQ_DEV void put(long long k, double est, double, uint32_t nev, uint32_t st) const {
-        tb->est[k] = est;
-        tb->nev[k] = nev;
-        tb->st[k] = st;
+// The nodes of one trip of an outer integral in the reference's evaluation order
+// (single/qk/naive.rs:60-68: lower nodes j = 0..N-1, upper nodes, centre), for one rule or for
+// the two rules of a bisection step.
+struct NodeSet {
+    int N, K;  // node pairs per rule, nodes in the trip (rules * (2N + 1))
+    double lo[2], hi[2];
+    GKQ_DEV double operator()(int k) const {
+        const int per = 2 * N + 1;
+        const int half = k >= per ? 1 : 0;
+        const int t = k - per * half;
+        const double center = 0.5 * (lo[half] + hi[half]);
+        const double half_length = 0.5 * (hi[half] - lo[half]);
+        if (t >= 2 * N) return center;
+        const int j = t < N ? t : t - N;
+        const double abscissa = half_length * (N == 8 ? c_xgk17[j] : c_xgk25[j]);
+        return t < N ? center - abscissa : center + abscissa;
     }
 };
 
-template <class F2T, bool QAGP>
-struct WarpOuter {
-    OuterIntegrand<F2T, QAGP> o;
-    bool exact;
-    Lane* ls;       // this lane's inner-integral state (shared memory)
-    TaskBoard* tb;  // this warp's board
-
-    // The inner integrals of nodes 0..K-1 with budget `budget0` each, results on the board.
-    template <class NodeFn>
-    GKQ_DEV void run_lanes(int K, NodeFn node, unsigned long long budget0) {
-        const unsigned FULL = 0xffffffffu;
-        const int lane = threadIdx.x & 31;
-        const Slab& S = o.Sin;
-        const unsigned long long cap0 = o.inner_cap;
-        Lane& s = *ls;
-        s.active = false;
-        BoardSink sink;
-        sink.tb = tb;
-        Wrapped<InnerF<F2T>> g;
-        g.f.f = o.f;
-        g.f.x = 0.;
-        g.transform = false;
-        double ya = 0., yb = 0.;  // the lane's whole inner range (initial passes of QAGS)
-        int next = 0;
-        for (;;) {
-            // ---- idle lanes take the next inner integrals of the group, in order ----
-            const unsigned idle = __ballot_sync(FULL, !s.active);
-            if (idle && next < K) {
-                const int k = next + __popc(idle & ((1u << lane) - 1u));
-                next += __popc(idle);
-                if (!s.active && k < K) {
-                    lane_reset_common(s);
-                    s.idx = k;
-                    double x = node(k);
-                    if (o.transform) x = x * (1. / (1. - fabs(x)));
-                    double y0, y1;
-                    o.yr(x, y0, y1);
-                    const bool ytr = !is_finite(y0) || !is_finite(y1);
-                    if (ytr) {
-                        y0 = transform_point(y0);
-                        y1 = transform_point(y1);
-                    }
-                    g.f.x = x;
-                    g.transform = ytr;
-                    s.transform = ytr;
-                    ya = y0;
-                    yb = y1;
-                    tb->rsv[k] = 0u;
-                    s.nevals = 0;
-                    s.est0 = s.delta0 = s.abs0 = s.asc0 = 0.;
-                    if (QAGP) {
-                        s.nint = make_sorted_points(S, y0, y1, o.pts_xy + 1, o.npts, ytr, 2);
-                        if (budget0 < (unsigned long long)s.nint * 25ull) {  // qagp.rs:79-81
-                            sink.put(k, 0.0, F64_MAX, 0u, ST_INSUFFICIENT_ITERATION);
-                        } else {
-                            s.limit = (int)reserve_cap(
-                                cap0, s.nint + (budget0 - (unsigned long long)s.nint * 25ull) / 50ull);
-                            tb->rsv[k] = (RSV_QAGP << 28) | (uint32_t)s.nint;
-                            s.seeding = true;
-                            s.seed_k = 0;
-                            s.active = true;
-                        }
-                    } else if (budget0 < 17ull) {  // qags.rs:86-88
-                        sink.put(k, 0.0, F64_MAX, 0u, ST_INSUFFICIENT_ITERATION);
-                    } else {
-                        s.seeding = true;  // initial passes: seed_k = 0 -> qk17, 1 -> qk25
-                        s.seed_k = 0;
-                        s.active = true;
-                    }
-                }
-            }
-            const unsigned live = __ballot_sync(FULL, s.active);
-            if (live == 0u) break;
-
-            // ---- plan this trip ----
-            double ra0 = 0., rb0 = 0., ra1 = 0., rb1 = 0.;
-            bool has17 = false, has0 = false, has1 = false;
-            if (s.active) {
-                if (QAGP && s.seeding) {
-                    int w0 = -1, w1 = -1;
-                    int k = s.seed_k;
-                    for (; k < s.nint && w1 < 0; ++k) {
-                        const double lo = S.PTS(k), hi = S.PTS(k + 1);
-                        if (fabs(hi - lo) < 100. * F64_MIN_POSITIVE) continue;
-                        if (w0 < 0) {
-                            w0 = k; ra0 = lo; rb0 = hi; has0 = true;
-                        } else {
-                            w1 = k; ra1 = lo; rb1 = hi; has1 = true;
-                        }
-                    }
-                    s.w0 = w0;
-                    s.w1 = w1;
-                    s.seed_k = k;
-                } else if (!QAGP && s.seeding) {
-                    ra0 = ya;
-                    rb0 = yb;
-                    if (s.seed_k == 0) has17 = true; else has0 = true;
-                } else {
-                    const int wi = s.wi;
-                    ra0 = S.A(wi);
-                    rb1 = S.B(wi);
-                    rb0 = ra1 = (ra0 + rb1) * 0.5;
-                    has0 = has1 = true;
-                }
-            }
-
-            // ---- sample (warp-converged) ----
-            QK q0, q1;
-            q0.estimate = q0.delta = q0.absvalue = q0.asc = 0.;
-            q1 = q0;
-            if (!QAGP && __any_sync(FULL, has17)) {
-                if (has17) q0 = qk_rule<8, RuleUnroll<F2T, 8>::value>(g, ra0, rb0);
-            }
-#pragma unroll 1
-            for (int hh = 0; hh < 2; ++hh) {
-                const bool on = hh ? has1 : has0;
-                if (on) {
-                    const QK q = qk_rule<12, RuleUnroll<F2T, 12>::value>(g, hh ? ra1 : ra0, hh ? rb1 : rb0);
-                    if (hh) q1 = q; else q0 = q;
-                }
-            }
-
-            // ---- bookkeeping (per lane, divergent, short) ----
-            if (s.active) {
-                if (QAGP && s.seeding) {
-                    bool dead = false;
-#pragma unroll 1
-                    for (int hh = 0; hh < 2 && !dead; ++hh) {
-                        const int w = hh ? s.w1 : s.w0;
-                        if (w < 0) continue;
-                        const QK q = hh ? q1 : q0;
-                        s.nevals += 25;
-                        if (q.estimate != q.estimate) {  // qagp.rs:112-119
-                            s.active = false;
-                            sink.put(s.idx, s.est0, s.delta0, s.nevals, ST_NAN);
-                            dead = true;
-                            break;
-                        }
-                        const int lv = (q.delta == q.asc && q.delta != 0.0) ? 1 : 0;
-                        s.est0 += q.estimate;
-                        s.delta0 += q.delta;
-                        s.abs0 += q.absvalue;
-                        s.asc0 += q.asc;
-                        ws_push(S, s, hh ? ra1 : ra0, hh ? rb1 : rb0, q.estimate, q.delta, lv);
-                    }
-                    if (!dead && s.seed_k >= s.nint) {  // qagp.rs:132-179
-                        s.seeding = false;
-                        double deltasum = 0.;
-                        for (int k = 0; k < s.size; ++k) {
-                            if (S.LV(k) > 0) S.D(k) = s.delta0;
-                            deltasum += S.D(k);
-                        }
-                        for (int k = 0; k < s.size; ++k) S.LV(k) = 0;
-                        ws_sort_results(S, s);
-                        const double tolerance = o.tol.to_abs(fabs(s.est0));
-                        const double round_off = 100. * F64_EPSILON * s.abs0;
-                        if (s.delta0 <= round_off && s.delta0 > tolerance) {
-                            s.active = false;
-                            sink.put(s.idx, s.est0, s.delta0, s.nevals, ST_ROUNDOFF_ERROR);
-                        } else if ((s.delta0 <= tolerance && s.delta0 != s.asc0) || s.delta0 == 0.0) {
-                            s.active = false;
-                            sink.put(s.idx, s.est0, s.delta0, s.nevals, ST_NONE);
-                        } else if ((unsigned long long)s.nevals == budget0) {
-                            s.active = false;
-                            sink.put(s.idx, s.est0, s.delta0, s.nevals, ST_INSUFFICIENT_ITERATION);
-                        } else {
-                            tab_append(S, s, s.est0);
-                            s.area = s.est0;
-                            s.res_ext = s.est0;
-                            s.err_ext = F64_MAX;
-                            s.errsum = deltasum;
-                            s.eolr = deltasum;
-                            s.ertest = tolerance;
-                            s.max_iters = (unsigned long long)s.nint + (budget0 - s.nevals) / 50ull;
-                            s.iteration = (unsigned long long)s.nint;
-                        }
-                    }
-                } else if (!QAGP && s.seeding) {
-                    // initial_integral (qags.rs:315-376), one pass per trip
-                    const int pass = s.seed_k;
-                    const QK q = q0;
-                    s.nevals = pass ? 42u : 17u;
-                    const double tolerance = o.tol.to_abs(fabs(q.estimate));
-                    const double round_off = 100. * F64_EPSILON * q.absvalue;
-                    if (q.estimate != q.estimate) {
-                        s.active = false;
-                        sink.put(s.idx, q.estimate, q.delta, s.nevals, ST_NAN);
-                    } else if ((q.delta <= tolerance && q.delta != q.asc) || q.delta == 0.0) {
-                        s.active = false;
-                        sink.put(s.idx, q.estimate, q.delta, s.nevals, ST_NONE);
-                    } else if (q.delta <= round_off && q.delta > tolerance) {
-                        s.active = false;
-                        sink.put(s.idx, q.estimate, q.delta, s.nevals, ST_ROUNDOFF_ERROR);
-                    } else if (budget0 < (unsigned long long)(42 + pass * 25)) {
-                        s.active = false;
-                        sink.put(s.idx, q.estimate, q.delta, s.nevals, ST_INSUFFICIENT_ITERATION);
-                    } else if (pass == 0 && !(q.delta > tolerance * 1024.)) {
-                        s.seed_k = 1;
-                    } else {
-                        // main loop set-up (qags.rs:98-118)
-                        s.seeding = false;
-                        s.est0 = q.estimate;
-                        s.delta0 = q.delta;
-                        s.abs0 = q.absvalue;
-                        s.asc0 = 0.;
-                        s.max_iters = (budget0 - s.nevals) / 50ull;
-                        s.limit = (int)reserve_cap(cap0, s.max_iters + 1ull);
-                        tb->rsv[s.idx] = (RSV_QAGS << 28) | s.nevals;
-                        ws_push(S, s, ya, yb, s.est0, s.delta0, 0);
-                        tab_append(S, s, s.est0);
-                        s.area = s.est0;
-                        s.errsum = s.delta0;
-                        s.res_ext = s.est0;
-                        s.err_ext = F64_MAX;
-                        s.ertest = 0.;
-                        s.eolr = 0.;
-                        s.iteration = 1;
-                        if (s.iteration > s.max_iters) adaptive_epilogue(S, s, sink);
-                    }
-                } else {
-                    const int wi = s.wi;
-                    adaptive_step<QAGP>(S, s, o.tol, budget0, sink, ra0, rb1, rb0, S.E(wi), S.D(wi),
-                                        S.LV(wi), q0, q1);
-                }
-            }
-        }
-        __syncwarp();
-    }
-
-    // Evaluate the outer integrand at K <= 64 nodes t_k = node(k) given in the reference's
-    // evaluation order; val[r] receives the value of node lane + 32 r.
-    template <class NodeFn>
-    GKQ_DEV void run_group(int K, NodeFn node, double (&val)[2]) {
-        const unsigned FULL = 0xffffffffu;
-        const int lane = threadIdx.x & 31;
-        const double nan = __longlong_as_double(0x7ff8000000000000ll);
-        val[0] = val[1] = 0.;
-        if (!exact) {
-            const unsigned long long budget0 = o.budget_now();
-            run_lanes(K, node, budget0);
-            // order the group: evaluations spent before each call, first failing call
-            unsigned nev[2], st[2], rsv[2], incl[2];
-            unsigned carry = 0;
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int k = lane + 32 * r;
-                const bool on = k < K;
-                nev[r] = on ? tb->nev[k] : 0u;
-                st[r] = on ? tb->st[k] : (unsigned)ST_NONE;
-                rsv[r] = on ? tb->rsv[k] : 0u;
-                unsigned v = nev[r];
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const unsigned up = __shfl_up_sync(FULL, v, d);
-                    if (lane >= d) v += up;
-                }
-                incl[r] = v + carry;
-                carry = __shfl_sync(FULL, incl[r], 31);
-            }
-            const unsigned m0 = __ballot_sync(FULL, st[0] != ST_NONE);
-            const unsigned m1 = __ballot_sync(FULL, st[1] != ST_NONE);
-            const int e = m0 ? (__ffs(m0) - 1) : (m1 ? 32 + (__ffs(m1) - 1) : 64);
-            bool fine = true;
-            unsigned long long mine[2];
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int k = lane + 32 * r;
-                const unsigned excl = incl[r] - nev[r];
-                mine[r] = budget0 >= excl ? budget0 - excl : 0ull;
-                const unsigned kind = rsv[r] >> 28, rn = rsv[r] & 0x0fffffffu;
-                const unsigned long long margin =
-                    2ull * nev[r] + 200ull + (kind == RSV_QAGP ? 100ull * rn : 0ull);
-                if (k < K && k <= e && excl != 0u && !(budget0 >= excl && mine[r] >= margin)) fine = false;
-            }
-            if (__all_sync(FULL, fine)) {
-                // calls after the first failure get a zero budget: no evaluations, an
-                // InsufficientIteration of their own, NaN into the outer rule
-                const unsigned spent0 = __shfl_sync(FULL, incl[0], e < 32 ? e : 31);
-                const unsigned spent1 = __shfl_sync(FULL, incl[1], (e >= 32 && e < 64) ? e - 32 : 31);
-                o.nevals += (e < 32) ? spent0 : spent1;
-                const unsigned st_e0 = __shfl_sync(FULL, st[0], e < 32 ? e : 0);
-                const unsigned st_e1 = __shfl_sync(FULL, st[1], (e >= 32 && e < 64) ? e - 32 : 0);
-                if (e < 64 && o.error == ST_NONE) o.error = e < 32 ? st_e0 : st_e1;
-                // capacity of the persistent inner workspace, replayed in call order
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int k = lane + 32 * r;
-                    const unsigned kind = rsv[r] >> 28;
-                    const unsigned long long rn = rsv[r] & 0x0fffffffu;
-                    unsigned long long req = 0;
-                    if (k < K && k <= e) {
-                        if (kind == RSV_QAGS) req = (mine[r] - rn) / 50ull + 1ull;
-                        if (kind == RSV_QAGP) req = rn + (mine[r] - 25ull * rn) / 50ull;
-                    }
-                    unsigned need = __ballot_sync(FULL, req > o.inner_cap);
-                    while (need) {
-                        const int w = __ffs(need) - 1;
-                        const unsigned long long rq = __shfl_sync(FULL, req, w);
-                        o.inner_cap = reserve_cap(o.inner_cap, rq);
-                        need = __ballot_sync(FULL, req > o.inner_cap) & ~((2u << w) - 1u);
-                    }
-                    if (k < K) {
-                        double v = (st[r] != ST_NONE || k > e) ? nan : tb->est[k];
-                        if (o.transform) {
-                            const double coef = 1. / (1. - fabs(node(k)));
-                            v = v * coef * coef;
-                        }
-                        val[r] = v;
-                    }
-                }
-                __syncwarp();
-                return;
-            }
-            exact = true;
-        }
-        // exact path: all lanes, same call, in order
-#pragma unroll 1
-        for (int k2 = 0; k2 < K; ++k2) {
-            const double v = o(node(k2));
-            if (k2 == lane) val[0] = v;
-            if (k2 == lane + 32) val[1] = v;
-        }
-    }
-
-    template <int N>
-    GKQ_DEV QK rule(double a, double b) {
-        using R = Rule<N>;
-        const unsigned FULL = 0xffffffffu;
-        const double center = 0.5 * (a + b);
-        const double half_length = 0.5 * (b - a);
-        // single/qk/naive.rs:60-68: lower nodes j = 0..N-1, upper nodes, centre
-        auto node = [&](int k) {
-            if (k >= 2 * N) return center;
-            const double abscissa = half_length * R::xgk(k < N ? k : k - N);
-            return k < N ? center - abscissa : center + abscissa;
-        };
-        double val[2];
-        run_group(2 * N + 1, node, val);
-        double fv1[N], fv2[N];
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            fv1[j] = __shfl_sync(FULL, val[0], j);
-            fv2[j] = __shfl_sync(FULL, val[0], N + j);
-        }
-        const double fc = __shfl_sync(FULL, val[0], 2 * N);
-        return qk_reduce<N>(fv1, fv2, fc, a, b);
-    }
-
-    GKQ_DEV void pair(double a, double c, double b, QK& q1, QK& q2) {
-        using R = Rule<12>;
-        const unsigned FULL = 0xffffffffu;
-        auto node = [&](int k) {
-            const int half = k >= 25 ? 1 : 0;
-            const int t = k - 25 * half;
-            const double lo = half ? c : a, hi = half ? b : c;
-            const double center = 0.5 * (lo + hi);
-            const double half_length = 0.5 * (hi - lo);
-            if (t >= 24) return center;
-            const double abscissa = half_length * R::xgk(t < 12 ? t : t - 12);
-            return t < 12 ? center - abscissa : center + abscissa;
-        };
-        double val[2];
-        run_group(50, node, val);
-        auto pull = [&](int slot) {
-            return slot < 32 ? __shfl_sync(FULL, val[0], slot) : __shfl_sync(FULL, val[1], slot - 32);
-        };
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            double fv1[12], fv2[12];
-#pragma unroll
-            for (int j = 0; j < 12; ++j) {
-                fv1[j] = pull(25 * half + j);
-                fv2[j] = pull(25 * half + 12 + j);
-            }
-            const double fc = pull(25 * half + 24);
-            const QK q = qk_reduce<12>(fv1, fv2, fc, half ? c : a, half ? b : c);
-            if (half) q2 = q; else q1 = q;
-        }
-    }
-};
-
-constexpr int NBLOCK = 128;  // k_nested_warp: 4 outer integrals in flight per block
-
-template <class F2T, bool QAGP, int NPARAMS>
-__global__ void __launch_bounds__(NBLOCK, 4) k_nested_warp(const Batch2D P) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const unsigned long long t = (unsigned long long)blockIdx.x * NBLOCK + threadIdx.x;
-    Slab Sout, Sin;
-    Sout.d = P.slab.dbase + t;
-    Sout.w = P.slab.wbase + t;
-    Sout.stride = P.slab.stride;
-    Sout.cap = P.cap_outer;
-    const unsigned long long outer_d = slab_doubles(P.cap_outer, P.npts_max + 2);
-    Sin.d = Sout.d + outer_d * P.slab.stride;
-    Sin.w = Sout.w + slab_ints(P.cap_outer) * P.slab.stride;
-    Sin.stride = P.slab.stride;
-    Sin.cap = P.cap_inner;
-    __shared__ Lane s_lanes[NBLOCK];
-    __shared__ TaskBoard s_boards[NBLOCK / 32];
-
-    const unsigned long long total = P.worklist ? *P.worklist_count : (unsigned long long)P.n;
-    unsigned long long* head = QAGP ? &P.ctl->headP : &P.ctl->head2;
-    for (;;) {
-        unsigned long long slot = 0;
-        if (lane == 0) slot = atomicAdd(head, 1ull);
-        slot = __shfl_sync(FULL, slot, 0);
-        if (slot >= total) break;
-        const unsigned long long i = P.worklist ? (unsigned long long)P.worklist[slot] : slot;
-        const double* my_pts = P.pts_xy;
-        int my_npts = P.npts;
-        if (P.pts_offsets) {
-            const long long o0 = P.pts_offsets[i];
-            my_pts = P.pts_xy + 2 * o0;
-            my_npts = (int)(P.pts_offsets[i + 1] - o0);
-        }
-
-        WarpOuter<F2T, QAGP> G;
-#pragma unroll
-        for (int k = 0; k < MAX_PARAMS; ++k)
-            G.o.f.p[k] = (k < NPARAMS)
-                             ? (P.fparam_stride ? P.fparams[(long long)k * P.fparam_stride + (long long)i]
-                                                : P.fparams[k])
-                             : 0.0;
-        G.o.yr.id = P.yrange_id;
-        G.o.yr.q[0] = G.o.yr.q[1] = 0.;
-        for (int k = 0; k < P.nyparams && k < 2; ++k)
-            G.o.yr.q[k] = P.yparam_stride ? P.yparams[(long long)k * P.yparam_stride + (long long)i]
-                                          : P.yparams[k];
-        G.o.tol = P.tol;
-        G.o.total_evals = P.max_evals;
-        G.o.nevals = 0;
-        G.o.error = ST_NONE;
-        G.o.inner_cap = 0;  // WorkSpace::new()
-        G.o.Sin = Sin;
-        G.o.pts_xy = my_pts;
-        G.o.npts = my_npts;
-        G.exact = false;
-        G.ls = &s_lanes[threadIdx.x];
-        G.tb = &s_boards[threadIdx.x >> 5];
-
-        double xa = P.x0[(long long)i * P.range_stride];
-        double xb = P.x1[(long long)i * P.range_stride];
-        const bool xtr = !is_finite(xa) || !is_finite(xb);
-        if (xtr) {
-            xa = transform_point(xa);
-            xb = transform_point(xb);
-        }
-        G.o.transform = xtr;
-
-        unsigned long long outer_cap = 0;
-        const unsigned long long outer_evals = P.max_evals / 17ull;
-        Res r;
-        if (QAGP) {
-            const double* p = my_pts;
-            auto user_pt = [p, xtr](int k) {
-                const double x = p[2 * k];
-                return xtr ? transform_point(x) : x;
-            };
-            r = seq_qagp<RM_COLLECTIVE, 1>(G, xa, xb, xtr, user_pt, my_npts, P.tol, outer_evals, outer_cap, Sout);
-        } else {
-            r = seq_qags<RM_COLLECTIVE, 1>(G, xa, xb, P.tol, outer_evals, outer_cap, Sout);
-        }
-        if (lane == 0)
-            write_result(P.out, (long long)i, r.est, r.dlt, (uint32_t)G.o.nevals,
-                         G.o.error != ST_NONE ? G.o.error : r.st);
-        __syncwarp();
-    }
-}
+}  // namespace gkq
+#include "kernels_2d_pool.cuh"
+namespace gkq {
 
 struct Launch2D {
     void (*run[2])(const Batch2D&, int grid, cudaStream_t);  // [0] QAGS2, [1] QAGP2 (thread per outer integral)
     int (*occupancy[2])();
-    void (*run_warp[2])(const Batch2D&, int grid, cudaStream_t);  // warp per outer integral (NBLOCK threads)
-    int (*occupancy_warp[2])();
+    void (*run_pool[2])(const Batch2D&, int grid, cudaStream_t);  // k_nested_pool (PB threads per block)
+    int (*occupancy_pool[2])();
 };
 template <int ID>
 Launch2D make_launch2d();
@@ -1056,20 +579,40 @@ GKQ_F2_LIST(GKQ_DECL_F2)
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_nested<F2<ID>, true, NP>, BLOCK, 0); \
             return nb;                                                                            \
         };                                                                                        \
-        L.run_warp[0] = [](const Batch2D& P, int grid, cudaStream_t st) {                         \
-            k_nested_warp<F2<ID>, false, NP><<<grid, NBLOCK, 0, st>>>(P);                         \
+        L.run_pool[0] = [](const Batch2D& P, int grid, cudaStream_t st) {                         \
+            static bool once = false;                                                             \
+            const int smem = (PB / 32) * (int)sizeof(PoolShared);                                 \
+            if (!once) {                                                                          \
+                cudaFuncSetAttribute(k_nested_pool<F2<ID>, false, NP>,                            \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem);          \
+                once = true;                                                                      \
+            }                                                                                     \
+            k_nested_pool<F2<ID>, false, NP><<<grid, PB, smem, st>>>(P);                          \
         };                                                                                        \
-        L.run_warp[1] = [](const Batch2D& P, int grid, cudaStream_t st) {                         \
-            k_nested_warp<F2<ID>, true, NP><<<grid, NBLOCK, 0, st>>>(P);                          \
+        L.run_pool[1] = [](const Batch2D& P, int grid, cudaStream_t st) {                         \
+            static bool once = false;                                                             \
+            const int smem = (PB / 32) * (int)sizeof(PoolShared);                                 \
+            if (!once) {                                                                          \
+                cudaFuncSetAttribute(k_nested_pool<F2<ID>, true, NP>,                             \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem);          \
+                once = true;                                                                      \
+            }                                                                                     \
+            k_nested_pool<F2<ID>, true, NP><<<grid, PB, smem, st>>>(P);                           \
         };                                                                                        \
-        L.occupancy_warp[0] = []() {                                                              \
+        L.occupancy_pool[0] = []() {                                                              \
             int nb = 0;                                                                           \
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_nested_warp<F2<ID>, false, NP>, NBLOCK, 0); \
+            const int smem = (PB / 32) * (int)sizeof(PoolShared);                                 \
+            cudaFuncSetAttribute(k_nested_pool<F2<ID>, false, NP>,                                \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem);              \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_nested_pool<F2<ID>, false, NP>, PB, smem); \
             return nb;                                                                            \
         };                                                                                        \
-        L.occupancy_warp[1] = []() {                                                              \
+        L.occupancy_pool[1] = []() {                                                              \
             int nb = 0;                                                                           \
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_nested_warp<F2<ID>, true, NP>, NBLOCK, 0); \
+            const int smem = (PB / 32) * (int)sizeof(PoolShared);                                 \
+            cudaFuncSetAttribute(k_nested_pool<F2<ID>, true, NP>,                                 \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem);              \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_nested_pool<F2<ID>, true, NP>, PB, smem); \
             return nb;                                                                            \
         };                                                                                        \
         return L;                                                                                 \
