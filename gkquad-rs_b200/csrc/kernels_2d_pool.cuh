@@ -36,7 +36,7 @@
 namespace gkq {
 
 constexpr int PB = 128;                 // threads per block of k_nested_pool
-constexpr int POOL_R = 8;               // outer integrals per warp
+constexpr int POOL_R = 6;               // outer integrals per warp (shared memory: 16 warps per SM)
 constexpr int POOL_T = POOL_R * 50;     // board slots per warp (a bisection step posts 50 tasks)
 
 struct TripPlan {
@@ -48,7 +48,7 @@ struct TripPlan {
 // (the same phases k_adaptive runs; here for both levels of the nest)
 
 // Begin integral `idx` over the (already transformed) range [a, b].  `rsv` (optional) receives how
-// the call sized its workspace (RSV_* << 28 | n).
+// the call sized its workspace (RSV_* << 3 | n << 5; the low 3 bits are left for the status).
 template <bool QAGP, class Sink>
 GKQ_DEV void lane_start(const Slab& S, Lane& s, long long idx, double a, double b, bool transform,
                         const double* pts, int npts, int pts_stride, bool pts_pre_transform,
@@ -68,7 +68,7 @@ GKQ_DEV void lane_start(const Slab& S, Lane& s, long long idx, double a, double 
         }
         // ws.reserve(nint + (max_evals - nint*25)/50)   qagp.rs:83-84
         s.limit = (int)reserve_cap(cap0, s.nint + (budget - (unsigned long long)s.nint * 25ull) / 50ull);
-        if (rsv) *rsv = (RSV_QAGP << 28) | (uint32_t)s.nint;
+        if (rsv) *rsv = (RSV_QAGP << 3) | ((uint32_t)s.nint << 5);
         s.seeding = true;
         s.seed_k = 0;
         s.active = true;
@@ -210,7 +210,7 @@ GKQ_DEV void lane_finish(const Slab& S, Lane& s, const Tol& tol, unsigned long l
             s.asc0 = 0.;
             s.max_iters = (budget - s.nevals) / 50ull;
             s.limit = (int)reserve_cap(cap0, s.max_iters + 1ull);
-            if (rsv) *rsv = (RSV_QAGS << 28) | s.nevals;
+            if (rsv) *rsv = (RSV_QAGS << 3) | (s.nevals << 5);
             ws_push(S, s, wa, wb, s.est0, s.delta0, 0);
             tab_append(S, s, s.est0);
             s.area = s.est0;
@@ -248,14 +248,14 @@ struct PoolShared {
     Lane outer[POOL_R];
     OuterCtx ctx[POOL_R];
     double est[POOL_T];
-    uint32_t nev[POOL_T], st[POOL_T], rsv[POOL_T];
+    uint32_t nev[POOL_T], meta[POOL_T];  // meta = status | RSV_* << 3 | n << 5
 };
 struct PoolBoardSink {
     PoolShared* W;
     GKQ_DEV void put(long long t, double est, double, uint32_t nev, uint32_t st) const {
         W->est[t] = est;
         W->nev[t] = nev;
-        W->st[t] = st;
+        W->meta[t] = (W->meta[t] & ~7u) | st;
     }
 };
 struct PoolOuterSink {
@@ -268,7 +268,7 @@ struct PoolOuterSink {
 };
 
 template <class F2T, bool QAGP, int NPARAMS>
-__global__ void __launch_bounds__(PB, 3) k_nested_pool(const Batch2D P) {
+__global__ void __launch_bounds__(PB, 4) k_nested_pool(const Batch2D P) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned long long t = (unsigned long long)blockIdx.x * PB + threadIdx.x;
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(PB, 3) k_nested_pool(const Batch2D P) {
                             budget0 = c.budget0;
                             cap0 = c.inner_cap;
                             lane_start<QAGP>(Sin, s, tk, y0, y1, ytr, c.pts_xy + 1, c.npts, 2, false, budget0,
-                                             cap0, bsink, &W.rsv[tk]);
+                                             cap0, bsink, &W.meta[tk]);
                         }
                     }
                 }
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(PB, 3) k_nested_pool(const Batch2D P) {
                     }
                 }
                 if (s.active)
-                    lane_finish<QAGP>(Sin, s, P.tol, budget0, cap0, bsink, &W.rsv[s.idx], p, q0, q1, ya, yb);
+                    lane_finish<QAGP>(Sin, s, P.tol, budget0, cap0, bsink, &W.meta[s.idx], p, q0, q1, ya, yb);
             }
         }
         __syncwarp();
@@ -506,9 +506,9 @@ __global__ void __launch_bounds__(PB, 3) k_nested_pool(const Batch2D P) {
                         W.est[base + k] = nan;
                         continue;
                     }
-                    const uint32_t nev = W.nev[base + k], st = W.st[base + k], rsv = W.rsv[base + k];
-                    const uint32_t kind = rsv >> 28;
-                    const unsigned long long rn = rsv & 0x0fffffffu;
+                    const uint32_t nev = W.nev[base + k], meta = W.meta[base + k];
+                    const uint32_t st = meta & 7u, kind = (meta >> 3) & 3u;
+                    const unsigned long long rn = meta >> 5;
                     if (spent != 0ull) {
                         const unsigned long long margin = 2ull * nev + 200ull + (kind == RSV_QAGP ? 100ull * rn : 0ull);
                         if (budget0 < spent || budget0 - spent < margin) {
