@@ -148,20 +148,25 @@ template <class F>
 struct Wrapped {
     F f;
     bool transform;
-    GKQ_DEV double operator()(double x) const {
-        if (transform) {
+    // TR = whether the infinite-range map is on, as a compile-time constant (kernels that hoist
+    // the test out of the node loop); the run-time forms below dispatch on `transform`.
+    template <bool TR>
+    GKQ_DEV double at(double x) const {
+        if (TR) {
             double coef = 1. / (1. - fabs(x));
             double x2 = x * coef;
             return f(x2) * coef * coef;
         }
         return f(x);
     }
+    GKQ_DEV double operator()(double x) const { return transform ? at<true>(x) : at<false>(x); }
     // Two samples at once.  The integrand bodies run branch-free (FastMath) in ONE basic block so
     // that ptxas interleaves their dependent chains (DFMA latency is ~9 cycles, profiles/); the
     // rare out-of-range argument re-evaluates both samples through the always-valid path.
-    GKQ_DEV void pair(double x1, double x2, double& f1, double& f2) const {
+    template <bool TR>
+    GKQ_DEV void pair_t(double x1, double x2, double& f1, double& f2) const {
         double c1 = 1., c2 = 1.;
-        if (transform) {
+        if (TR) {
             c1 = 1. / (1. - fabs(x1));
             c2 = 1. / (1. - fabs(x2));
             x1 = x1 * c1;
@@ -180,10 +185,16 @@ struct Wrapped {
             f1 = f(x1);
             f2 = f(x2);
         }
-        if (transform) {
+        if (TR) {
             f1 = f1 * c1 * c1;
             f2 = f2 * c2 * c2;
         }
+    }
+    GKQ_DEV void pair(double x1, double x2, double& f1, double& f2) const {
+        if (transform)
+            pair_t<true>(x1, x2, f1, f2);
+        else
+            pair_t<false>(x1, x2, f1, f2);
     }
 };
 
@@ -242,6 +253,27 @@ GKQ_DEV QK qk_rule(const G& g, double a, double b) {
     }
     const double f_center = g(center);
     return qk_reduce<N>(fv1, fv2, f_center, a, b);
+}
+// The same rule with the infinite-range test hoisted out of the node loop (two copies of the
+// loop: worth it in the flat bulk kernels, where the loop is all there is).
+template <int N, int UNROLL, bool TR, class G>
+GKQ_DEV QK qk_rule_fixed(const G& g, double a, double b) {
+    using R = Rule<N>;
+    double fv1[N], fv2[N];
+    const double center = 0.5 * (a + b);
+    const double half_length = 0.5 * (b - a);
+#pragma unroll UNROLL
+    for (int j = 0; j < N; ++j) {
+        double abscissa = half_length * R::xgk(j);
+        g.template pair_t<TR>(center - abscissa, center + abscissa, fv1[j], fv2[j]);
+    }
+    const double f_center = g.template at<TR>(center);
+    return qk_reduce<N>(fv1, fv2, f_center, a, b);
+}
+template <int N, int UNROLL, class G>
+GKQ_DEV QK qk_rule_hoisted(const G& g, double a, double b) {
+    if (g.transform) return qk_rule_fixed<N, UNROLL, true>(g, a, b);
+    return qk_rule_fixed<N, UNROLL, false>(g, a, b);
 }
 
 // Warp-cooperative 25-point rule on up to two ranges (one bisection step = 50 samples) of ONE

@@ -184,11 +184,22 @@ struct RuleUnroll {
     // heavy (transcendental) bodies: one node pair per loop trip; light bodies: fully unrolled
     static constexpr int value = F::HEAVY ? 1 : N;
 };
+// the flat initial-pass kernels (tuning knobs for A/B builds)
+#ifndef GKQ_INIT_UNROLL_HEAVY
+#define GKQ_INIT_UNROLL_HEAVY 1
+#endif
+#ifndef GKQ_INIT17_MIN_BLOCKS
+#define GKQ_INIT17_MIN_BLOCKS 4
+#endif
+template <class F, int N>
+struct InitUnroll {
+    static constexpr int value = F::HEAVY ? GKQ_INIT_UNROLL_HEAVY : N;
+};
 
 // ---- QAGS initial passes -------------------------------------------------------------------
 // PASS 0: N = 8 (qk17) over the whole batch (or `worklist`); PASS 1: N = 12 (qk25) over list25.
 template <class F, int N, int NPARAMS>
-__global__ void __launch_bounds__(BLOCK, (N == 8) ? 4 : 3) k_qags_init(const Batch1D P) {
+__global__ void __launch_bounds__(BLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : 3) k_qags_init(const Batch1D P) {
     constexpr int PASS = (N == 8) ? 0 : 1;
     long long total;
     if (PASS == 0)
@@ -209,7 +220,7 @@ __global__ void __launch_bounds__(BLOCK, (N == 8) ? 4 : 3) k_qags_init(const Bat
             load_range(P, i, a, b, g.transform);
             load_functor(g.f, P, i, NPARAMS);
 
-            const QK q = qk_rule<N, RuleUnroll<F, N>::value>(g, a, b);
+            const QK q = qk_rule_hoisted<N, InitUnroll<F, N>::value>(g, a, b);
             const uint32_t nevals = (PASS == 0) ? 17u : 42u;
 
             // initial_integral, pass i = PASS (qags.rs:336-372)

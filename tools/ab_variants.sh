@@ -1,0 +1,8 @@
+# A/B of kernel-tuning builds: bash tools/ab_variants.sh lib lib_x ...   (directories under gkquad-rs_b200/)
+for v in "$@"; do
+  echo "== $v"
+  GKQ_LIB=$PWD/gkquad-rs_b200/$v/libgkquad_b200.so python bench.py --steps 64 --warmup 16 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
+import json,sys
+j=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('value %.4g ms/step %.4f'%(j['value'], j['ms_per_step']), [(k['kernel'], round(1e3*k['ms'],1)) for k in j['roofline']['kernels']])"
+done
