@@ -957,7 +957,8 @@ int gkq_qk_batch(gkq_handle_t h, int rule, int functor_id, int64_t n, const doub
                  const double* b, int64_t range_stride, const double* params,
                  int64_t param_stride, double* out4, void* stream) {
     if (!h) return GKQ_ERR_INVALID_ARGUMENT;
-    if (rule != 17 && rule != 25) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "rule must be 17 or 25");
+    if (rule != 17 && rule != 25 && rule != 33 && rule != 41 && rule != 49 && rule != 57)
+        return fail(h, GKQ_ERR_INVALID_ARGUMENT, "rule must be 17, 25, 33, 41, 49 or 57");
     if (functor_id < 0 || functor_id >= F1_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown functor id");
     if (n < 0 || !a || !b || !out4) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "bad argument");
     if (F1_TABLE[functor_id].nparams > 0 && !params) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "params is NULL");
@@ -972,10 +973,7 @@ int gkq_qk_batch(gkq_handle_t h, int rule, int functor_id, int64_t n, const doub
     P.params = params;
     P.param_stride = param_stride;
     const int grid = (int)((n + BLOCK - 1) / BLOCK);
-    if (rule == 17)
-        h->l1[functor_id].qk17(P, out4, grid, (cudaStream_t)stream);
-    else
-        h->l1[functor_id].qk25(P, out4, grid, (cudaStream_t)stream);
+    h->l1[functor_id].qk[(rule - 17) / 8](P, out4, grid, (cudaStream_t)stream);
     return launch_check(h, "k_qk_batch");
 }
 

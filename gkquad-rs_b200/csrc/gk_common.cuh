@@ -33,56 +33,48 @@ enum : uint32_t {
 };
 enum : int { ALGO_AUTO = 0, ALGO_QAGS = 1, ALGO_QAGP = 2 };
 
-// Node tables of the 17- and 25-point Kronrod rules (values: single/qk/mod.rs:78-148).
+// Node tables of the Kronrod rules (values: single/qk/mod.rs:78-412; gk_tables.inc is generated
+// from first principles by tools/gen_gk_tables.py and checked bit-identical to those literals).
 // All lanes of a warp read the same entry at the same time (thread-per-integral mapping),
-// so constant memory broadcasts them at register speed.
+// so constant memory broadcasts them at register speed.  The adaptive drivers use the 17- and
+// 25-point rules only (qags.rs:315-376); 33 ... 57 are the public rule-level entries
+// (single/qk/mod.rs:44-73) behind gkq_qk_batch.
+#include "gk_tables.inc"
 template <int N> struct Rule;
-static __constant__ double c_xgk17[8] = {
-    0.183434642495649804939476142360184, 0.360701097928131957192548622296891,
-    0.525532409916328985817739049189246, 0.672354070945158677156310738092831,
-    0.796666477413626739591553936475830, 0.894120906847456421948361017538251,
-    0.960289856497536231683560868569473, 0.993379875881716155935888069019671};
-static __constant__ double c_wg17[4] = {
-    0.362683783378361982965150449277196, 0.313706645877887287337962201986601,
-    0.222381034453374470544355994426241, 0.101228536290376259152531354309962};
-static __constant__ double c_wgk17[8] = {
-    0.181400025068034643061748525172550, 0.172070608555211311857294880203857,
-    0.156652606168188400490248088486969, 0.136263109255172215262338745254506,
-    0.111646370826839613222108158933941, 0.082482298931358330688625193445608,
-    0.049439395002139308500363969446998, 0.017822383320710355152786961202750};
-static __constant__ double c_xgk25[12] = {
-    0.125233408511468915472441369463853, 0.248505748320469276267790960362718,
-    0.367831498998180193752691536643718, 0.481339450478157092935943615018832,
-    0.587317954286617447296702418940534, 0.684059895470055893944929100341155,
-    0.769902674194304687036893833212818, 0.843558124161153244792141885059839,
-    0.904117256370474856678465866119096, 0.950537795943121296549060195131619,
-    0.981560634246719250690549090149281, 0.996933922529595426912350237258385};
-static __constant__ double c_wg25[6] = {
-    0.249147045813402785000562436042951, 0.233492536538354808760849898924878,
-    0.203167426723065921749064455809798, 0.160078328543346226334652529543359,
-    0.106939325995318430960254718193996, 0.047175336386511827194615961485017};
-static __constant__ double c_wgk25[12] = {
-    0.124584164536156073437312473209229, 0.121626303523948383246099758091310,
-    0.116712053501756826293580745305730, 0.110022604977644072635907398742250,
-    0.101649732279060277715688770491228, 0.091549468295049210528171939739614,
-    0.079920275333601701493392609529783, 0.067250907050839930304940940047316,
-    0.053697017607756251228889163320458, 0.038915230469299477115089632285863,
-    0.023036084038982232591084580367969, 0.008257711433168395757693922439212};
+static __constant__ double c_xgk17[8] = {GK_XGK17};
+static __constant__ double c_wg17[4] = {GK_WG17};
+static __constant__ double c_wgk17[8] = {GK_WGK17};
+static __constant__ double c_xgk25[12] = {GK_XGK25};
+static __constant__ double c_wg25[6] = {GK_WG25};
+static __constant__ double c_wgk25[12] = {GK_WGK25};
+static __constant__ double c_xgk33[16] = {GK_XGK33};
+static __constant__ double c_wg33[8] = {GK_WG33};
+static __constant__ double c_wgk33[16] = {GK_WGK33};
+static __constant__ double c_xgk41[20] = {GK_XGK41};
+static __constant__ double c_wg41[10] = {GK_WG41};
+static __constant__ double c_wgk41[20] = {GK_WGK41};
+static __constant__ double c_xgk49[24] = {GK_XGK49};
+static __constant__ double c_wg49[12] = {GK_WG49};
+static __constant__ double c_wgk49[24] = {GK_WGK49};
+static __constant__ double c_xgk57[28] = {GK_XGK57};
+static __constant__ double c_wg57[14] = {GK_WG57};
+static __constant__ double c_wgk57[28] = {GK_WGK57};
 
-template <> struct Rule<8> {
-    static constexpr int NPTS = 17;
-    static constexpr double WCK = 0.184446405744691643528970955705643;
-    GKQ_DEV static double xgk(int j) { return c_xgk17[j]; }
-    GKQ_DEV static double wgk(int j) { return c_wgk17[j]; }
-    GKQ_DEV static double wg(int j) { return c_wg17[j]; }
-};
-template <> struct Rule<12> {
-    static constexpr int NPTS = 25;
-    static constexpr double WCK = 0.125556893905474335304296132860078;
-    GKQ_DEV static double xgk(int j) { return c_xgk25[j]; }
-    GKQ_DEV static double wgk(int j) { return c_wgk25[j]; }
-    GKQ_DEV static double wg(int j) { return c_wg25[j]; }
-};
+#define GKQ_RULE(N_, NPTS_)                                                     \
+    template <> struct Rule<N_> {                                               \
+        static constexpr int NPTS = NPTS_;                                      \
+        static constexpr double WCK = GK_WCK##NPTS_;                            \
+        GKQ_DEV static double xgk(int j) { return c_xgk##NPTS_[j]; }            \
+        GKQ_DEV static double wgk(int j) { return c_wgk##NPTS_[j]; }            \
+        GKQ_DEV static double wg(int j) { return c_wg##NPTS_[j]; }              \
+    };
+GKQ_RULE(8, 17)
+GKQ_RULE(12, 25)
+GKQ_RULE(16, 33)
+GKQ_RULE(20, 41)
+GKQ_RULE(24, 49)
+GKQ_RULE(28, 57)
+#undef GKQ_RULE
 
 // Tolerance::to_abs (common.rs:34-41).  fmax/fmin return the non-NaN operand, which is
 // what Rust's f64::max / f64::min do.

@@ -711,7 +711,7 @@ __global__ void __launch_bounds__(BLOCK) k_qk_batch(const Batch1D P, double* out
     g.transform = false;  // the public rules take finite ranges only (naive.rs:53)
     load_functor(g.f, P, i, NPARAMS);
     const double a = P.a[i * P.range_stride], b = P.b[i * P.range_stride];
-    const QK q = qk_rule<N, RuleUnroll<F, N>::value>(g, a, b);
+    const QK q = qk_rule<N, (N <= 12) ? RuleUnroll<F, N>::value : 1>(g, a, b);
     out4[i] = q.estimate;
     out4[P.n + i] = q.delta;
     out4[2 * P.n + i] = q.absvalue;
@@ -737,8 +737,7 @@ struct Launch1D {
     void (*qags_first)(const Batch1D&, int grid, cudaStream_t);
     void (*qags_loop)(const Batch1D&, int grid, cudaStream_t);
     void (*qagp)(const Batch1D&, int grid, cudaStream_t);
-    void (*qk17)(const Batch1D&, double* out4, int grid, cudaStream_t);
-    void (*qk25)(const Batch1D&, double* out4, int grid, cudaStream_t);
+    void (*qk[6])(const Batch1D&, double* out4, int grid, cudaStream_t);  // 17, 25, 33, 41, 49, 57 points
     void (*eval)(const Batch1D&, const double* x, double* y, int grid, cudaStream_t);
     int (*occupancy_loop)();   // resident blocks per SM of the persistent kernels
     int (*occupancy_qagp)();
@@ -769,11 +768,23 @@ GKQ_F1_LIST(GKQ_DECL_F1)
         L.qagp = [](const Batch1D& P, int grid, cudaStream_t st) {                                   \
             k_adaptive<F1<ID>, true, NP><<<grid, ABLOCK, 0, st>>>(P);                                 \
         };                                                                                           \
-        L.qk17 = [](const Batch1D& P, double* o, int grid, cudaStream_t st) {                        \
-            k_qk_batch<F1<ID>, 8, NP><<<grid, BLOCK, 0, st>>>(P, o);                                 \
+        L.qk[0] = [](const Batch1D& P, double* o, int grid, cudaStream_t st) {                       \
+            k_qk_batch<F1<ID>, 8, NP><<<grid, BLOCK, 0, st>>>(P, o);                                \
         };                                                                                           \
-        L.qk25 = [](const Batch1D& P, double* o, int grid, cudaStream_t st) {                        \
+        L.qk[1] = [](const Batch1D& P, double* o, int grid, cudaStream_t st) {                       \
             k_qk_batch<F1<ID>, 12, NP><<<grid, BLOCK, 0, st>>>(P, o);                                \
+        };                                                                                           \
+        L.qk[2] = [](const Batch1D& P, double* o, int grid, cudaStream_t st) {                       \
+            k_qk_batch<F1<ID>, 16, NP><<<grid, BLOCK, 0, st>>>(P, o);                                \
+        };                                                                                           \
+        L.qk[3] = [](const Batch1D& P, double* o, int grid, cudaStream_t st) {                       \
+            k_qk_batch<F1<ID>, 20, NP><<<grid, BLOCK, 0, st>>>(P, o);                                \
+        };                                                                                           \
+        L.qk[4] = [](const Batch1D& P, double* o, int grid, cudaStream_t st) {                       \
+            k_qk_batch<F1<ID>, 24, NP><<<grid, BLOCK, 0, st>>>(P, o);                                \
+        };                                                                                           \
+        L.qk[5] = [](const Batch1D& P, double* o, int grid, cudaStream_t st) {                       \
+            k_qk_batch<F1<ID>, 28, NP><<<grid, BLOCK, 0, st>>>(P, o);                                \
         };                                                                                           \
         L.eval = [](const Batch1D& P, const double* x, double* y, int grid, cudaStream_t st) {       \
             k_eval<F1<ID>, NP><<<grid, BLOCK, 0, st>>>(P, x, y);                                     \

@@ -205,7 +205,7 @@ class Engine:
         return BatchPlan(self, self.L.gkq_integrate_batch_host, args, False, r, (aa, bb, pp, po, pv, cfg))
 
     def qk_batch(self, rule: int, functor, a, b, params=None):
-        """single::qk17 / qk25 for a batch (device tensors in, [4, n] tensor out)."""
+        """single::qk17 ... qk57 for a batch (`rule` = number of points; host arrays in, [4, n] device tensor out)."""
         import torch
         fid, fname, npar, _ = self.functor(1, functor)
         dev = f"cuda:{self.device}"

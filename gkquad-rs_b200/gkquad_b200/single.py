@@ -207,3 +207,23 @@ def qk17(f: DeviceIntegrand, r) -> QKResult:
 def qk25(f: DeviceIntegrand, r) -> QKResult:
     """single/qk/mod.rs:36-41"""
     return _qk(25, f, r)
+
+
+def qk33(f: DeviceIntegrand, r) -> QKResult:
+    """single/qk/mod.rs:44-49"""
+    return _qk(33, f, r)
+
+
+def qk41(f: DeviceIntegrand, r) -> QKResult:
+    """single/qk/mod.rs:52-57"""
+    return _qk(41, f, r)
+
+
+def qk49(f: DeviceIntegrand, r) -> QKResult:
+    """single/qk/mod.rs:60-65"""
+    return _qk(49, f, r)
+
+
+def qk57(f: DeviceIntegrand, r) -> QKResult:
+    """single/qk/mod.rs:68-73"""
+    return _qk(57, f, r)

@@ -181,8 +181,9 @@ int gkq_integrate2_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor
                               uint32_t* out_status);
 
 /* ---- rule level -------------------------------------------------------------------------
- * replaces: single::qk17 / qk25 (single/qk/mod.rs:28-41) -> QKResult (:16-25).  `rule` is 17
- * or 25.  Device pointers; out4 is [4][n] SoA: estimate, delta, absvalue, asc. */
+ * replaces: single::qk17 / qk25 / qk33 / qk41 / qk49 / qk57 (single/qk/mod.rs:28-73) -> QKResult
+ * (:16-25).  `rule` is the number of points: 17, 25, 33, 41, 49 or 57.  Device pointers; out4 is
+ * [4][n] SoA: estimate, delta, absvalue, asc. */
 int gkq_qk_batch(gkq_handle_t h, int rule, int functor_id, int64_t n, const double* a,
                  const double* b, int64_t range_stride, const double* params,
                  int64_t param_stride, double* out4, void* stream);

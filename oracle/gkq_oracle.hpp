@@ -99,43 +99,35 @@ struct QKResult {
 };
 
 // ---------------------------------------------------------------------------
-// Node tables: single/qk/mod.rs:78-148 (data; qk33..57 tables :150-412 are in
-// gkq_oracle_tables_hi.hpp for the rule-level golden vectors).
+// Node tables: single/qk/mod.rs:78-412 (data).  gk_tables.inc is generated from first principles
+// by tools/gen_gk_tables.py (roots of the Legendre / Stieltjes polynomials at 120 digits) and was
+// checked there to be bit-identical to the reference's literals.
 // ---------------------------------------------------------------------------
-static const double XGK17[8] = {
-    0.183434642495649804939476142360184, 0.360701097928131957192548622296891,
-    0.525532409916328985817739049189246, 0.672354070945158677156310738092831,
-    0.796666477413626739591553936475830, 0.894120906847456421948361017538251,
-    0.960289856497536231683560868569473, 0.993379875881716155935888069019671};
-static const double WG17[4] = {
-    0.362683783378361982965150449277196, 0.313706645877887287337962201986601,
-    0.222381034453374470544355994426241, 0.101228536290376259152531354309962};
-static const double WCK17 = 0.184446405744691643528970955705643;
-static const double WGK17[8] = {
-    0.181400025068034643061748525172550, 0.172070608555211311857294880203857,
-    0.156652606168188400490248088486969, 0.136263109255172215262338745254506,
-    0.111646370826839613222108158933941, 0.082482298931358330688625193445608,
-    0.049439395002139308500363969446998, 0.017822383320710355152786961202750};
-
-static const double XGK25[12] = {
-    0.125233408511468915472441369463853, 0.248505748320469276267790960362718,
-    0.367831498998180193752691536643718, 0.481339450478157092935943615018832,
-    0.587317954286617447296702418940534, 0.684059895470055893944929100341155,
-    0.769902674194304687036893833212818, 0.843558124161153244792141885059839,
-    0.904117256370474856678465866119096, 0.950537795943121296549060195131619,
-    0.981560634246719250690549090149281, 0.996933922529595426912350237258385};
-static const double WG25[6] = {
-    0.249147045813402785000562436042951, 0.233492536538354808760849898924878,
-    0.203167426723065921749064455809798, 0.160078328543346226334652529543359,
-    0.106939325995318430960254718193996, 0.047175336386511827194615961485017};
-static const double WCK25 = 0.125556893905474335304296132860078;
-static const double WGK25[12] = {
-    0.124584164536156073437312473209229, 0.121626303523948383246099758091310,
-    0.116712053501756826293580745305730, 0.110022604977644072635907398742250,
-    0.101649732279060277715688770491228, 0.091549468295049210528171939739614,
-    0.079920275333601701493392609529783, 0.067250907050839930304940940047316,
-    0.053697017607756251228889163320458, 0.038915230469299477115089632285863,
-    0.023036084038982232591084580367969, 0.008257711433168395757693922439212};
+#include "gk_tables.inc"
+static const double XGK17[8] = {GK_XGK17};
+static const double WG17[4] = {GK_WG17};
+static const double WCK17 = GK_WCK17;
+static const double WGK17[8] = {GK_WGK17};
+static const double XGK25[12] = {GK_XGK25};
+static const double WG25[6] = {GK_WG25};
+static const double WCK25 = GK_WCK25;
+static const double WGK25[12] = {GK_WGK25};
+static const double XGK33[16] = {GK_XGK33};
+static const double WG33[8] = {GK_WG33};
+static const double WCK33 = GK_WCK33;
+static const double WGK33[16] = {GK_WGK33};
+static const double XGK41[20] = {GK_XGK41};
+static const double WG41[10] = {GK_WG41};
+static const double WCK41 = GK_WCK41;
+static const double WGK41[20] = {GK_WGK41};
+static const double XGK49[24] = {GK_XGK49};
+static const double WG49[12] = {GK_WG49};
+static const double WCK49 = GK_WCK49;
+static const double WGK49[24] = {GK_WGK49};
+static const double XGK57[28] = {GK_XGK57};
+static const double WG57[14] = {GK_WG57};
+static const double WCK57 = GK_WCK57;
+static const double WGK57[28] = {GK_WGK57};
 
 // single/util.rs:118-141
 inline double rescale_error(double err, double result_abs, double result_asc) {
@@ -226,6 +218,15 @@ template <class W>
 inline QKResult qk17(W& f, const Range& r) { return qk<8>(f, r, XGK17, WG17, WGK17, WCK17); }
 template <class W>
 inline QKResult qk25(W& f, const Range& r) { return qk<12>(f, r, XGK25, WG25, WGK25, WCK25); }
+// single/qk/mod.rs:44-73
+template <class W>
+inline QKResult qk33(W& f, const Range& r) { return qk<16>(f, r, XGK33, WG33, WGK33, WCK33); }
+template <class W>
+inline QKResult qk41(W& f, const Range& r) { return qk<20>(f, r, XGK41, WG41, WGK41, WCK41); }
+template <class W>
+inline QKResult qk49(W& f, const Range& r) { return qk<24>(f, r, XGK49, WG49, WGK49, WCK49); }
+template <class W>
+inline QKResult qk57(W& f, const Range& r) { return qk<28>(f, r, XGK57, WG57, WGK57, WCK57); }
 
 // single/util.rs:110-115
 inline bool subrange_too_small(double a1, double a2, double b2) {

@@ -202,7 +202,7 @@ struct Dispatch2<F2_COUNT> {
     static int go(int, const Batch2Args&) { return -1; }
 };
 
-// rule-level: qk17 / qk25 on one range
+// rule-level: qk17 ... qk57 on one range
 template <int ID>
 struct DispatchQK {
     static int go(int id, int rule, double a, double b, const double* p, double* out4) {
@@ -210,7 +210,15 @@ struct DispatchQK {
             F1<ID> f{p};
             IntegrandWrapper<F1<ID>> w{f, false};
             Range r{a, b};
-            QKResult q = (rule == 17) ? qk17(w, r) : qk25(w, r);
+            QKResult q;
+            switch (rule) {
+                case 17: q = qk17(w, r); break;
+                case 25: q = qk25(w, r); break;
+                case 33: q = qk33(w, r); break;
+                case 41: q = qk41(w, r); break;
+                case 49: q = qk49(w, r); break;
+                default: q = qk57(w, r); break;
+            }
             out4[0] = q.estimate;
             out4[1] = q.delta;
             out4[2] = q.absvalue;
@@ -315,7 +323,7 @@ int gkqo_integrate2_batch(int algo, int functor2_id, int yrange_id, int64_t n, c
 }
 
 int gkqo_qk(int rule, int functor_id, double a, double b, const double* params, double* out4) {
-    if (rule != 17 && rule != 25) return -2;
+    if (rule != 17 && rule != 25 && rule != 33 && rule != 41 && rule != 49 && rule != 57) return -2;
     return DispatchQK<0>::go(functor_id, rule, a, b, params, out4);
 }
 

@@ -56,6 +56,25 @@ def test_golden_qk(eng, case):
         assert_rel(out[3], case["asc"], 1e-13)
 
 
+@pytest.mark.parametrize("rule", [17, 25, 33, 41, 49, 57])
+def test_qk_batch_bit_exact(eng, rule):
+    """Rule level (single/qk/mod.rs:28-73) on a batch of IEEE-exact integrands: every field of QKResult
+    bit-identical to the oracle, forward and reversed ranges."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(rule)
+    n = 257
+    for f, lo, hi in (("lorentz_p", -3.0, 3.0), ("recip_p", 0.1, 5.0)):
+        p = rng.uniform(0.5, 50.0, (1, n))
+        a = rng.uniform(lo, 0.5 * (lo + hi), n)
+        b = rng.uniform(0.5 * (lo + hi), hi, n)
+        a[::3], b[::3] = b[::3].copy(), a[::3].copy()  # reversed ranges
+        out = eng.qk_batch(rule, f, a, b, p).cpu().numpy()
+        for i in range(n):
+            r = O.qk(rule, f, float(a[i]), float(b[i]), [float(p[0, i])])
+            got = out[:, i]
+            assert (got[0], got[1], got[2], got[3]) == (r["estimate"], r["delta"], r["absvalue"], r["asc"]), (f, i)
+
+
 @pytest.mark.parametrize("case", G["single"], ids=lambda c: c["name"])
 def test_golden_single(eng, case):
     etol = 1e-15 if case["functor"] in _EXACT_FUNCTORS else 1e-13
