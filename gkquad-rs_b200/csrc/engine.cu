@@ -829,7 +829,8 @@ static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functo
                                const double* params, int64_t param_stride, const int64_t* pts_offsets,
                                const double* pts, double* out_estimate, double* out_delta,
                                uint32_t* out_nevals, uint32_t* out_status, void* stream, bool patch,
-                               unsigned long long idx_offset, Control* ctl_zeroed = nullptr) {
+                               unsigned long long idx_offset, Control* ctl_zeroed = nullptr,
+                               const gkq_overrides* ov = nullptr, long long ov_offset = 0) {
     if (!h) return GKQ_ERR_INVALID_ARGUMENT;
     if (!cfg) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "cfg is NULL");
     if (functor_id < 0 || functor_id >= F1_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown functor id");
@@ -868,6 +869,11 @@ static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functo
     P.tol.rel_tol = cfg->tol.rel_tol;
     P.max_evals = cfg->max_evals;
     P.ws_capacity = cfg->workspace_capacity;
+    if (ov) {  // per-integral tolerance / budget (device arrays)
+        P.abs_tol_each = ov->abs_tol ? ov->abs_tol + ov_offset : nullptr;
+        P.rel_tol_each = ov->rel_tol ? ov->rel_tol + ov_offset : nullptr;
+        P.max_evals_each = ov->max_evals ? (const unsigned long long*)ov->max_evals + ov_offset : nullptr;
+    }
     P.out.estimate = out_estimate;
     P.out.delta = out_delta;
     P.out.nevals = out_nevals;
@@ -941,16 +947,25 @@ static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functo
     return GKQ_OK;
 }
 
+int gkq_integrate_batch_ex(gkq_handle_t h, const gkq_config* cfg, const gkq_overrides* ov,
+                           int functor_id, int64_t n, const double* a, const double* b,
+                           int64_t range_stride, const double* params, int64_t param_stride,
+                           const int64_t* pts_offsets, const double* pts, double* out_estimate,
+                           double* out_delta, uint32_t* out_nevals, uint32_t* out_status, void* stream) {
+    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
+    h->cur = 0;
+    return integrate_batch_ctx(h, cfg, functor_id, n, a, b, range_stride, params, param_stride,
+                               pts_offsets, pts, out_estimate, out_delta, out_nevals, out_status, stream,
+                               false, 0ull, nullptr, ov, 0);
+}
+
 int gkq_integrate_batch(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
                         const double* a, const double* b, int64_t range_stride,
                         const double* params, int64_t param_stride, const int64_t* pts_offsets,
                         const double* pts, double* out_estimate, double* out_delta,
                         uint32_t* out_nevals, uint32_t* out_status, void* stream) {
-    if (!h) return GKQ_ERR_INVALID_ARGUMENT;
-    h->cur = 0;
-    return integrate_batch_ctx(h, cfg, functor_id, n, a, b, range_stride, params, param_stride,
-                               pts_offsets, pts, out_estimate, out_delta, out_nevals, out_status, stream,
-                               false, 0ull);
+    return gkq_integrate_batch_ex(h, cfg, nullptr, functor_id, n, a, b, range_stride, params, param_stride,
+                                  pts_offsets, pts, out_estimate, out_delta, out_nevals, out_status, stream);
 }
 
 int gkq_qk_batch(gkq_handle_t h, int rule, int functor_id, int64_t n, const double* a,
@@ -1008,6 +1023,15 @@ int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_
                              const double* params, int64_t param_stride,
                              const int64_t* pts_offsets, const double* pts, double* out_estimate,
                              double* out_delta, uint32_t* out_nevals, uint32_t* out_status) {
+    return gkq_integrate_batch_host_ex(h, cfg, nullptr, functor_id, n, a, b, range_stride, params, param_stride,
+                                       pts_offsets, pts, out_estimate, out_delta, out_nevals, out_status);
+}
+
+int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq_overrides* ov_host,
+                                int functor_id, int64_t n, const double* a, const double* b,
+                                int64_t range_stride, const double* params, int64_t param_stride,
+                                const int64_t* pts_offsets, const double* pts, double* out_estimate,
+                                double* out_delta, uint32_t* out_nevals, uint32_t* out_status) {
     (void)pts;
     if (!h) return GKQ_ERR_INVALID_ARGUMENT;
     if (!cfg) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "cfg is NULL");
@@ -1057,7 +1081,8 @@ int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_
     const size_t N = (size_t)n;
     const size_t fixed_bytes = 64 * 8, ctl_bytes = sizeof(Control) * MAXC;
     const size_t in_doubles = (size_t)((range_stride ? 2 : 0) + np_batch) * N;
-    const size_t want = fixed_bytes + ctl_bytes + in_doubles * 8 + N * 24 + 256;
+    const int n_ov = ov_host ? (ov_host->abs_tol != nullptr) + (ov_host->rel_tol != nullptr) + (ov_host->max_evals != nullptr) : 0;
+    const size_t want = fixed_bytes + ctl_bytes + in_doubles * 8 + N * 24 + (size_t)n_ov * N * 8 + 256;
     if (want > h->stage_bytes) {
         if (h->stage_dev) GKQ_CUDA(h, cudaFree(h->stage_dev));
         h->stage_dev = nullptr;
@@ -1077,6 +1102,14 @@ int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_
     double* d_dlt = d_est + N;
     uint32_t* d_nev = (uint32_t*)(d_dlt + N);
     uint32_t* d_st = d_nev + N;
+    // per-integral tolerance / budget arrays (when given) behind the outputs
+    gkq_overrides ov_dev = {nullptr, nullptr, nullptr};
+    {
+        double* q = (double*)(d_st + N);
+        if (ov_host && ov_host->abs_tol) { ov_dev.abs_tol = q; q += N; }
+        if (ov_host && ov_host->rel_tol) { ov_dev.rel_tol = q; q += N; }
+        if (ov_host && ov_host->max_evals) { ov_dev.max_evals = (const uint64_t*)q; q += N; }
+    }
 
     // GKQ_HOST_TRACE=1: per-chunk timeline (timing events) printed to stderr -- tuning aid
     const bool trace = getenv("GKQ_HOST_TRACE") != nullptr;
@@ -1102,6 +1135,12 @@ int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_
         for (int k = 0; k < np; ++k) h->fixed_pin[2 + k] = params[k];
     GKQ_CUDA(h, cudaMemcpyAsync(d_fixed, h->fixed_pin, 64 * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
     GKQ_CUDA(h, cudaMemsetAsync(d_ctl, 0, sizeof(Control) * (size_t)nchunks, h->s_in));
+    if (ov_dev.abs_tol)
+        GKQ_CUDA(h, cudaMemcpyAsync((void*)ov_dev.abs_tol, ov_host->abs_tol, N * 8, cudaMemcpyHostToDevice, h->s_in));
+    if (ov_dev.rel_tol)
+        GKQ_CUDA(h, cudaMemcpyAsync((void*)ov_dev.rel_tol, ov_host->rel_tol, N * 8, cudaMemcpyHostToDevice, h->s_in));
+    if (ov_dev.max_evals)
+        GKQ_CUDA(h, cudaMemcpyAsync((void*)ov_dev.max_evals, ov_host->max_evals, N * 8, cudaMemcpyHostToDevice, h->s_in));
     const bool is_qags = cfg->algo == GKQ_ALGO_QAGS || (cfg->algo == GKQ_ALGO_AUTO && cfg->npoints == 0);
     const int rbi = h->rb_cur;
     if (is_qags) {
@@ -1140,7 +1179,8 @@ int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_
                                  range_stride ? d_b + off : d_b, range_stride,
                                  param_stride ? d_par + off : d_par, param_stride ? (int64_t)N : 0, nullptr,
                                  nullptr, d_est + off, d_dlt + off, d_nev + off, d_st + off, sc,
-                                 /*patch=*/true, (unsigned long long)off, d_ctl + c);
+                                 /*patch=*/true, (unsigned long long)off, d_ctl + c, n_ov ? &ov_dev : nullptr,
+                                 (long long)off);
         if (rc) break;
         GKQ_CUDA(h, cudaEventRecord(h->ev_done[c], sc));
         mark(sc);

@@ -70,6 +70,8 @@ struct alignas(16) StragglerRec {
     unsigned int ro1;              // roundoff_type1 after the first step
     unsigned int call;             // slot of the owning call in the outputs table
     unsigned int pad_;
+    double abs_tol, rel_tol;       // the integral's own tolerance and budget (per-integral overrides
+    unsigned long long max_evals;  // or the batch configuration)
 };
 struct RecCtl {
     unsigned long long count;  // records appended
@@ -119,6 +121,11 @@ struct Batch1D {
     Tol tol;
     unsigned long long max_evals;
     unsigned long long ws_capacity;
+    // optional per-integral overrides of tol.abs_tol / tol.rel_tol / max_evals (gkq_overrides);
+    // max_evals values are clamped to `max_evals`, which sizes the interval slabs
+    const double* abs_tol_each;
+    const double* rel_tol_each;
+    const unsigned long long* max_evals_each;
     Outputs out;
     // scratch owned by the handle
     Control* ctl;
@@ -143,6 +150,19 @@ GKQ_DEV void init_sink(RecordSink& s, const Batch1D& P) {
     s.recs = P.recs;
     s.call_outs = P.call_outs;
     s.patch = P.patch;
+}
+
+// The integral's own tolerance / evaluation budget (per-integral configuration).
+GKQ_DEV Tol load_tol(const Batch1D& P, long long i) {
+    Tol t = P.tol;
+    if (P.abs_tol_each) t.abs_tol = P.abs_tol_each[i];
+    if (P.rel_tol_each) t.rel_tol = P.rel_tol_each[i];
+    return t;
+}
+GKQ_DEV unsigned long long load_max_evals(const Batch1D& P, long long i) {
+    if (!P.max_evals_each) return P.max_evals;
+    const unsigned long long m = P.max_evals_each[i];
+    return m < P.max_evals ? m : P.max_evals;
 }
 
 template <class F>
@@ -219,14 +239,16 @@ __global__ void __launch_bounds__(BLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : 3) k
             double a, b;
             load_range(P, i, a, b, g.transform);
             load_functor(g.f, P, i, NPARAMS);
-
+            if (PASS == 0 && P.max_evals_each && load_max_evals(P, i) < 17ull) {  // qags.rs:86-88
+                write_result(P.out, i, 0.0, F64_MAX, 0u, ST_INSUFFICIENT_ITERATION);
+            } else {
             const QK q = qk_rule_hoisted<N, InitUnroll<F, N>::value>(g, a, b);
             const uint32_t nevals = (PASS == 0) ? 17u : 42u;
 
             // initial_integral, pass i = PASS (qags.rs:336-372)
             uint32_t status = ST_NONE;
             bool done = true;
-            const double tolerance = P.tol.to_abs(fabs(q.estimate));
+            const double tolerance = load_tol(P, i).to_abs(fabs(q.estimate));
             const double round_off = 100. * F64_EPSILON * q.absvalue;
             if (q.estimate != q.estimate) {
                 status = ST_NAN;
@@ -234,7 +256,7 @@ __global__ void __launch_bounds__(BLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : 3) k
                 status = ST_NONE;
             } else if (q.delta <= round_off && q.delta > tolerance) {
                 status = ST_ROUNDOFF_ERROR;
-            } else if (P.max_evals < (unsigned long long)(42 + PASS * 25)) {
+            } else if (load_max_evals(P, i) < (unsigned long long)(42 + PASS * 25)) {
                 status = ST_INSUFFICIENT_ITERATION;
             } else {
                 done = false;
@@ -248,6 +270,7 @@ __global__ void __launch_bounds__(BLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : 3) k
             if (done || toLoop) {
                 write_result(P.out, i, q.estimate, q.delta, nevals, status);
                 if (toLoop) P.abs0[i] = q.absvalue;
+            }
             }
         }
         if (PASS == 0) list_append(to25, (unsigned int)i, P.list25, &P.ctl->count25);
@@ -278,7 +301,9 @@ __global__ void __launch_bounds__(BLOCK, 3) k_qags_first(const Batch1D P) {
             load_functor(g.f, P, i, NPARAMS);
             const double est0 = P.out.estimate[i], delta0 = P.out.delta[i];
             uint32_t nevals = P.out.nevals[i];
-            const unsigned long long max_iters = (P.max_evals - nevals) / 50;
+            const Tol tol = load_tol(P, i);
+            const unsigned long long max_evals = load_max_evals(P, i);
+            const unsigned long long max_iters = (max_evals - nevals) / 50;
             if (max_iters >= 1) {  // else: zero trips, result0 already is the answer (qags.rs:274-276)
                 const double center = (a + b) * 0.5;
                 const QK q1 = qk_rule<12, RuleUnroll<F, 12>::value>(g, a, center);
@@ -294,7 +319,7 @@ __global__ void __launch_bounds__(BLOCK, 3) k_qags_first(const Batch1D P) {
                     errsum += error12 - delta0;
                     double area = est0;
                     area += area12 - est0;
-                    const double tolerance = P.tol.to_abs(fabs(area));
+                    const double tolerance = tol.to_abs(fabs(area));
                     int ro1 = 0;
                     if (q1.asc != q1.delta && q2.asc != q2.delta) {
                         if (fabs(est0 - area12) <= 1e-5 * fabs(area12) && error12 >= 0.99 * delta0) ro1 = 1;
@@ -330,6 +355,9 @@ __global__ void __launch_bounds__(BLOCK, 3) k_qags_first(const Batch1D P) {
                         rec.ro1 = (unsigned int)ro1;
                         rec.call = P.call_slot;
                         rec.pad_ = 0;
+                        rec.abs_tol = tol.abs_tol;
+                        rec.rel_tol = tol.rel_tol;
+                        rec.max_evals = max_evals;
                     }
                 }
             }
@@ -428,6 +456,15 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
     Lane& s = s_lanes[threadIdx.x];
     s.active = false;
     s.idx = 0;
+    // the lane's own tolerance and budget (batch configuration or per-integral overrides)
+    __shared__ double s_abs_tol[ABLOCK], s_rel_tol[ABLOCK];
+    __shared__ unsigned long long s_max_evals[ABLOCK];
+    double& my_abs_tol = s_abs_tol[threadIdx.x];
+    double& my_rel_tol = s_rel_tol[threadIdx.x];
+    unsigned long long& my_max_evals = s_max_evals[threadIdx.x];
+    my_abs_tol = P.tol.abs_tol;
+    my_rel_tol = P.tol.rel_tol;
+    my_max_evals = P.max_evals;
     // QAGP lanes write the batch outputs directly; QAGS lanes finish straggler records and write
     // to the owning call's outputs or to the host-pipeline patch (s.idx = record slot)
     typename SinkFor<QAGP>::type sink;
@@ -504,8 +541,11 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
                         s.abs0 = r.abs0;
                         s.nevals = r.nevals;  // nevals of result0 + 50
                         const uint32_t nev0 = s.nevals - 50u;
+                        my_abs_tol = r.abs_tol;
+                        my_rel_tol = r.rel_tol;
+                        my_max_evals = r.max_evals;
                         // ws.reserve((max_evals - nevals) / 50 + 1)   qags.rs:98-99
-                        s.max_iters = (P.max_evals - nev0) / 50;
+                        s.max_iters = (my_max_evals - nev0) / 50;
                         s.limit = (int)reserve_cap(P.ws_capacity, s.max_iters + 1);
                         const double e1 = r.e1, d1 = r.d1, e2 = r.e2, d2 = r.d2;
                         const double center = (a + b) * 0.5;
@@ -547,12 +587,18 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
                         s.nint = make_sorted_points(S, a, b, up, nup, s.transform);
                         s.nevals = 0;
                         s.est0 = s.delta0 = s.abs0 = s.asc0 = 0.;
-                        if (P.max_evals < (unsigned long long)s.nint * 25ull) {  // qagp.rs:79-81
+                        {
+                            const Tol t = load_tol(P, s.idx);
+                            my_abs_tol = t.abs_tol;
+                            my_rel_tol = t.rel_tol;
+                            my_max_evals = load_max_evals(P, s.idx);
+                        }
+                        if (my_max_evals < (unsigned long long)s.nint * 25ull) {  // qagp.rs:79-81
                             write_result(P.out, s.idx, 0.0, F64_MAX, 0u, ST_INSUFFICIENT_ITERATION);
                         } else {
                             // ws.reserve(nint + (max_evals - nint*25)/50)   qagp.rs:83-84
                             s.limit = (int)reserve_cap(
-                                P.ws_capacity, s.nint + (P.max_evals - (unsigned long long)s.nint * 25ull) / 50ull);
+                                P.ws_capacity, s.nint + (my_max_evals - (unsigned long long)s.nint * 25ull) / 50ull);
                             s.seeding = true;
                             s.seed_k = 0;
                             s.active = true;
@@ -669,7 +715,10 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
                     for (int k = 0; k < s.size; ++k) S.LV(k) = 0;
                     ws_sort_results(S, s);
 
-                    const double tolerance = P.tol.to_abs(fabs(s.est0));
+                    Tol tol = P.tol;
+                    tol.abs_tol = my_abs_tol;
+                    tol.rel_tol = my_rel_tol;
+                    const double tolerance = tol.to_abs(fabs(s.est0));
                     const double round_off = 100. * F64_EPSILON * s.abs0;
                     if (s.delta0 <= round_off && s.delta0 > tolerance) {
                         s.active = false;
@@ -677,7 +726,7 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
                     } else if ((s.delta0 <= tolerance && s.delta0 != s.asc0) || s.delta0 == 0.0) {
                         s.active = false;
                         write_result(P.out, s.idx, s.est0, s.delta0, s.nevals, ST_NONE);
-                    } else if ((unsigned long long)s.nevals == P.max_evals) {
+                    } else if ((unsigned long long)s.nevals == my_max_evals) {
                         s.active = false;
                         write_result(P.out, s.idx, s.est0, s.delta0, s.nevals,
                                      ST_INSUFFICIENT_ITERATION);
@@ -689,13 +738,16 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
                         s.errsum = deltasum;
                         s.eolr = deltasum;
                         s.ertest = tolerance;
-                        s.max_iters = (unsigned long long)s.nint + (P.max_evals - s.nevals) / 50ull;
+                        s.max_iters = (unsigned long long)s.nint + (my_max_evals - s.nevals) / 50ull;
                         s.iteration = (unsigned long long)s.nint;
                     }
                 }
             } else {
                 const int wi = s.wi;  // the bisected interval (untouched since the plan step)
-                adaptive_step<QAGP>(S, s, P.tol, P.max_evals, sink, ra0, rb1, rb0, S.E(wi), S.D(wi),
+                Tol tol = P.tol;
+                tol.abs_tol = my_abs_tol;
+                tol.rel_tol = my_rel_tol;
+                adaptive_step<QAGP>(S, s, tol, my_max_evals, sink, ra0, rb1, rb0, S.E(wi), S.D(wi),
                                     S.LV(wi), q0, q1);
             }
         }

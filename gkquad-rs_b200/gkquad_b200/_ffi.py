@@ -35,6 +35,11 @@ class gkq_config(C.Structure):
                 ("points", C.POINTER(C.c_double)), ("npoints", C.c_int64)]
 
 
+class gkq_overrides(C.Structure):
+    """Per-integral tolerance values / budgets (NULL = the batch value); include/gkquad_b200.h."""
+    _fields_ = [("abs_tol", C.c_void_p), ("rel_tol", C.c_void_p), ("max_evals", C.c_void_p)]
+
+
 class gkq_stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("batches", C.c_uint64), ("integrals", C.c_uint64),
                 ("scratch_bytes", C.c_uint64), ("last_survivors_qk25", C.c_uint64),
@@ -46,7 +51,7 @@ class gkq_stats(C.Structure):
 SYMBOLS = [
     "gkq_abi_version", "gkq_config_default", "gkq_create", "gkq_destroy", "gkq_last_error",
     "gkq_functor_count", "gkq_functor_info", "gkq_functor_lookup", "gkq_integrate_batch",
-    "gkq_integrate_batch_host", "gkq_integrate2_batch", "gkq_integrate2_batch_host", "gkq_qk_batch",
+    "gkq_integrate_batch_host", "gkq_integrate_batch_ex", "gkq_integrate_batch_host_ex", "gkq_integrate2_batch", "gkq_integrate2_batch_host", "gkq_qk_batch",
     "gkq_functor_eval_batch",
     "gkq_set_deferred_join", "gkq_join", "gkq_sync", "gkq_get_stats", "gkq_reset_stats", "gkq_set_profiling", "gkq_get_profile",
     "gkq_measure_fp64_peak",
@@ -80,6 +85,9 @@ def lib():
               dp, dp, dp, u32p, u32p]
     L.gkq_integrate_batch.argtypes = batch1 + [vp]
     L.gkq_integrate_batch_host.argtypes = batch1
+    batch1x = batch1[:2] + [C.POINTER(gkq_overrides)] + batch1[2:]
+    L.gkq_integrate_batch_ex.argtypes = batch1x + [vp]
+    L.gkq_integrate_batch_host_ex.argtypes = batch1x
     batch2 = [vp, C.POINTER(gkq_config), C.c_int, C.c_int, C.c_int64, dp, dp, C.c_int64, dp, C.c_int64,
               dp, C.c_int64, i64p, dp, dp, dp, u32p, u32p]
     L.gkq_integrate2_batch.argtypes = batch2 + [vp]

@@ -117,7 +117,8 @@ class Engine:
         return self.plan_batch(functor, a, b, params, **kw).run()
 
     def plan_batch(self, functor, a, b, params=None, *, algo=ALGO_AUTO, tol=None, max_evals=2000,
-                   points=None, pts_offsets=None, pts=None, workspace_capacity=0, n=None, out=None):
+                   points=None, pts_offsets=None, pts=None, workspace_capacity=0, n=None, out=None,
+                   abs_tol_each=None, rel_tol_each=None, max_evals_each=None):
         """Validate and marshal one batch call once; BatchPlan.run() then only crosses the C ABI
         (the counterpart of an Integrator that owns its integrand and config and is run many times).
         n independent integrals of `functor` (registry name or id).
@@ -126,7 +127,10 @@ class Engine:
         params: None, a sequence of scalars (shared), or an array [nparams, n] (SoA).
         Arrays may be numpy (host entry: staged through pinned/pageable copies by the library) or
         torch CUDA float64 tensors (device entry: asynchronous on the current stream).
-        out = (estimate, delta, nevals, status) to write into caller-owned arrays."""
+        out = (estimate, delta, nevals, status) to write into caller-owned arrays.
+        abs_tol_each / rel_tol_each / max_evals_each: optional arrays [n] -- every integral's own
+        tolerance values and evaluation budget (an Integrator configured anew for each integral of a
+        sweep); the tolerance kind stays that of `tol`, budgets are clamped to `max_evals`."""
         fid, fname, npar, _ = self.functor(1, functor)
         tol = tol or Tolerance.default()
         on_dev = any(_is_torch(x) for x in (a, b, params) if x is not None)
@@ -181,6 +185,23 @@ class Engine:
             else:
                 po = np.ascontiguousarray(pts_offsets, dtype=np.int64)
                 pv = arr(pts)
+        # per-integral overrides
+        ov = None
+        keep_ov = ()
+        if abs_tol_each is not None or rel_tol_each is not None or max_evals_each is not None:
+            ate, rte = arr(abs_tol_each), arr(rel_tol_each)
+            mee = None
+            if max_evals_each is not None:
+                if on_dev:
+                    mee = (max_evals_each if _is_torch(max_evals_each)
+                           else xp.as_tensor(np.asarray(max_evals_each, dtype=np.int64), device=f"cuda:{self.device}"))
+                    assert mee.dtype == xp.int64 and mee.is_contiguous()
+                else:
+                    mee = np.ascontiguousarray(max_evals_each, dtype=np.uint64)
+            for x in (ate, rte, mee):
+                assert x is None or int(x.shape[0]) == n, "per-integral arrays need n entries"
+            ov = _ffi.gkq_overrides(self._ptr(ate), self._ptr(rte), self._ptr(mee))
+            keep_ov = (ate, rte, mee, ov)
         if on_dev:
             if out is None:
                 dev = f"cuda:{self.device}"
@@ -191,6 +212,12 @@ class Engine:
             else:
                 est, dlt, nev, st = out
             r = BatchResult(est, dlt, nev, st)
+            if ov is not None:
+                args = (self.h, C.byref(cfg), C.byref(ov), fid, n, self._ptr(aa), self._ptr(bb), rs, self._ptr(pp),
+                        ps, self._ptr(po), self._ptr(pv), self._ptr(est), self._ptr(dlt), self._ptr(nev),
+                        self._ptr(st))
+                return BatchPlan(self, self.L.gkq_integrate_batch_ex, args, True, r,
+                                 (aa, bb, pp, po, pv, cfg) + keep_ov)
             args = (self.h, C.byref(cfg), fid, n, self._ptr(aa), self._ptr(bb), rs, self._ptr(pp), ps,
                     self._ptr(po), self._ptr(pv), self._ptr(est), self._ptr(dlt), self._ptr(nev), self._ptr(st))
             return BatchPlan(self, self.L.gkq_integrate_batch, args, True, r, (aa, bb, pp, po, pv, cfg))
@@ -200,6 +227,11 @@ class Engine:
         else:
             est, dlt, nev, st = out
         r = BatchResult(est, dlt, nev, st)
+        if ov is not None:
+            args = (self.h, C.byref(cfg), C.byref(ov), fid, n, self._ptr(aa), self._ptr(bb), rs, self._ptr(pp), ps,
+                    self._ptr(po), self._ptr(pv), self._ptr(est), self._ptr(dlt), self._ptr(nev), self._ptr(st))
+            return BatchPlan(self, self.L.gkq_integrate_batch_host_ex, args, False, r,
+                             (aa, bb, pp, po, pv, cfg) + keep_ov)
         args = (self.h, C.byref(cfg), fid, n, self._ptr(aa), self._ptr(bb), rs, self._ptr(pp), ps,
                 self._ptr(po), self._ptr(pv), self._ptr(est), self._ptr(dlt), self._ptr(nev), self._ptr(st))
         return BatchPlan(self, self.L.gkq_integrate_batch_host, args, False, r, (aa, bb, pp, po, pv, cfg))

@@ -26,6 +26,14 @@ pub struct gkq_tolerance {
     pub rel_tol: c_double,
 }
 
+/// Per-integral tolerance values / budgets (null = the batch value); include/gkquad_b200.h.
+#[repr(C)]
+pub struct gkq_overrides {
+    pub abs_tol: *const c_double,
+    pub rel_tol: *const c_double,
+    pub max_evals: *const u64,
+}
+
 #[repr(C)]
 pub struct gkq_config {
     pub algo: i32,
@@ -87,6 +95,14 @@ extern "C" {
                                      pts_offsets: *const i64, pts_xy: *const c_double,
                                      out_estimate: *mut c_double, out_delta: *mut c_double,
                                      out_nevals: *mut u32, out_status: *mut u32) -> c_int;
+    pub fn gkq_integrate_batch_ex(h: gkq_handle_t, cfg: *const gkq_config, ov: *const gkq_overrides,
+        functor_id: c_int, n: i64, a: *const f64, b: *const f64, range_stride: i64, params: *const f64,
+        param_stride: i64, pts_offsets: *const i64, pts: *const f64, out_estimate: *mut f64,
+        out_delta: *mut f64, out_nevals: *mut u32, out_status: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn gkq_integrate_batch_host_ex(h: gkq_handle_t, cfg: *const gkq_config, ov: *const gkq_overrides,
+        functor_id: c_int, n: i64, a: *const f64, b: *const f64, range_stride: i64, params: *const f64,
+        param_stride: i64, pts_offsets: *const i64, pts: *const f64, out_estimate: *mut f64,
+        out_delta: *mut f64, out_nevals: *mut u32, out_status: *mut u32) -> c_int;
     pub fn gkq_qk_batch(h: gkq_handle_t, rule: c_int, functor_id: c_int, n: i64, a: *const c_double,
                         b: *const c_double, range_stride: i64, params: *const c_double,
                         param_stride: i64, out4: *mut c_double, stream: *mut c_void) -> c_int;

@@ -180,6 +180,30 @@ int gkq_integrate2_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor
                               double* out_estimate, double* out_delta, uint32_t* out_nevals,
                               uint32_t* out_status);
 
+/* ---- per-integral configuration -------------------------------------
+ * replaces: an Integrator whose tolerance / max_evals differ from integral to integral
+ * (single/integrator.rs:69-84 called once per integral in a parameter sweep).  Each array is
+ * optional (NULL = the value of `cfg` for every integral) and has n entries; the tolerance KIND
+ * stays cfg->tol.kind.  max_evals[i] is clamped to cfg->max_evals, which sizes the engine's
+ * interval lists.  NaN tolerances are not checked here (the reference panics,
+ * single/integrator.rs:71).  1-D entries only.
+ * gkq_integrate_batch_ex: device pointers; gkq_integrate_batch_host_ex: host pointers. */
+typedef struct gkq_overrides {
+    const double* abs_tol;
+    const double* rel_tol;
+    const uint64_t* max_evals;
+} gkq_overrides;
+int gkq_integrate_batch_ex(gkq_handle_t h, const gkq_config* cfg, const gkq_overrides* ov,
+                           int functor_id, int64_t n, const double* a, const double* b,
+                           int64_t range_stride, const double* params, int64_t param_stride,
+                           const int64_t* pts_offsets, const double* pts, double* out_estimate,
+                           double* out_delta, uint32_t* out_nevals, uint32_t* out_status, void* stream);
+int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq_overrides* ov,
+                                int functor_id, int64_t n, const double* a, const double* b,
+                                int64_t range_stride, const double* params, int64_t param_stride,
+                                const int64_t* pts_offsets, const double* pts, double* out_estimate,
+                                double* out_delta, uint32_t* out_nevals, uint32_t* out_status);
+
 /* ---- rule level -------------------------------------------------------------------------
  * replaces: single::qk17 / qk25 / qk33 / qk41 / qk49 / qk57 (single/qk/mod.rs:28-73) -> QKResult
  * (:16-25).  `rule` is the number of points: 17, 25, 33, 41, 49 or 57.  Device pointers; out4 is

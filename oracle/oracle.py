@@ -50,6 +50,10 @@ def lib():
         L.gkqo_integrate_batch.argtypes = [
             C.c_int, C.c_int, C.c_int64, dp, dp, C.c_int64, dp, C.c_int64, i64p, dp, C.c_int64,
             C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_uint64, dp, dp, u32p, u32p, C.c_int]
+        L.gkqo_integrate_batch_ex.argtypes = [
+            C.c_int, C.c_int, C.c_int64, dp, dp, C.c_int64, dp, C.c_int64, i64p, dp, C.c_int64,
+            C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_uint64, dp, dp, C.POINTER(C.c_uint64),
+            dp, dp, u32p, u32p, C.c_int]
         L.gkqo_integrate2_batch.argtypes = [
             C.c_int, C.c_int, C.c_int, C.c_int64, dp, dp, C.c_int64, dp, C.c_int64, dp, C.c_int64,
             i64p, dp, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_uint64, dp, dp, u32p, u32p,
@@ -130,9 +134,10 @@ def integrate_one(algo, functor, a, b, params=(), points=(), tol=("abs_or_rel", 
 
 def integrate_batch(algo, functor, a, b, params=None, points=None, pts_offsets=None,
                     tol=("abs_or_rel", 1.49e-8, 1.49e-8), max_evals=2000, ws_capacity=0,
-                    nthreads=0, n=None):
+                    nthreads=0, n=None, abs_tol_each=None, rel_tol_each=None, max_evals_each=None):
     """a, b: scalars (shared range; n required) or arrays[n]. params: array [np, n] (SoA) or [np]
-    (shared). points: shared list, or flat array with pts_offsets[n+1]."""
+    (shared). points: shared list, or flat array with pts_offsets[n+1].  *_each: optional per-integral
+    tolerance values / budgets (the tolerance kind stays that of `tol`; budgets are clamped to max_evals)."""
     fid = functor_id(1, functor)
     if np.isscalar(a):
         assert n is not None
@@ -166,9 +171,13 @@ def integrate_batch(algo, functor, a, b, params=None, points=None, pts_offsets=N
     nev = np.empty(n, dtype=np.uint32)
     st = np.empty(n, dtype=np.uint32)
     k, ta, tr = tol_tuple(tol)
-    rc = lib().gkqo_integrate_batch(
+    ate = None if abs_tol_each is None else np.ascontiguousarray(abs_tol_each, dtype=np.float64)
+    rte = None if rel_tol_each is None else np.ascontiguousarray(rel_tol_each, dtype=np.float64)
+    mee = None if max_evals_each is None else np.ascontiguousarray(max_evals_each, dtype=np.uint64)
+    rc = lib().gkqo_integrate_batch_ex(
         algo, fid, n, _dp(aa), _dp(bb), rs, _dp(pp), ps, po_p, _dp(pts), npts, k, ta, tr,
-        max_evals, ws_capacity, _dp(est), _dp(dlt),
+        max_evals, ws_capacity, None if ate is None else _dp(ate), None if rte is None else _dp(rte),
+        None if mee is None else mee.ctypes.data_as(C.POINTER(C.c_uint64)), _dp(est), _dp(dlt),
         nev.ctypes.data_as(C.POINTER(C.c_uint32)), st.ctypes.data_as(C.POINTER(C.c_uint32)), nthreads)
     assert rc == 0, rc
     return dict(estimate=est, delta=dlt, nevals=nev, status=st)

@@ -65,6 +65,11 @@ struct BatchArgs {
     uint32_t* out_nevals;
     uint32_t* out_status;
     int nthreads;
+    // per-integral tolerance / budget (an Integrator configured anew for every integral of a sweep,
+    // single/integrator.rs:69-84); NULL = the batch value
+    const double* abs_tol_each = nullptr;
+    const double* rel_tol_each = nullptr;
+    const uint64_t* max_evals_each = nullptr;
 };
 
 template <int ID>
@@ -82,6 +87,9 @@ void run_batch(const BatchArgs& A) {
             Config cfg;
             cfg.tol = A.tol;
             cfg.max_evals = A.max_evals;
+            if (A.abs_tol_each) cfg.tol.abs_ = A.abs_tol_each[i];
+            if (A.rel_tol_each) cfg.tol.rel_ = A.rel_tol_each[i];
+            if (A.max_evals_each) cfg.max_evals = A.max_evals_each[i] < A.max_evals ? A.max_evals_each[i] : A.max_evals;
             if (A.pts_offsets) {
                 cfg.points = A.pts + A.pts_offsets[i];
                 cfg.npoints = (size_t)(A.pts_offsets[i + 1] - A.pts_offsets[i]);
@@ -304,6 +312,23 @@ int gkqo_integrate_batch(int algo, int functor_id, int64_t n, const double* a, c
                 params,      param_stride, pts_offsets, pts,      npts,
                 Tolerance{tol_kind, tol_abs, tol_rel}, max_evals, ws_capacity,
                 out_estimate, out_delta,  out_nevals, out_status, nthreads};
+    return Dispatch1<0>::go(functor_id, A);
+}
+
+int gkqo_integrate_batch_ex(int algo, int functor_id, int64_t n, const double* a, const double* b,
+                            int64_t range_stride, const double* params, int64_t param_stride,
+                            const int64_t* pts_offsets, const double* pts, int64_t npts, int tol_kind,
+                            double tol_abs, double tol_rel, uint64_t max_evals, uint64_t ws_capacity,
+                            const double* abs_tol_each, const double* rel_tol_each,
+                            const uint64_t* max_evals_each, double* out_estimate, double* out_delta,
+                            uint32_t* out_nevals, uint32_t* out_status, int nthreads) {
+    BatchArgs A{algo,        n,          a,         b,          range_stride,
+                params,      param_stride, pts_offsets, pts,      npts,
+                Tolerance{tol_kind, tol_abs, tol_rel}, max_evals, ws_capacity,
+                out_estimate, out_delta,  out_nevals, out_status, nthreads};
+    A.abs_tol_each = abs_tol_each;
+    A.rel_tol_each = rel_tol_each;
+    A.max_evals_each = max_evals_each;
     return Dispatch1<0>::go(functor_id, A);
 }
 

@@ -389,6 +389,60 @@ def test_double_budget_exhaustion(eng, mode, monkeypatch):
                 compare(g, ref, _tol(tol), exact=f != "g2", label=f"{f} max_evals={me}")
 
 
+def test_per_integral_tolerance_and_budget(eng):
+    """every integral with its own tolerance values and evaluation budget (an Integrator
+    re-configured per integral, single/integrator.rs:69-84) -- device entry, host entry, QAGS and QAGP,
+    bit-exact against the oracle on IEEE-exact integrands."""
+    import torch
+    from gkquad_b200 import Tolerance
+    from gpu_common import compare
+    from oracle import oracle as O
+    rng = np.random.default_rng(7)
+    n = 20000
+    p = rng.uniform(1.0, 3000.0, (1, n))
+    rel = 10.0 ** rng.uniform(-13, -3, n)
+    ab = 10.0 ** rng.uniform(-14, -6, n)
+    me = rng.choice([0, 10, 17, 41, 42, 66, 67, 92, 117, 500, 2000, 5000], n).astype(np.uint64)
+    for kind, tol in (("rel", Tolerance.Relative(1e-9)), ("abs_or_rel", Tolerance.AbsOrRel(1e-12, 1e-9))):
+        otol = ("rel", 1e-9) if kind == "rel" else ("abs_or_rel", 1e-12, 1e-9)
+        ref = O.integrate_batch(ALGO["QAGS"], "lorentz_p", -1.0, 1.0, p, tol=otol, max_evals=2000, n=n,
+                                abs_tol_each=ab, rel_tol_each=rel, max_evals_each=me)
+        assert len(np.unique(ref["status"])) >= 2 and len(np.unique(ref["nevals"])) > 6
+        # device entry
+        g = eng.integrate_batch("lorentz_p", -1.0, 1.0, torch.as_tensor(p, device="cuda:0"), algo=ALGO["QAGS"],
+                                tol=tol, max_evals=2000, n=n, abs_tol_each=ab, rel_tol_each=rel,
+                                max_evals_each=me.astype(np.int64))
+        compare(g, ref, tol, exact=True, label=f"device {kind}")
+        # host entry
+        g = eng.integrate_batch("lorentz_p", -1.0, 1.0, p, algo=ALGO["QAGS"], tol=tol, max_evals=2000, n=n,
+                                abs_tol_each=ab, rel_tol_each=rel, max_evals_each=me)
+        compare(g, ref, tol, exact=True, label=f"host {kind}")
+    # QAGP with a shared break point
+    pq = rng.uniform(0.5, 2.0, (1, n))
+    ref = O.integrate_batch(ALGO["QAGP"], "recip_p", -1.0, 1.0, pq, points=[0.0], tol=("abs", 1e-8), max_evals=2000,
+                            n=n, abs_tol_each=ab, max_evals_each=me)
+    g = eng.integrate_batch("recip_p", -1.0, 1.0, torch.as_tensor(pq, device="cuda:0"), algo=ALGO["QAGP"],
+                            tol=Tolerance.Absolute(1e-8), max_evals=2000, points=[0.0], n=n, abs_tol_each=ab,
+                            max_evals_each=me.astype(np.int64))
+    compare(g, ref, Tolerance.Absolute(1e-8), exact=True, label="QAGP")
+    # the deferred-join pipeline keeps each record's own configuration
+    eng.set_deferred_join(True)
+    try:
+        outs = []
+        for k in range(3):
+            outs.append(eng.integrate_batch("lorentz_p", -1.0, 1.0, torch.as_tensor(p, device="cuda:0"),
+                                            algo=ALGO["QAGS"], tol=Tolerance.Relative(1e-9), max_evals=2000, n=n,
+                                            rel_tol_each=rel * (10.0 ** -k), max_evals_each=me.astype(np.int64)))
+        eng.join()
+        torch.cuda.synchronize()
+        for k, g in enumerate(outs):
+            ref = O.integrate_batch(ALGO["QAGS"], "lorentz_p", -1.0, 1.0, p, tol=("rel", 1e-9), max_evals=2000, n=n,
+                                    rel_tol_each=rel * (10.0 ** -k), max_evals_each=me)
+            compare(g, ref, Tolerance.Relative(1e-9), exact=True, label=f"deferred {k}")
+    finally:
+        eng.set_deferred_join(False)
+
+
 def test_api_mirror_on_gpu(eng):
     """The host-side mirror of gkquad's API (single::integral, Integrator builder, integral2)."""
     from gkquad_b200 import Tolerance, double, single
