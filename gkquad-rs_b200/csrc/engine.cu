@@ -1310,6 +1310,7 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
     P.yparam_stride = yparam_stride;
     P.yrange_id = yrange_id;
     P.nyparams = YR_TABLE[yrange_id].nparams;
+    P.swap_xy = (cfg->flags & GKQ_FLAG_SWAP_XY) != 0;
     P.tol.kind = cfg->tol.kind;
     P.tol.abs_tol = cfg->tol.abs_tol;
     P.tol.rel_tol = cfg->tol.rel_tol;

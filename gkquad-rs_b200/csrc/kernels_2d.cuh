@@ -366,6 +366,7 @@ struct Batch2D {
     Control* ctl;
     SlabGeom slab;
     int cap_outer, cap_inner;
+    bool swap_xy;  // GKQ_FLAG_SWAP_XY
     int pool_r;  // k_nested_pool: outer integrals per warp (<= POOL_R)
 };
 
@@ -374,9 +375,12 @@ template <class F2T>
 struct InnerF {
     F2T f;
     double x;
+    bool swap;  // GKQ_FLAG_SWAP_XY: the integrand takes (inner, outer) -- DynamicX, qags.rs:37
     static constexpr bool PAIRWISE = false;
-    GKQ_DEV double operator()(double y) const { return f(x, y); }
-    template <class M> GKQ_DEV double eval(double y, M& m) const { return f.eval(x, y, m); }
+    GKQ_DEV double operator()(double y) const { return swap ? f(y, x) : f(x, y); }
+    template <class M> GKQ_DEV double eval(double y, M& m) const {
+        return swap ? f.eval(y, x, m) : f.eval(x, y, m);
+    }
 };
 
 // The outer integrand of double/algorithm/qags.rs:66-87 / qagp.rs:108-131 with the infinite
@@ -394,6 +398,7 @@ struct OuterIntegrand {
     const double* pts_xy;
     int npts;
     bool transform;  // outer x-range infinite
+    bool swap_xy;
 
     // One inner integral over y(x) with an explicit budget and workspace capacity; touches no
     // state of the outer integrand.
@@ -409,6 +414,7 @@ struct OuterIntegrand {
         Wrapped<InnerF<F2T>> g;
         g.f.f = f;
         g.f.x = x;
+        g.f.swap = swap_xy;
         g.transform = ytr;
         if (QAGP) {
             const double* p = pts_xy;
@@ -494,6 +500,7 @@ __global__ void __launch_bounds__(BLOCK) k_nested(const Batch2D P) {
         G.Sin = Sin;
         G.pts_xy = my_pts;
         G.npts = my_npts;
+        G.swap_xy = P.swap_xy;
 
         double xa = P.x0[(long long)i * P.range_stride];
         double xb = P.x1[(long long)i * P.range_stride];

@@ -390,6 +390,7 @@ __global__ void __launch_bounds__(PB, 4) k_nested_pool(const Batch2D P) {
 #pragma unroll
             for (int k = 0; k < MAX_PARAMS; ++k) g.f.f.p[k] = 0.;
             g.f.x = 0.;
+            g.f.swap = P.swap_xy;
             g.transform = false;
             double ya = 0., yb = 0.;  // the lane's whole inner range (initial passes of QAGS)
             unsigned long long budget0 = 0, cap0 = 0;
@@ -469,6 +470,7 @@ __global__ void __launch_bounds__(PB, 4) k_nested_pool(const Batch2D P) {
                         for (int k = 0; k < MAX_PARAMS; ++k)
                             go.f.f.p[k] = (k < NPARAMS) ? __shfl_sync(FULL, g.f.f.p[k], own) : 0.0;
                         go.f.x = __shfl_sync(FULL, g.f.x, own);
+                        go.f.swap = P.swap_xy;
                         go.transform = __shfl_sync(FULL, (int)g.transform, own) != 0;
                         const bool oh0 = __shfl_sync(FULL, (int)p.has0, own) != 0;
                         const bool oh1 = __shfl_sync(FULL, (int)p.has1, own) != 0;
@@ -549,6 +551,7 @@ __global__ void __launch_bounds__(PB, 4) k_nested_pool(const Batch2D P) {
                 G.Sin = Sin;
                 G.pts_xy = cx.pts_xy;
                 G.npts = cx.npts;
+                G.swap_xy = P.swap_xy;
                 G.transform = false;  // applied below, like the speculative path
 #pragma unroll 1
                 for (int k = 0; k < K; ++k) {

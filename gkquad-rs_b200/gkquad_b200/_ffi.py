@@ -30,7 +30,7 @@ class gkq_tolerance(C.Structure):
 
 
 class gkq_config(C.Structure):
-    _fields_ = [("algo", C.c_int32), ("_pad", C.c_int32), ("tol", gkq_tolerance),
+    _fields_ = [("algo", C.c_int32), ("flags", C.c_int32), ("tol", gkq_tolerance),
                 ("max_evals", C.c_uint64), ("workspace_capacity", C.c_uint64),
                 ("points", C.POINTER(C.c_double)), ("npoints", C.c_int64)]
 

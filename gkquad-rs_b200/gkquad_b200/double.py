@@ -40,9 +40,21 @@ class DynamicY:
     new = classmethod(lambda cls, x1, x2, yrange, yparams=None: cls(x1, x2, yrange, yparams))
 
 
+class DynamicX:
+    """double/range.rs:38-75: y in [y1, y2], x in xrange(y).  The algorithms swap the arguments of
+    the integrand, integrate over y outside and x inside, and swap the coordinates of the singular
+    points (double/algorithm/qags.rs:29-44, qagp.rs:34-53)."""
+
+    def __init__(self, xrange: str, y1, y2, xparams=None):
+        self.yrange = Range(y1, y2)
+        self.xrange, self.xparams = xrange, xparams
+
+    new = classmethod(lambda cls, xrange, y1, y2, xparams=None: cls(xrange, y1, y2, xparams))
+
+
 def _into_range2(r):
     """IntoRange2 (double/range.rs:125-173)."""
-    if isinstance(r, DynamicY):
+    if isinstance(r, (DynamicY, DynamicX)):
         return r
     if isinstance(r, Rectangle):
         return DynamicY(r.xrange.begin, r.xrange.end, "const", [r.yrange.begin, r.yrange.end])  # qags.rs:18-27
@@ -78,9 +90,15 @@ class Algorithm2:
         p = f.params
         if p is not None and hasattr(p, "ndim") and p.ndim == 2:
             n = int(p.shape[1])
-        res = eng.integrate2_batch(f.functor, r.yrange, r.xrange.begin, r.xrange.end, fparams=p,
-                                   yparams=r.yparams, algo=self.ALGO, tol=config.tolerance,
-                                   max_evals=config.max_evals, points=config.points, n=n)
+        if isinstance(r, DynamicX):
+            res = eng.integrate2_batch(f.functor, r.xrange, r.yrange.begin, r.yrange.end, fparams=p,
+                                       yparams=r.xparams, algo=self.ALGO, tol=config.tolerance,
+                                       max_evals=config.max_evals, n=n, swap_xy=True,
+                                       points=[(y, x) for (x, y) in config.points])  # qagp.rs:49
+        else:
+            res = eng.integrate2_batch(f.functor, r.yrange, r.xrange.begin, r.xrange.end, fparams=p,
+                                       yparams=r.yparams, algo=self.ALGO, tol=config.tolerance,
+                                       max_evals=config.max_evals, points=config.points, n=n)
         return res[0] if (len(res) == 1 and n is None) else res
 
     def __eq__(self, o):

@@ -273,10 +273,14 @@ class Engine:
 
     # ---- 2-D ------------------------------------------------------------------------------
     def integrate2_batch(self, functor2, yrange, x0, x1, fparams=None, yparams=None, *, algo=ALGO_AUTO,
-                         tol=None, max_evals=100000, points=None, pts_offsets=None, pts_xy=None, n=None):
+                         tol=None, max_evals=100000, points=None, pts_offsets=None, pts_xy=None, n=None,
+                         swap_xy=False):
         """n nested double integrals; yrange = registry name of the y(x) functor ('const',
         'zero_to_x', 'circle'); points = list of (x, y) pairs shared by the batch, or per-integral
-        CSR: pts_offsets[n+1] (counting pairs) + pts_xy[m, 2]."""
+        CSR: pts_offsets[n+1] (counting pairs) + pts_xy[m, 2].
+        swap_xy (GKQ_FLAG_SWAP_XY, the reference's DynamicX): the integrand is evaluated as
+        f(inner, outer); x0/x1 and the range functor then describe the outer / inner variable and the
+        points are (outer, inner) pairs."""
         fid, fname, npar, _ = self.functor(2, functor2)
         yid, yname, nq, _ = self.functor(0, yrange)
         tol = tol or Tolerance.default()
@@ -321,6 +325,7 @@ class Engine:
         if n is None:
             n = 1
         cfg = self._config(algo, tol, max_evals, points, 0, 2)
+        cfg.flags = 1 if swap_xy else 0
         po = pv = None
         if pts_offsets is not None:
             if on_dev:

@@ -34,10 +34,12 @@ pub struct gkq_overrides {
     pub max_evals: *const u64,
 }
 
+pub const GKQ_FLAG_SWAP_XY: i32 = 1;
+
 #[repr(C)]
 pub struct gkq_config {
     pub algo: i32,
-    pub _pad: i32,
+    pub flags: i32,
     pub tol: gkq_tolerance,
     pub max_evals: u64,
     pub workspace_capacity: u64,

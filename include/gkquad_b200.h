@@ -84,13 +84,21 @@ typedef enum gkq_error {
  * 0 = a fresh WorkSpace::new() per integral, as single::integral does (integral.rs:17-19). */
 typedef struct gkq_config {
     int32_t algo; /* gkq_algo */
-    int32_t _pad;
+    int32_t flags; /* GKQ_FLAG_* (0 = none) */
     gkq_tolerance tol;
     uint64_t max_evals;
     uint64_t workspace_capacity;
     const double* points;
     int64_t npoints;
 } gkq_config;
+
+/* 2-D entries: integrate x inside and y outside, i.e. the reference's DynamicX range
+ * (double/range.rs:38-75): the algorithms swap the arguments of the integrand, hand the x-range
+ * functor the outer variable and swap the coordinates of the singular points
+ * (double/algorithm/qags.rs:29-44, qagp.rs:34-53).  With this flag the engine evaluates
+ * f(inner, outer); x0/x1 are the OUTER (y) range, the range functor yields the inner (x) range and
+ * points are given as (outer, inner) pairs -- the host mirrors do the swapping. */
+#define GKQ_FLAG_SWAP_XY 1
 
 /* Fills *cfg with the reference's defaults: dim 1 -> IntegrationConfig::default(),
  * dim 2 -> IntegrationConfig2::default(). */

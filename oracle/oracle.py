@@ -57,7 +57,7 @@ def lib():
         L.gkqo_integrate2_batch.argtypes = [
             C.c_int, C.c_int, C.c_int, C.c_int64, dp, dp, C.c_int64, dp, C.c_int64, dp, C.c_int64,
             i64p, dp, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_uint64, dp, dp, u32p, u32p,
-            C.c_int]
+            C.c_int, C.c_int]
         L.gkqo_qk.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, dp, dp]
         L.gkqo_integrate_one.argtypes = [
             C.c_int, C.c_int, C.c_double, C.c_double, dp, dp, C.c_int64, C.c_int, C.c_double,
@@ -185,8 +185,10 @@ def integrate_batch(algo, functor, a, b, params=None, points=None, pts_offsets=N
 
 def integrate2_batch(algo, functor2, yrange, x0, x1, fparams=None, yparams=None, points=None,
                      pts_offsets=None, tol=("abs_or_rel", 1.49e-8, 1.49e-8), max_evals=100000,
-                     nthreads=0, n=None):
-    """points: list of (x, y) pairs shared by the batch, or flat [m,2] array with pts_offsets."""
+                     nthreads=0, n=None, swap_xy=False):
+    """points: list of (x, y) pairs shared by the batch, or flat [m,2] array with pts_offsets.
+    swap_xy: the DynamicX form -- the algorithms see g(x, y) = f(y, x); ranges and points are given
+    in (outer, inner) order, as the reference passes them on after its own swap."""
     fid = functor_id(2, functor2)
     yid = functor_id(0, yrange)
     if np.isscalar(x0):
@@ -226,7 +228,8 @@ def integrate2_batch(algo, functor2, yrange, x0, x1, fparams=None, yparams=None,
     rc = lib().gkqo_integrate2_batch(
         algo, fid, yid, n, _dp(aa), _dp(bb), rs, _dp(fp), fs, _dp(yp), ys, po_p, _dp(pts), npts,
         k, ta, tr, max_evals, _dp(est), _dp(dlt),
-        nev.ctypes.data_as(C.POINTER(C.c_uint32)), st.ctypes.data_as(C.POINTER(C.c_uint32)), nthreads)
+        nev.ctypes.data_as(C.POINTER(C.c_uint32)), st.ctypes.data_as(C.POINTER(C.c_uint32)), nthreads,
+        1 if swap_xy else 0)
     assert rc == 0, rc
     return dict(estimate=est, delta=dlt, nevals=nev, status=st)
 

@@ -159,6 +159,14 @@ struct Batch2Args {
     uint32_t* out_nevals;
     uint32_t* out_status;
     int nthreads;
+    int swap_xy = 0;  // DynamicX: the algorithms see g(x, y) = f(y, x) (double/algorithm/qags.rs:36-37)
+};
+
+// double/algorithm/qags.rs:36-37, qagp.rs:41-42: `let mut g = |x, y| f.apply((y, x));`
+template <class F>
+struct SwappedF2 {
+    F& f;
+    double operator()(double x, double y) { return f(y, x); }
 };
 
 template <int ID>
@@ -186,7 +194,13 @@ void run_batch2(const Batch2Args& A) {
             cfg.points_xy = A.pts_xy;
             cfg.npoints = (size_t)A.npts;
         }
-        Result res = integrate2(A.algo, f, xr, yr, cfg);
+        Result res;
+        if (A.swap_xy) {
+            SwappedF2<F2<ID>> g{f};
+            res = integrate2(A.algo, g, xr, yr, cfg);
+        } else {
+            res = integrate2(A.algo, f, xr, yr, cfg);
+        }
         A.out_estimate[i] = res.estimate;
         A.out_delta[i] = res.delta;
         A.out_nevals[i] = (uint32_t)res.nevals;
@@ -338,12 +352,13 @@ int gkqo_integrate2_batch(int algo, int functor2_id, int yrange_id, int64_t n, c
                           const int64_t* pts_offsets, const double* pts_xy, int64_t npts,
                           int tol_kind, double tol_abs, double tol_rel, uint64_t max_evals,
                           double* out_estimate, double* out_delta, uint32_t* out_nevals,
-                          uint32_t* out_status, int nthreads) {
+                          uint32_t* out_status, int nthreads, int swap_xy) {
     if (yrange_id < 0 || yrange_id >= YR_COUNT) return -1;
     Batch2Args A{algo,       yrange_id,     n,          x0,         x1,         range_stride,
                  fparams,    fparam_stride, yparams,    yparam_stride, pts_offsets, pts_xy,
                  npts,       Tolerance{tol_kind, tol_abs, tol_rel}, max_evals,
                  out_estimate, out_delta,   out_nevals, out_status, nthreads};
+    A.swap_xy = swap_xy;
     return Dispatch2<0>::go(functor2_id, A);
 }
 

@@ -443,6 +443,40 @@ def test_per_integral_tolerance_and_budget(eng):
         eng.set_deferred_join(False)
 
 
+@pytest.mark.parametrize("mode", ["1", "2"], ids=["thread_per_outer", "pool"])
+def test_double_dynamic_x(eng, mode, monkeypatch):
+    """DynamicX (double/range.rs:38-75; algorithms: qags.rs:29-44, qagp.rs:34-53): x inside, y outside,
+    integrand arguments and point coordinates swapped.  Bit-exact against the oracle, and equal to the
+    DynamicY result of the transposed problem where the integrand is symmetric."""
+    from gkquad_b200 import Tolerance, double
+    from gpu_common import compare
+    from oracle import oracle as O
+    monkeypatch.setenv("GKQ_NESTED_MODE", mode)
+    cases = [("gp2", "circle", -1.0, 1.0, [1.0], ("abs", 1e-5), ALGO["QAGP"], [(0.0, 0.0)]),     # x / (x^2 + y^2)
+             ("g2", "zero_to_x", 0.1, 1.0, [], ("rel", 1e-8), ALGO["QAGS"], []),                  # exp(y / x)
+             ("g4", "const", 0.0, 2.0, [0.0, 3.0], ("abs", 1e-9), ALGO["QAGS"], []),
+             ("gp1", "const", -1.0, 2.0, [-1.0, 1.0], ("rel", 1e-4), ALGO["QAGP"], [(0.5, 0.0), (0.0, 0.0)])]
+    for f, xr, y1, y2, xq, tol, algo, pts in cases:
+        pts_sw = [(y, x) for (x, y) in pts]
+        ref = O.integrate2_batch(algo, f, xr, y1, y2, yparams=xq, points=pts_sw, tol=tol, max_evals=100000, n=1,
+                                 swap_xy=True)
+        g = eng.integrate2_batch(f, xr, y1, y2, yparams=xq, algo=algo, tol=_tol(tol), max_evals=100000,
+                                 points=pts_sw, n=1, swap_xy=True)
+        compare(g, ref, _tol(tol), exact=f != "g2", label=f"DynamicX {f}")
+        plain = O.integrate2_batch(algo, f, xr, y1, y2, yparams=xq, points=pts_sw, tol=tol, max_evals=100000, n=1)
+        if f in ("gp2", "g2"):  # not symmetric in (x, y): the swap must change the answer
+            assert plain["estimate"][0] != ref["estimate"][0]
+        else:                   # g4, gp1 are symmetric in (x, y) up to the rounding of 1 + x + y
+            assert abs(plain["estimate"][0] - ref["estimate"][0]) <= 1e-13 * abs(ref["estimate"][0])
+            assert plain["nevals"][0] == ref["nevals"][0]
+    # through the mirror of the reference API
+    it = double.Integrator2.new(double.DeviceIntegrand2("gp1")).tolerance(Tolerance.Relative(1e-4)).points([(0.0, 0.5)])
+    r = it.run(double.DynamicX.new("const", -1.0, 2.0, [-1.0, 1.0]))
+    ref = O.integrate2_batch(ALGO["QAGP"], "gp1", "const", -1.0, 2.0, yparams=[-1.0, 1.0], points=[(0.5, 0.0)],
+                             tol=("rel", 1e-4), max_evals=100000, n=1, swap_xy=True)
+    assert r.value.estimate == ref["estimate"][0] and r.value.nevals == ref["nevals"][0]
+
+
 def test_api_mirror_on_gpu(eng):
     """The host-side mirror of gkquad's API (single::integral, Integrator builder, integral2)."""
     from gkquad_b200 import Tolerance, double, single
