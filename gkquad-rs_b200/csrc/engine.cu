@@ -823,6 +823,23 @@ static int run_qagp(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, int n
     return launch_check(h, "k_adaptive<QAGP>");
 }
 
+// QAG: one thread per integral over a persistent grid (deprecated algorithm: available, not tuned).
+static int run_qag(gkq_handle_t h, const Launch1D& L, Batch1D P, cudaStream_t st) {
+    int rc;
+    const unsigned long long need = P.max_evals / 50ull + 2ull;
+    if (need > (1ull << 26)) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
+    const int cap = (int)need;
+    const long long nblocks = (P.n + ABLOCK - 1) / ABLOCK;
+    int grid = persistent_grid(h, 4, cap, 2, ABLOCK);
+    if (grid < 1) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
+    if ((long long)grid > nblocks) grid = (int)nblocks;
+    if ((rc = ensure_slab(h, (unsigned long long)grid * ABLOCK, cap, 2, P.slab))) return rc;
+    prof_begin(h, "k_qag", st);
+    L.qag(P, grid, st);
+    prof_end(h, st);
+    return launch_check(h, "k_qag");
+}
+
 // The batch call proper, on bulk scratch context h->cur.  patch / idx_offset: host pipeline.
 static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
                                const double* a, const double* b, int64_t range_stride,
@@ -835,7 +852,7 @@ static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functo
     if (!cfg) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "cfg is NULL");
     if (functor_id < 0 || functor_id >= F1_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown functor id");
     if (n < 0 || n > 0xffffffffll) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "n out of range");
-    if (cfg->algo < 0 || cfg->algo > 2) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown algorithm");
+    if (cfg->algo < 0 || cfg->algo > 3) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown algorithm");
     if (range_stride != 0 && range_stride != 1) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "range_stride must be 0 or 1");
     if (param_stride != 0 && param_stride < n) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "param_stride must be 0 or >= n");
     if (cfg->max_evals > 0x7fffffffull) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "max_evals must fit in 31 bits");
@@ -892,7 +909,9 @@ static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functo
     h->stats.integrals += (uint64_t)n;
 
     bool did_qags = false;
-    if (!pts_offsets) {
+    if (cfg->algo == GKQ_ALGO_QAG) {
+        rc = run_qag(h, L, P, st);  // never looks at points (qag.rs:39-60)
+    } else if (!pts_offsets) {
         const bool use_qags = cfg->algo == GKQ_ALGO_QAGS || (cfg->algo == GKQ_ALGO_AUTO && cfg->npoints == 0);
         if (use_qags) {
             rc = run_qags_bulk(h, L, functor_id, P, st, patch);

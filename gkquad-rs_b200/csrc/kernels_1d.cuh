@@ -754,6 +754,119 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
     }
 }
 
+// ---- QAG (deprecated in the reference, still public): single/algorithm/qag.rs:65-248 -------------
+// QAGS' skeleton without the epsilon table.  One thread walks one integral sequentially out of its
+// slab (qag.rs has no caller in the adaptive drivers; this keeps the public algorithm available,
+// not fast).  Differences from QAGS that matter for parity: the initial pass takes 50 eps (not 100)
+// as round-off floor (:217), the loop counts roundoff_type2 for every non-type-1 step (:139-141),
+// gives up only while deltasum > tolerance (:147-162), and does report nothing when the budget
+// runs out (falls through to `finish`, :176).
+template <class F, int NPARAMS>
+__global__ void __launch_bounds__(ABLOCK) k_qag(const Batch1D P) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * ABLOCK + threadIdx.x;
+    Slab S;
+    S.d = P.slab.dbase + t;
+    S.w = P.slab.wbase + t;
+    S.stride = P.slab.stride;
+    S.cap = P.slab.cap;
+    const long long step = (long long)gridDim.x * ABLOCK;
+    for (long long i = (long long)t; i < P.n; i += step) {
+        Wrapped<F> g;
+        double a, b;
+        load_range(P, i, a, b, g.transform);
+        load_functor(g.f, P, i, NPARAMS);
+        const Tol tol = load_tol(P, i);
+        const unsigned long long max_evals = load_max_evals(P, i);
+        if (max_evals < 17ull) {  // qag.rs:76-78
+            write_result(P.out, i, 0.0, F64_MAX, 0u, ST_INSUFFICIENT_ITERATION);
+            continue;
+        }
+        // initial_integral (qag.rs:185-234)
+        QK q;
+        uint32_t nevals = 0, status = ST_NONE;
+        bool finished = false;
+#pragma unroll 1
+        for (int pass = 0; pass < 2 && !finished; ++pass) {
+            if (pass == 0) {
+                nevals += 17;
+                q = qk_rule<8, 1>(g, a, b);
+            } else {
+                nevals += 25;
+                q = qk_rule<12, 1>(g, a, b);
+            }
+            const double tolerance = tol.to_abs(fabs(q.estimate));
+            const double round_off = 50. * F64_EPSILON * q.absvalue;
+            if (q.estimate != q.estimate) {
+                status = ST_NAN;
+                finished = true;
+            } else if ((q.delta <= tolerance && q.delta != q.asc) || q.delta == 0.0) {
+                finished = true;
+            } else if (q.delta <= round_off && q.delta > tolerance) {
+                status = ST_ROUNDOFF_ERROR;
+                finished = true;
+            } else if (max_evals < (unsigned long long)(42 + pass * 25)) {
+                status = ST_INSUFFICIENT_ITERATION;
+                finished = true;
+            } else if (pass == 0 && q.delta > tolerance * 1024.) {
+                break;
+            }
+        }
+        if (finished) {
+            write_result(P.out, i, q.estimate, q.delta, nevals, status);
+            continue;
+        }
+        double area = q.estimate, deltasum = q.delta;
+        const unsigned long long max_iters = (max_evals - nevals) / 50ull;
+        Lane s;
+        lane_reset_common(s);
+        s.limit = (int)reserve_cap(P.ws_capacity, max_iters + 1ull);  // ws.clear(); ws.reserve(..)  :97-98
+        ws_push(S, s, a, b, q.estimate, q.delta, 0);
+        int ro1 = 0, ro2 = 0;
+        uint32_t error = ST_NONE;
+        bool returned = false;
+#pragma unroll 1
+        for (unsigned long long it = 1; it <= max_iters; ++it) {
+            const int wi = s.wi;
+            const double ia = S.A(wi), ib = S.B(wi), ie = S.E(wi), id = S.D(wi);
+            const int lv = S.LV(wi) + 1;
+            const double center = (ia + ib) * 0.5;
+            const QK q1 = qk_rule<12, 1>(g, ia, center);
+            const QK q2 = qk_rule<12, 1>(g, center, ib);
+            nevals += 50;
+            if (q1.estimate != q1.estimate || q2.estimate != q2.estimate) {  // :122-125
+                error = ST_NAN;
+                break;
+            }
+            const double area12 = q1.estimate + q2.estimate;
+            const double delta12 = q1.delta + q2.delta;
+            deltasum += delta12 - id;
+            area += area12 - ie;
+            if (q1.asc != q1.delta && q2.asc != q2.delta) {  // :135-142
+                if (fabs(ie - area12) <= 1e-5 * fabs(area12) && delta12 >= 0.99 * id)
+                    ro1 += 1;
+                else
+                    ro2 += 1;
+            }
+            const double tolerance = tol.to_abs(fabs(area));
+            if (deltasum > tolerance) {  // :147-162
+                if (ro1 >= 6 || ro2 >= 20)
+                    error = ST_ROUNDOFF_ERROR;
+                else if (subrange_too_small(ia, center, ib))
+                    error = ST_SUBRANGE_TOO_SMALL;
+                if (error != ST_NONE) {
+                    write_result(P.out, i, ws_sum_results(S, s) - ie + q1.estimate + q2.estimate, deltasum, nevals,
+                                 error);
+                    returned = true;
+                    break;
+                }
+            }
+            ws_update(S, s, ia, center, q1.estimate, q1.delta, center, ib, q2.estimate, q2.delta, lv);
+            if (deltasum <= tolerance) break;  // :170-172
+        }
+        if (!returned) write_result(P.out, i, ws_sum_results(S, s), deltasum, nevals, error);  // :176
+    }
+}
+
 // ---- rule-level batch (single/qk/mod.rs:28-41) --------------------------------------------------
 template <class F, int N, int NPARAMS>
 __global__ void __launch_bounds__(BLOCK) k_qk_batch(const Batch1D P, double* out4) {
@@ -789,6 +902,7 @@ struct Launch1D {
     void (*qags_first)(const Batch1D&, int grid, cudaStream_t);
     void (*qags_loop)(const Batch1D&, int grid, cudaStream_t);
     void (*qagp)(const Batch1D&, int grid, cudaStream_t);
+    void (*qag)(const Batch1D&, int grid, cudaStream_t);
     void (*qk[6])(const Batch1D&, double* out4, int grid, cudaStream_t);  // 17, 25, 33, 41, 49, 57 points
     void (*eval)(const Batch1D&, const double* x, double* y, int grid, cudaStream_t);
     int (*occupancy_loop)();   // resident blocks per SM of the persistent kernels
@@ -837,6 +951,9 @@ GKQ_F1_LIST(GKQ_DECL_F1)
         };                                                                                           \
         L.qk[5] = [](const Batch1D& P, double* o, int grid, cudaStream_t st) {                       \
             k_qk_batch<F1<ID>, 28, NP><<<grid, BLOCK, 0, st>>>(P, o);                                \
+        };                                                                                           \
+        L.qag = [](const Batch1D& P, int grid, cudaStream_t st) {                                    \
+            k_qag<F1<ID>, NP><<<grid, ABLOCK, 0, st>>>(P);                                           \
         };                                                                                           \
         L.eval = [](const Batch1D& P, const double* x, double* y, int grid, cudaStream_t st) {       \
             k_eval<F1<ID>, NP><<<grid, BLOCK, 0, st>>>(P, x, y);                                     \

@@ -10,5 +10,5 @@ include/gkquad_b200.h); there is no CPU fallback.
 from . import double, single  # noqa: F401
 from .common import (BatchResult, IntegrationResult, RuntimeError, RuntimeError_, Solution,  # noqa: F401
                      Tolerance)
-from .engine import ALGO_AUTO, ALGO_QAGP, ALGO_QAGS, BatchPlan, Engine, default_engine  # noqa: F401
+from .engine import ALGO_AUTO, ALGO_QAG, ALGO_QAGP, ALGO_QAGS, BatchPlan, Engine, default_engine  # noqa: F401
 from ._ffi import GkqError, functor_table  # noqa: F401

@@ -14,7 +14,7 @@ import numpy as np
 from . import _ffi
 from .common import BatchResult, Tolerance
 
-ALGO_AUTO, ALGO_QAGS, ALGO_QAGP = 0, 1, 2
+ALGO_AUTO, ALGO_QAGS, ALGO_QAGP, ALGO_QAG = 0, 1, 2, 3
 _engines = {}
 _lock = threading.Lock()
 

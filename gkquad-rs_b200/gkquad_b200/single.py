@@ -15,7 +15,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from .common import BatchResult, IntegrationResult, Tolerance
-from .engine import ALGO_AUTO, ALGO_QAGP, ALGO_QAGS, default_engine
+from .engine import ALGO_AUTO, ALGO_QAG, ALGO_QAGP, ALGO_QAGS, default_engine
 
 
 class Range:
@@ -128,6 +128,11 @@ class QAGS(Algorithm):
 class QAGP(Algorithm):
     """single/algorithm/qagp.rs:20-64"""
     ALGO = ALGO_QAGP
+
+
+class QAG(Algorithm):
+    """single/algorithm/qag.rs:16-60 (deprecated in the reference since 0.0.3: "always worse than QAGS")."""
+    ALGO = ALGO_QAG
 
 
 class AUTO(Algorithm):

@@ -11,6 +11,7 @@ pub type gkq_handle_t = *mut gkq_handle_s;
 pub const GKQ_ALGO_AUTO: i32 = 0;
 pub const GKQ_ALGO_QAGS: i32 = 1;
 pub const GKQ_ALGO_QAGP: i32 = 2;
+pub const GKQ_ALGO_QAG: i32 = 3;
 
 pub const GKQ_TOL_ABSOLUTE: i32 = 0;
 pub const GKQ_TOL_RELATIVE: i32 = 1;

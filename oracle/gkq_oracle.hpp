@@ -766,6 +766,120 @@ Result qags(F& f, const Range& range, const Config& config, WorkSpace& ws) {
     return qags_impl(w, r, config, ws);
 }
 
+// ---------------------------------------------------------------------------
+// QAG (deprecated in the reference, still public): single/algorithm/qag.rs:65-248.
+// The same skeleton as QAGS without the epsilon table; its initial pass uses 50 eps (not 100)
+// for the round-off floor (qag.rs:217) and keeps no absvalue.
+// ---------------------------------------------------------------------------
+template <class W>
+inline Result qag_initial_integral(W& f, const Range& range, const Config& config, bool& finished) {
+    Result solution;  // Solution::default()
+    finished = true;
+    for (int i = 0; i < 2; ++i) {
+        QKResult result0;
+        if (i == 0) {
+            solution.nevals += 17;
+            result0 = qk17(f, range);
+        } else {
+            solution.nevals += 25;
+            result0 = qk25(f, range);
+        }
+        solution.estimate = result0.estimate;
+        solution.delta = result0.delta;
+        if (result0.estimate != result0.estimate) {  // qag.rs:204-209
+            solution.status = ST_NAN_VALUE_ENCOUNTERED;
+            return solution;
+        }
+        double tolerance = config.tol.to_abs(std::fabs(result0.estimate));
+        if ((result0.delta <= tolerance && result0.delta != result0.asc) || result0.delta == 0.0)
+            return solution;  // :212-214
+        double round_off = 50. * F64_EPSILON * result0.absvalue;  // :217
+        if (result0.delta <= round_off && result0.delta > tolerance) {
+            solution.status = ST_ROUNDOFF_ERROR;
+            return solution;
+        }
+        if (config.max_evals < (uint64_t)(42 + i * 25)) {  // :222-227
+            solution.status = ST_INSUFFICIENT_ITERATION;
+            return solution;
+        }
+        if (i == 0 && result0.delta > tolerance * 1024.) break;  // :229-231
+    }
+    finished = false;
+    return solution;
+}
+
+// qag.rs:65-183
+template <class W>
+Result qag_impl(W& f, const Range& range, const Config& config, WorkSpace& ws) {
+    int roundoff_type1 = 0, roundoff_type2 = 0;
+    uint32_t error = ST_NONE;
+    if (config.max_evals < 17) {
+        Result r;
+        r.status = ST_INSUFFICIENT_ITERATION;
+        return r;
+    }
+    bool finished;
+    Result result0 = qag_initial_integral(f, range, config, finished);
+    if (finished) return result0;
+
+    double area = result0.estimate;
+    double deltasum = result0.delta;
+    uint64_t nevals = result0.nevals;
+
+    ws.clear();
+    ws.reserve((config.max_evals - nevals) / 50 + 1);
+    ws.push(SubRangeInfo{range, result0.estimate, result0.delta, 0});
+
+    const uint64_t max_iters = (config.max_evals - nevals) / 50;
+    for (uint64_t it = 1; it <= max_iters; ++it) {
+        const SubRangeInfo info = ws.get();
+        size_t current_level = info.level + 1;
+        double center = (info.range.begin + info.range.end) * 0.5;  // util.rs:151-159
+        Range r1{info.range.begin, center};
+        Range r2{center, info.range.end};
+        QKResult result1 = qk25(f, r1);
+        QKResult result2 = qk25(f, r2);
+        nevals += 50;
+        if (result1.estimate != result1.estimate || result2.estimate != result2.estimate) {
+            error = ST_NAN_VALUE_ENCOUNTERED;  // :122-125
+            break;
+        }
+        double area12 = result1.estimate + result2.estimate;
+        double delta12 = result1.delta + result2.delta;
+        deltasum += delta12 - info.delta;
+        area += area12 - info.estimate;
+        if (result1.asc != result1.delta && result2.asc != result2.delta) {  // :135-142
+            if (std::fabs(info.estimate - area12) <= 1e-5 * std::fabs(area12) && delta12 >= 0.99 * info.delta)
+                roundoff_type1 += 1;
+            else
+                roundoff_type2 += 1;
+        }
+        double tolerance = config.tol.to_abs(std::fabs(area));
+        if (deltasum > tolerance) {  // :147-162
+            if (roundoff_type1 >= 6 || roundoff_type2 >= 20)
+                error = ST_ROUNDOFF_ERROR;
+            else if (subrange_too_small(r1.begin, r1.end, r2.end))
+                error = ST_SUBRANGE_TOO_SMALL;
+            if (error != ST_NONE)
+                return finish(ws.sum_results() - info.estimate + result1.estimate + result2.estimate, deltasum,
+                              nevals, error);
+        }
+        ws.update(SubRangeInfo{r1, result1.estimate, result1.delta, current_level},
+                  SubRangeInfo{r2, result2.estimate, result2.delta, current_level});
+        if (deltasum <= tolerance) break;  // :170-172
+    }
+    return finish(ws.sum_results(), deltasum, nevals, error);  // :176
+}
+
+// qag.rs:39-60
+template <class F>
+Result qag(F& f, const Range& range, const Config& config, WorkSpace& ws) {
+    bool transform = !std::isfinite(range.begin) || !std::isfinite(range.end);
+    IntegrandWrapper<F> w{f, transform};
+    Range r = transform ? transform_range(range) : range;
+    return qag_impl(w, r, config, ws);
+}
+
 // single/util.rs:178-211 -- insertion sort with a strict comparator.  An element is
 // left in place when is_less(prev, target); otherwise it moves down to just above the
 // first lower neighbour for which is_less(another, target) holds.
@@ -1026,7 +1140,7 @@ Result qagp(F& f, const Range& range, const Config& config, WorkSpace& ws) {
     return qagp_impl(w, r, config, transform, ws);
 }
 
-enum Algo : int { ALGO_AUTO = 0, ALGO_QAGS = 1, ALGO_QAGP = 2 };
+enum Algo : int { ALGO_AUTO = 0, ALGO_QAGS = 1, ALGO_QAGP = 2, ALGO_QAG = 3 };
 
 // single/algorithm/auto.rs:7-35 -- AUTO owns one workspace per algorithm.
 struct Workspaces {
@@ -1038,6 +1152,7 @@ template <class F>
 Result integrate(int algo, F& f, const Range& range, const Config& config, Workspaces& w) {
     if (algo == ALGO_QAGS) return qags(f, range, config, w.qags_ws);
     if (algo == ALGO_QAGP) return qagp(f, range, config, w.qagp_ws);
+    if (algo == ALGO_QAG) return qag(f, range, config, w.qags_ws);  // (shares the QAGS slot: one list)
     if (config.npoints == 0) return qags(f, range, config, w.qags_ws);
     return qagp(f, range, config, w.qagp_ws);
 }

@@ -272,7 +272,7 @@ struct DispatchOne {
             out2[1] = res.delta;
             *out_nevals = (uint32_t)res.nevals;
             *out_status = res.status;
-            bool use_qags = (algo == ALGO_QAGS) || (algo == ALGO_AUTO && cfg.npoints == 0);
+            bool use_qags = (algo == ALGO_QAGS) || (algo == ALGO_QAG) || (algo == ALGO_AUTO && cfg.npoints == 0);
             const WorkSpace& ws = use_qags ? w.qags_ws : w.qagp_ws;
             *order_len = (int64_t)ws.order.size();
             for (int64_t k = 0; k < (int64_t)ws.order.size() && k < order_cap; ++k)

@@ -1,7 +1,7 @@
 """Shared helpers for the test-suite (not product code)."""
 import math
 
-ALGO = {"AUTO": 0, "QAGS": 1, "QAGP": 2}
+ALGO = {"AUTO": 0, "QAGS": 1, "QAGP": 2, "QAG": 3}
 STATUS = {"None": 0, "InsufficientIteration": 1, "RoundoffError": 2, "SubrangeTooSmall": 3,
           "Divergent": 4, "NanValueEncountered": 5}
 

@@ -389,6 +389,29 @@ def test_double_budget_exhaustion(eng, mode, monkeypatch):
                 compare(g, ref, _tol(tol), exact=f != "g2", label=f"{f} max_evals={me}")
 
 
+def test_qag_batch_bit_exact(eng):
+    """The deprecated QAG (single/algorithm/qag.rs:65-248) on batches of IEEE-exact integrands: finite and
+    infinite ranges, per-integral budgets, device and host entry -- bit-identical to the oracle."""
+    import torch
+    from gkquad_b200 import Tolerance
+    from gpu_common import compare
+    from oracle import oracle as O
+    rng = np.random.default_rng(11)
+    n = 6000
+    p = 10.0 ** rng.uniform(0, 4, (1, n))
+    me = rng.choice([0, 16, 17, 41, 42, 66, 67, 117, 500, 2000], n).astype(np.uint64)
+    for a, b, tol, otol in ((-1.0, 1.0, Tolerance.Relative(1e-11), ("rel", 1e-11)),
+                            (-math.inf, math.inf, Tolerance.Absolute(1e-10), ("abs", 1e-10)),
+                            (0.0, 1.0, Tolerance.Absolute(1e-15), ("abs", 1e-15))):
+        ref = O.integrate_batch(ALGO["QAG"], "lorentz_p", a, b, p, tol=otol, max_evals=2000, n=n, max_evals_each=me)
+        g = eng.integrate_batch("lorentz_p", a, b, torch.as_tensor(p, device="cuda:0"), algo=ALGO["QAG"], tol=tol,
+                                max_evals=2000, n=n, max_evals_each=me.astype(np.int64))
+        compare(g, ref, tol, exact=True, label=f"QAG device [{a}, {b}]")
+        g = eng.integrate_batch("lorentz_p", a, b, p, algo=ALGO["QAG"], tol=tol, max_evals=2000, n=n, max_evals_each=me)
+        compare(g, ref, tol, exact=True, label=f"QAG host [{a}, {b}]")
+    assert len(np.unique(ref["status"])) >= 2
+
+
 def test_per_integral_tolerance_and_budget(eng):
     """every integral with its own tolerance values and evaluation budget (an Integrator
     re-configured per integral, single/integrator.rs:69-84) -- device entry, host entry, QAGS and QAGP,
