@@ -771,6 +771,11 @@ static int run_qags_bulk(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, 
     if (h->occ_init25[fid] < 0) h->occ_init25[fid] = L.occupancy_init25();
     long long g25 = (long long)h->sm_count * (h->occ_init25[fid] > 0 ? h->occ_init25[fid] : 1);
     if (g25 > nblocks) g25 = nblocks;
+    // the first-step kernel has its own shape: enough resident threads for the loop entrants of a
+    // typical batch to run as ONE wave (a grid-stride second trip doubles its time)
+    long long gfirst = (long long)h->sm_count * GKQ_FIRST_MIN_BLOCKS;
+    const long long nb_first = (P.n + FBLOCK - 1) / FBLOCK;
+    if (gfirst > nb_first) gfirst = nb_first;
 
     // fork: chain 1 (qk25 pass + its first steps) runs on the side stream.  In profiling mode
     // everything stays on one stream so that the per-kernel event brackets are clean.
@@ -790,7 +795,7 @@ static int run_qags_bulk(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, 
             if ((rc = launch_check(h, "k_qags_init<qk25>"))) return rc;
         }
         prof_begin(h, c == 0 ? "k_qags_first[0]" : "k_qags_first[1]", cs);
-        L.qags_first(Q, (int)g25, cs);
+        L.qags_first(Q, (int)gfirst, cs);
         prof_end(h, cs);
         if ((rc = launch_check(h, "k_qags_first"))) return rc;
     }

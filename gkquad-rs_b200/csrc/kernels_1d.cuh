@@ -211,6 +211,15 @@ struct RuleUnroll {
 #ifndef GKQ_INIT17_MIN_BLOCKS
 #define GKQ_INIT17_MIN_BLOCKS 4
 #endif
+// the persistent kernel: its loop also holds the list / epsilon-table code, so the rule is unrolled
+// less than in the flat kernels (instruction cache; profiles/)
+#ifndef GKQ_ADAPT_UNROLL_LIGHT
+#define GKQ_ADAPT_UNROLL_LIGHT 12
+#endif
+template <class F, int N>
+struct AdaptUnroll {
+    static constexpr int value = F::HEAVY ? 1 : (GKQ_ADAPT_UNROLL_LIGHT < N ? GKQ_ADAPT_UNROLL_LIGHT : N);
+};
 template <class F, int N>
 struct InitUnroll {
     static constexpr int value = F::HEAVY ? GKQ_INIT_UNROLL_HEAVY : N;
@@ -285,11 +294,18 @@ __global__ void __launch_bounds__(BLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : 3) k
 // the integrals that need a second step go on to the persistent kernel, which resumes them
 // from the state this kernel parks (list = the two halves ordered by error, order = [0, 1],
 // epsilon table = [result0, area], ktmin = 1: what qags.rs leaves behind after iteration 1).
+#ifndef GKQ_FIRST_BLOCK
+#define GKQ_FIRST_BLOCK 128
+#endif
+#ifndef GKQ_FIRST_MIN_BLOCKS
+#define GKQ_FIRST_MIN_BLOCKS 7
+#endif
+constexpr int FBLOCK = GKQ_FIRST_BLOCK;
 template <class F, int NPARAMS>
-__global__ void __launch_bounds__(BLOCK, 3) k_qags_first(const Batch1D P) {
+__global__ void __launch_bounds__(FBLOCK, GKQ_FIRST_MIN_BLOCKS) k_qags_first(const Batch1D P) {
     const long long total = (long long)P.ctl->chain[P.chain].countLoop;
-    for (long long k = (long long)blockIdx.x * BLOCK + threadIdx.x; k - threadIdx.x % 32 < total;
-         k += (long long)gridDim.x * BLOCK) {
+    for (long long k = (long long)blockIdx.x * FBLOCK + threadIdx.x; k - threadIdx.x % 32 < total;
+         k += (long long)gridDim.x * FBLOCK) {
         bool survive = false;
         long long i = 0;
         StragglerRec rec;
@@ -651,7 +667,7 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
             for (int hh = 0; hh < 2; ++hh) {
                 const bool on = hh ? has1 : has0;
                 if (on) {
-                    const QK q = qk_rule<12, RuleUnroll<F, 12>::value>(g, hh ? ra1 : ra0, hh ? rb1 : rb0);
+                    const QK q = qk_rule<12, AdaptUnroll<F, 12>::value>(g, hh ? ra1 : ra0, hh ? rb1 : rb0);
                     if (hh) q1 = q; else q0 = q;
                 }
             }
@@ -926,7 +942,7 @@ GKQ_F1_LIST(GKQ_DECL_F1)
             k_qags_init<F1<ID>, 12, NP><<<grid, BLOCK, 0, st>>>(P);                                  \
         };                                                                                           \
         L.qags_first = [](const Batch1D& P, int grid, cudaStream_t st) {                             \
-            k_qags_first<F1<ID>, NP><<<grid, BLOCK, 0, st>>>(P);                                     \
+            k_qags_first<F1<ID>, NP><<<grid, FBLOCK, 0, st>>>(P);                                    \
         };                                                                                           \
         L.qags_loop = [](const Batch1D& P, int grid, cudaStream_t st) {                              \
             k_adaptive<F1<ID>, false, NP><<<grid, ABLOCK, 0, st>>>(P);                                \
