@@ -57,7 +57,11 @@ template <int ID> struct F1;
         }                                                                        \
     };
 #define GKQ_F1(ID, HEAVY_, BODY) GKQ_F1_IMPL(ID, HEAVY_, false, BODY)
+#ifdef GKQ_NO_PAIRWISE
+#define GKQ_F1P(ID, HEAVY_, BODY) GKQ_F1_IMPL(ID, HEAVY_, false, BODY)
+#else
 #define GKQ_F1P(ID, HEAVY_, BODY) GKQ_F1_IMPL(ID, HEAVY_, true, BODY)
+#endif
 GKQ_F1(F1_SQUARE, false, return x * x;)                                   // benches/single.rs:11
 GKQ_F1(F1_RECIP_P, false, return p[0] / x;)                               // benches/single.rs:20
 GKQ_F1(F1_LORENTZ_P, false, return 1.0 / (1.0 + p[0] * (x * x));)         // benches/single.rs:32
