@@ -1422,6 +1422,7 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
             // outer integrals per warp: as few as still keep every warp of the grid busy
             const long long warps = (long long)grid * (PB / 32);
             long long r = (n + warps - 1) / warps;
+            if (const char* env = getenv("GKQ_POOL_R")) r = atoll(env);  // tuning knob
             if (r < 1) r = 1;
             if (r > POOL_R) r = POOL_R;
             Q.pool_r = (int)r;

@@ -15,8 +15,9 @@
 //   2. the 32 lanes of the warp work the board off as "inner lanes": each owns one inner
 //      integral at a time (initial passes / break-point seeding / bisection loop), takes the next
 //      task when its own terminates, and all lanes meet once per trip in the same sampling code,
-//      so the warp stays converged however different the iteration counts are; when only a few
-//      long inner integrals are left, the warp spreads the 50 samples of each over its lanes;
+//      so the warp stays converged however different the iteration counts are (a cooperative
+//      50-samples-over-32-lanes mode for the last few long inner integrals exists behind
+//      GKQ_POOL_COOP_MAX_LIVE; with several outer integrals per warp it measured slower);
 //   3. the owners commit their tasks in the reference's call order (below), reduce the values in
 //      the reference's summation order (bit-identical outer arithmetic) and advance their outer
 //      state machines, POOL_R of them side by side.
@@ -38,6 +39,10 @@ namespace gkq {
 constexpr int PB = 128;                 // threads per block of k_nested_pool
 constexpr int POOL_R = 6;               // outer integrals per warp (shared memory: 16 warps per SM)
 constexpr int POOL_T = POOL_R * 50;     // board slots per warp (a bisection step posts 50 tasks)
+#ifndef GKQ_POOL_COOP_MAX_LIVE
+#define GKQ_POOL_COOP_MAX_LIVE 0  /* measured: D1 13.6 ms with 0, 15.4 with 2, 17.9 with 8 (profiles/) */
+#endif
+constexpr int POOL_COOP_MAX_LIVE = GKQ_POOL_COOP_MAX_LIVE;  // <= this many live inner lanes: cooperative sampling
 
 struct TripPlan {
     double ra0, rb0, ra1, rb1;
@@ -449,7 +454,7 @@ __global__ void __launch_bounds__(PB, 4) k_nested_pool(const Batch2D P) {
                 if (!QAGP && __any_sync(FULL, p.has17)) {
                     if (p.has17) q0 = qk_rule<8, NESTED_UNROLL>(g, p.ra0, p.rb0);
                 }
-                if (__popc(live) > COOP_MAX_LIVE) {
+                if (POOL_COOP_MAX_LIVE == 0 || __popc(live) > POOL_COOP_MAX_LIVE) {
 #pragma unroll 1
                     for (int hh = 0; hh < 2; ++hh) {
                         const bool on = hh ? p.has1 : p.has0;
