@@ -1289,7 +1289,7 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
 }
 
 // ---- 2-D ----------------------------------------------------------------------------------------
-int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id, int yrange_id,
+int gkq_integrate2_batch_ex(gkq_handle_t h, const gkq_config* cfg, const gkq_overrides* ov, int functor2_id, int yrange_id,
                          int64_t n, const double* x0, const double* x1, int64_t range_stride,
                          const double* fparams, int64_t fparam_stride, const double* yparams,
                          int64_t yparam_stride, const int64_t* pts_offsets, const double* pts_xy,
@@ -1335,6 +1335,11 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
     P.yrange_id = yrange_id;
     P.nyparams = YR_TABLE[yrange_id].nparams;
     P.swap_xy = (cfg->flags & GKQ_FLAG_SWAP_XY) != 0;
+    if (ov) {  // per-integral tolerance values / total budgets (device arrays)
+        P.abs_tol_each = ov->abs_tol;
+        P.rel_tol_each = ov->rel_tol;
+        P.max_evals_each = (const unsigned long long*)ov->max_evals;
+    }
     P.tol.kind = cfg->tol.kind;
     P.tol.abs_tol = cfg->tol.abs_tol;
     P.tol.rel_tol = cfg->tol.rel_tol;
@@ -1448,6 +1453,17 @@ int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
     return GKQ_OK;
 }
 
+int gkq_integrate2_batch(gkq_handle_t h, const gkq_config* cfg, int functor2_id, int yrange_id,
+                         int64_t n, const double* x0, const double* x1, int64_t range_stride,
+                         const double* fparams, int64_t fparam_stride, const double* yparams,
+                         int64_t yparam_stride, const int64_t* pts_offsets, const double* pts_xy,
+                         double* out_estimate, double* out_delta, uint32_t* out_nevals,
+                         uint32_t* out_status, void* stream) {
+    return gkq_integrate2_batch_ex(h, cfg, nullptr, functor2_id, yrange_id, n, x0, x1, range_stride, fparams,
+                                   fparam_stride, yparams, yparam_stride, pts_offsets, pts_xy, out_estimate,
+                                   out_delta, out_nevals, out_status, stream);
+}
+
 int gkq_integrate2_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor2_id,
                               int yrange_id, int64_t n, const double* x0, const double* x1,
                               int64_t range_stride, const double* fparams, int64_t fparam_stride,
@@ -1455,6 +1471,17 @@ int gkq_integrate2_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor
                               const int64_t* pts_offsets, const double* pts_xy,
                               double* out_estimate, double* out_delta, uint32_t* out_nevals,
                               uint32_t* out_status) {
+    return gkq_integrate2_batch_host_ex(h, cfg, nullptr, functor2_id, yrange_id, n, x0, x1, range_stride, fparams,
+                                        fparam_stride, yparams, yparam_stride, pts_offsets, pts_xy,
+                                        out_estimate, out_delta, out_nevals, out_status);
+}
+
+int gkq_integrate2_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq_overrides* ov_host,
+                                 int functor2_id, int yrange_id, int64_t n, const double* x0,
+                                 const double* x1, int64_t range_stride, const double* fparams,
+                                 int64_t fparam_stride, const double* yparams, int64_t yparam_stride,
+                                 const int64_t* pts_offsets, const double* pts_xy, double* out_estimate,
+                                 double* out_delta, uint32_t* out_nevals, uint32_t* out_status) {
     if (!h) return GKQ_ERR_INVALID_ARGUMENT;
     if (n < 0) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "n out of range");
     if (n == 0) return GKQ_OK;
@@ -1472,7 +1499,8 @@ int gkq_integrate2_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor
     const size_t nx = range_stride ? N : 1, nfp = fparam_stride ? N : 1, nyp = yparam_stride ? N : 1;
     const size_t in_d = 2 * nx + (size_t)np * nfp + (size_t)nq * nyp;
     const size_t csr_d = pts_offsets ? (N + 1) + 2 * npairs : 0;  // offsets (as 8-byte) + pairs
-    const size_t bytes = (in_d + csr_d) * 8 + N * 24 + 256;
+    const int n_ov = ov_host ? (ov_host->abs_tol != nullptr) + (ov_host->rel_tol != nullptr) + (ov_host->max_evals != nullptr) : 0;
+    const size_t bytes = (in_d + csr_d) * 8 + N * 24 + (size_t)n_ov * N * 8 + 256;
     if (bytes > h->stage_bytes) {
         if (h->stage_dev) GKQ_CUDA(h, cudaFree(h->stage_dev));
         h->stage_dev = nullptr;
@@ -1494,6 +1522,25 @@ int gkq_integrate2_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor
     double* d_dlt = d_est + N;
     uint32_t* d_nev = (uint32_t*)(d_dlt + N);
     uint32_t* d_st = d_nev + N;
+    gkq_overrides ov_dev = {nullptr, nullptr, nullptr};
+    {
+        double* q = (double*)(d_st + N);
+        if (ov_host && ov_host->abs_tol) {
+            ov_dev.abs_tol = q;
+            GKQ_CUDA(h, cudaMemcpyAsync(q, ov_host->abs_tol, N * 8, cudaMemcpyHostToDevice, st));
+            q += N;
+        }
+        if (ov_host && ov_host->rel_tol) {
+            ov_dev.rel_tol = q;
+            GKQ_CUDA(h, cudaMemcpyAsync(q, ov_host->rel_tol, N * 8, cudaMemcpyHostToDevice, st));
+            q += N;
+        }
+        if (ov_host && ov_host->max_evals) {
+            ov_dev.max_evals = (const uint64_t*)q;
+            GKQ_CUDA(h, cudaMemcpyAsync(q, ov_host->max_evals, N * 8, cudaMemcpyHostToDevice, st));
+            q += N;
+        }
+    }
     if (pts_offsets) {
         GKQ_CUDA(h, cudaMemcpyAsync(d_off, pts_offsets, (N + 1) * 8, cudaMemcpyHostToDevice, st));
         if (npairs) GKQ_CUDA(h, cudaMemcpyAsync(d_pairs, pts_xy, npairs * 16, cudaMemcpyHostToDevice, st));
@@ -1506,7 +1553,7 @@ int gkq_integrate2_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor
     for (int k = 0; k < nq; ++k)
         GKQ_CUDA(h, cudaMemcpyAsync(d_yp + (size_t)k * nyp, yparams + (size_t)k * (yparam_stride ? yparam_stride : 1),
                                     nyp * 8, cudaMemcpyHostToDevice, st));
-    int rc = gkq_integrate2_batch(h, cfg, functor2_id, yrange_id, n, d_x0, d_x1, range_stride, d_fp,
+    int rc = gkq_integrate2_batch_ex(h, cfg, n_ov ? &ov_dev : nullptr, functor2_id, yrange_id, n, d_x0, d_x1, range_stride, d_fp,
                                   fparam_stride ? (int64_t)N : 0, d_yp, yparam_stride ? (int64_t)N : 0,
                                   pts_offsets ? (const int64_t*)d_off : nullptr,
                                   pts_offsets ? d_pairs : nullptr, d_est, d_dlt, d_nev, d_st, st);

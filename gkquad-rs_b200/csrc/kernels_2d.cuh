@@ -367,8 +367,25 @@ struct Batch2D {
     SlabGeom slab;
     int cap_outer, cap_inner;
     bool swap_xy;  // GKQ_FLAG_SWAP_XY
+    // optional per-integral tolerance values / total budget (gkq_overrides); budgets are clamped
+    // to max_evals, which sizes the interval slabs
+    const double* abs_tol_each;
+    const double* rel_tol_each;
+    const unsigned long long* max_evals_each;
     int pool_r;  // k_nested_pool: outer integrals per warp (<= POOL_R)
 };
+
+GKQ_DEV Tol load_tol2(const Batch2D& P, long long i) {
+    Tol t = P.tol;
+    if (P.abs_tol_each) t.abs_tol = P.abs_tol_each[i];
+    if (P.rel_tol_each) t.rel_tol = P.rel_tol_each[i];
+    return t;
+}
+GKQ_DEV unsigned long long load_max_evals2(const Batch2D& P, long long i) {
+    if (!P.max_evals_each) return P.max_evals;
+    const unsigned long long m = P.max_evals_each[i];
+    return m < P.max_evals ? m : P.max_evals;
+}
 
 // f(x, .) as a 1-D integrand of y
 template <class F2T>
@@ -492,8 +509,10 @@ __global__ void __launch_bounds__(BLOCK) k_nested(const Batch2D P) {
         for (int k = 0; k < P.nyparams && k < 2; ++k)
             G.yr.q[k] = P.yparam_stride ? P.yparams[(long long)k * P.yparam_stride + (long long)i]
                                         : P.yparams[k];
-        G.tol = P.tol;
-        G.total_evals = P.max_evals;
+        const Tol my_tol = load_tol2(P, (long long)i);
+        const unsigned long long my_max_evals = load_max_evals2(P, (long long)i);
+        G.tol = my_tol;
+        G.total_evals = my_max_evals;
         G.nevals = 0;
         G.error = ST_NONE;
         G.inner_cap = 0;  // WorkSpace::new()
@@ -512,7 +531,7 @@ __global__ void __launch_bounds__(BLOCK) k_nested(const Batch2D P) {
         G.transform = xtr;
 
         unsigned long long outer_cap = 0;  // QAGS::new() / QAGP::new(): fresh outer workspace
-        const unsigned long long outer_evals = P.max_evals / 17ull;
+        const unsigned long long outer_evals = my_max_evals / 17ull;
         Res r;
         if (QAGP) {
             // outer points = x of the 2-D points, transformed HERE when the x-range is infinite
@@ -522,9 +541,9 @@ __global__ void __launch_bounds__(BLOCK) k_nested(const Batch2D P) {
                 const double x = p[2 * k];
                 return xtr ? transform_point(x) : x;
             };
-            r = seq_qagp<RM_ORDERED, 1>(G, xa, xb, xtr, user_pt, my_npts, P.tol, outer_evals, outer_cap, Sout);
+            r = seq_qagp<RM_ORDERED, 1>(G, xa, xb, xtr, user_pt, my_npts, my_tol, outer_evals, outer_cap, Sout);
         } else {
-            r = seq_qags<RM_ORDERED, 1>(G, xa, xb, P.tol, outer_evals, outer_cap, Sout);
+            r = seq_qags<RM_ORDERED, 1>(G, xa, xb, my_tol, outer_evals, outer_cap, Sout);
         }
         // result.value.nevals = nevals; if error.is_some() { result.error = error }
         write_result(P.out, (long long)i, r.est, r.dlt, (uint32_t)G.nevals,
@@ -587,23 +606,17 @@ GKQ_F2_LIST(GKQ_DECL_F2)
             return nb;                                                                            \
         };                                                                                        \
         L.run_pool[0] = [](const Batch2D& P, int grid, cudaStream_t st) {                         \
-            static bool once = false;                                                             \
             const int smem = (PB / 32) * (int)sizeof(PoolShared);                                 \
-            if (!once) {                                                                          \
-                cudaFuncSetAttribute(k_nested_pool<F2<ID>, false, NP>,                            \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem);          \
-                once = true;                                                                      \
-            }                                                                                     \
+            /* per device: set on every launch (an engine per GPU may live in one process) */     \
+            cudaFuncSetAttribute(k_nested_pool<F2<ID>, false, NP>,                            \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem);          \
             k_nested_pool<F2<ID>, false, NP><<<grid, PB, smem, st>>>(P);                          \
         };                                                                                        \
         L.run_pool[1] = [](const Batch2D& P, int grid, cudaStream_t st) {                         \
-            static bool once = false;                                                             \
             const int smem = (PB / 32) * (int)sizeof(PoolShared);                                 \
-            if (!once) {                                                                          \
-                cudaFuncSetAttribute(k_nested_pool<F2<ID>, true, NP>,                             \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem);          \
-                once = true;                                                                      \
-            }                                                                                     \
+            /* per device: set on every launch (an engine per GPU may live in one process) */     \
+            cudaFuncSetAttribute(k_nested_pool<F2<ID>, true, NP>,                             \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem);          \
             k_nested_pool<F2<ID>, true, NP><<<grid, PB, smem, st>>>(P);                           \
         };                                                                                        \
         L.occupancy_pool[0] = []() {                                                              \

@@ -242,6 +242,8 @@ struct OuterCtx {
     double wa, wb;          // transformed outer range
     unsigned long long nevals, inner_cap, budget0;  // running state; budget handed to this trip's tasks
     uint32_t error;         // first inner error
+    Tol tol;                // this outer integral's tolerance and total budget
+    unsigned long long max_evals;
     int npts;
     int base, K;            // this trip's tasks: board slots [base, base + K)
     bool xtr, exact;
@@ -255,6 +257,8 @@ struct PoolShared {
     double est[POOL_T];
     uint32_t nev[POOL_T], meta[POOL_T];  // meta = status | RSV_* << 3 | n << 5
 };
+// 4 warps per block, 4 blocks per SM must fit the 227 KB of shared memory (1 KB per block is reserved)
+static_assert(4 * sizeof(PoolShared) <= 55 * 1024, "PoolShared too large for 16 warps per SM");
 struct PoolBoardSink {
     PoolShared* W;
     GKQ_DEV void put(long long t, double est, double, uint32_t nev, uint32_t st) const {
@@ -296,7 +300,6 @@ __global__ void __launch_bounds__(PB, 4) k_nested_pool(const Batch2D P) {
 
     const unsigned long long total = P.worklist ? *P.worklist_count : (unsigned long long)P.n;
     unsigned long long* head = QAGP ? &P.ctl->headP : &P.ctl->head2;
-    const unsigned long long outer_evals = P.max_evals / 17ull;
     const bool owner = lane < P.pool_r;
     Lane& so = W.outer[owner ? lane : 0];
     OuterCtx& cx = W.ctx[owner ? lane : 0];
@@ -353,9 +356,11 @@ __global__ void __launch_bounds__(PB, 4) k_nested_pool(const Batch2D P) {
                 cx.nevals = 0;
                 cx.error = ST_NONE;
                 cx.inner_cap = 0;  // WorkSpace::new()
+                cx.tol = load_tol2(P, i);
+                cx.max_evals = load_max_evals2(P, i);
                 // outer points = x of the 2-D points, transformed HERE when the x-range is infinite
                 // (double/algorithm/qagp.rs:98-106) and once more inside make_sorted_points
-                lane_start<QAGP>(Sout, so, i, xa, xb, xtr, cx.pts_xy, cx.npts, 2, xtr, outer_evals, 0ull,
+                lane_start<QAGP>(Sout, so, i, xa, xb, xtr, cx.pts_xy, cx.npts, 2, xtr, cx.max_evals / 17ull, 0ull,
                                  osink, (uint32_t*)nullptr);
             }
         }
@@ -373,7 +378,7 @@ __global__ void __launch_bounds__(PB, 4) k_nested_pool(const Batch2D P) {
             K = cx.plan.has17 ? 17 : (cx.plan.has0 ? (cx.plan.has1 ? 50 : 25) : 0);
             ns.K = K;
             // config1.max_evals = if error.is_some() { 0 } else { config.max_evals - nevals }
-            cx.budget0 = (cx.error != ST_NONE || cx.nevals > P.max_evals) ? 0ull : (P.max_evals - cx.nevals);
+            cx.budget0 = (cx.error != ST_NONE || cx.nevals > cx.max_evals) ? 0ull : (cx.max_evals - cx.nevals);
         }
         if (__ballot_sync(FULL, oact) == 0u) break;  // nothing in flight and the batch is handed out
         int incl = K;
@@ -399,6 +404,7 @@ __global__ void __launch_bounds__(PB, 4) k_nested_pool(const Batch2D P) {
             g.transform = false;
             double ya = 0., yb = 0.;  // the lane's whole inner range (initial passes of QAGS)
             unsigned long long budget0 = 0, cap0 = 0;
+            Tol tol = P.tol;  // the owning outer integral's tolerance
             int next = 0;
             for (;;) {
                 const unsigned idle = __ballot_sync(FULL, !s.active);
@@ -434,6 +440,7 @@ __global__ void __launch_bounds__(PB, 4) k_nested_pool(const Batch2D P) {
                             yb = y1;
                             budget0 = c.budget0;
                             cap0 = c.inner_cap;
+                            tol = c.tol;
                             lane_start<QAGP>(Sin, s, tk, y0, y1, ytr, c.pts_xy + 1, c.npts, 2, false, budget0,
                                              cap0, bsink, &W.meta[tk]);
                         }
@@ -490,7 +497,7 @@ __global__ void __launch_bounds__(PB, 4) k_nested_pool(const Batch2D P) {
                     }
                 }
                 if (s.active)
-                    lane_finish<QAGP>(Sin, s, P.tol, budget0, cap0, bsink, &W.meta[s.idx], p, q0, q1, ya, yb);
+                    lane_finish<QAGP>(Sin, s, tol, budget0, cap0, bsink, &W.meta[s.idx], p, q0, q1, ya, yb);
             }
         }
         __syncwarp();
@@ -548,8 +555,8 @@ __global__ void __launch_bounds__(PB, 4) k_nested_pool(const Batch2D P) {
                 G.yr.id = P.yrange_id;
                 G.yr.q[0] = cx.yq[0];
                 G.yr.q[1] = cx.yq[1];
-                G.tol = P.tol;
-                G.total_evals = P.max_evals;
+                G.tol = cx.tol;
+                G.total_evals = cx.max_evals;
                 G.nevals = cx.nevals;
                 G.error = cx.error;
                 G.inner_cap = cx.inner_cap;
@@ -603,7 +610,7 @@ __global__ void __launch_bounds__(PB, 4) k_nested_pool(const Batch2D P) {
                     if (half) q1 = q; else q0 = q;
                 }
             }
-            lane_finish<QAGP>(Sout, so, P.tol, outer_evals, 0ull, osink, (uint32_t*)nullptr, cx.plan, q0, q1,
+            lane_finish<QAGP>(Sout, so, cx.tol, cx.max_evals / 17ull, 0ull, osink, (uint32_t*)nullptr, cx.plan, q0, q1,
                               cx.wa, cx.wb);
         }
         __syncwarp();

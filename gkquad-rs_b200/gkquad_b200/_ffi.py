@@ -51,7 +51,7 @@ class gkq_stats(C.Structure):
 SYMBOLS = [
     "gkq_abi_version", "gkq_config_default", "gkq_create", "gkq_destroy", "gkq_last_error",
     "gkq_functor_count", "gkq_functor_info", "gkq_functor_lookup", "gkq_integrate_batch",
-    "gkq_integrate_batch_host", "gkq_integrate_batch_ex", "gkq_integrate_batch_host_ex", "gkq_integrate2_batch", "gkq_integrate2_batch_host", "gkq_qk_batch",
+    "gkq_integrate_batch_host", "gkq_integrate_batch_ex", "gkq_integrate_batch_host_ex", "gkq_integrate2_batch_ex", "gkq_integrate2_batch_host_ex", "gkq_integrate2_batch", "gkq_integrate2_batch_host", "gkq_qk_batch",
     "gkq_functor_eval_batch",
     "gkq_set_deferred_join", "gkq_join", "gkq_sync", "gkq_get_stats", "gkq_reset_stats", "gkq_set_profiling", "gkq_get_profile",
     "gkq_measure_fp64_peak",
@@ -92,6 +92,9 @@ def lib():
               dp, C.c_int64, i64p, dp, dp, dp, u32p, u32p]
     L.gkq_integrate2_batch.argtypes = batch2 + [vp]
     L.gkq_integrate2_batch_host.argtypes = batch2
+    batch2x = batch2[:2] + [C.POINTER(gkq_overrides)] + batch2[2:]
+    L.gkq_integrate2_batch_ex.argtypes = batch2x + [vp]
+    L.gkq_integrate2_batch_host_ex.argtypes = batch2x
     L.gkq_qk_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int64, dp, dp, C.c_int64, dp, C.c_int64, dp, vp]
     L.gkq_functor_eval_batch.argtypes = [vp, C.c_int, C.c_int64, dp, dp, C.c_int64, dp, vp]
     L.gkq_set_deferred_join.argtypes = [vp, C.c_int]

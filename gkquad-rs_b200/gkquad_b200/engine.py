@@ -274,13 +274,15 @@ class Engine:
     # ---- 2-D ------------------------------------------------------------------------------
     def integrate2_batch(self, functor2, yrange, x0, x1, fparams=None, yparams=None, *, algo=ALGO_AUTO,
                          tol=None, max_evals=100000, points=None, pts_offsets=None, pts_xy=None, n=None,
-                         swap_xy=False):
+                         swap_xy=False, abs_tol_each=None, rel_tol_each=None, max_evals_each=None):
         """n nested double integrals; yrange = registry name of the y(x) functor ('const',
         'zero_to_x', 'circle'); points = list of (x, y) pairs shared by the batch, or per-integral
         CSR: pts_offsets[n+1] (counting pairs) + pts_xy[m, 2].
         swap_xy (GKQ_FLAG_SWAP_XY, the reference's DynamicX): the integrand is evaluated as
         f(inner, outer); x0/x1 and the range functor then describe the outer / inner variable and the
-        points are (outer, inner) pairs."""
+        points are (outer, inner) pairs.
+        abs_tol_each / rel_tol_each / max_evals_each: optional arrays [n], every nest's own tolerance
+        values and TOTAL evaluation budget (clamped to `max_evals`)."""
         fid, fname, npar, _ = self.functor(2, functor2)
         yid, yname, nq, _ = self.functor(0, yrange)
         tol = tol or Tolerance.default()
@@ -335,23 +337,39 @@ class Engine:
             else:
                 po = np.ascontiguousarray(pts_offsets, dtype=np.int64)
                 pv = np.ascontiguousarray(pts_xy, dtype=np.float64)
+        ov = None
+        keep_ov = ()
+        if abs_tol_each is not None or rel_tol_each is not None or max_evals_each is not None:
+            ate, rte = arr(abs_tol_each), arr(rel_tol_each)
+            mee = None
+            if max_evals_each is not None:
+                if on_dev:
+                    mee = (max_evals_each if _is_torch(max_evals_each) else torch.as_tensor(
+                        np.asarray(max_evals_each, dtype=np.int64), device=f"cuda:{self.device}"))
+                else:
+                    mee = np.ascontiguousarray(max_evals_each, dtype=np.uint64)
+            for x in (ate, rte, mee):
+                assert x is None or int(x.shape[0]) == n, "per-integral arrays need n entries"
+            ov = _ffi.gkq_overrides(self._ptr(ate), self._ptr(rte), self._ptr(mee))
+            keep_ov = (ate, rte, mee, ov)
+        ovp = C.byref(ov) if ov is not None else None
         if on_dev:
             dev = f"cuda:{self.device}"
             est = torch.empty(n, dtype=torch.float64, device=dev)
             dlt = torch.empty(n, dtype=torch.float64, device=dev)
             nev = torch.empty(n, dtype=torch.int32, device=dev)
             st = torch.empty(n, dtype=torch.int32, device=dev)
-            self._check(self.L.gkq_integrate2_batch(
-                self.h, C.byref(cfg), fid, yid, n, self._ptr(aa), self._ptr(bb), rs, self._ptr(fp), fs,
+            self._check(self.L.gkq_integrate2_batch_ex(
+                self.h, C.byref(cfg), ovp, fid, yid, n, self._ptr(aa), self._ptr(bb), rs, self._ptr(fp), fs,
                 self._ptr(yp), ys, self._ptr(po), self._ptr(pv), self._ptr(est), self._ptr(dlt),
                 self._ptr(nev), self._ptr(st), self._stream()))
             r = BatchResult(est, dlt, nev, st)
-            r._keep = (aa, bb, fp, yp, po, pv, cfg)
+            r._keep = (aa, bb, fp, yp, po, pv, cfg) + keep_ov
             return r
         est, dlt = np.empty(n), np.empty(n)
         nev, st = np.empty(n, dtype=np.uint32), np.empty(n, dtype=np.uint32)
-        self._check(self.L.gkq_integrate2_batch_host(
-            self.h, C.byref(cfg), fid, yid, n, self._ptr(aa), self._ptr(bb), rs, self._ptr(fp), fs,
+        self._check(self.L.gkq_integrate2_batch_host_ex(
+            self.h, C.byref(cfg), ovp, fid, yid, n, self._ptr(aa), self._ptr(bb), rs, self._ptr(fp), fs,
             self._ptr(yp), ys, self._ptr(po), self._ptr(pv), self._ptr(est), self._ptr(dlt), self._ptr(nev),
             self._ptr(st)))
         return BatchResult(est, dlt, nev, st)

@@ -106,6 +106,16 @@ extern "C" {
         functor_id: c_int, n: i64, a: *const f64, b: *const f64, range_stride: i64, params: *const f64,
         param_stride: i64, pts_offsets: *const i64, pts: *const f64, out_estimate: *mut f64,
         out_delta: *mut f64, out_nevals: *mut u32, out_status: *mut u32) -> c_int;
+    pub fn gkq_integrate2_batch_ex(h: gkq_handle_t, cfg: *const gkq_config, ov: *const gkq_overrides,
+        functor2_id: c_int, yrange_id: c_int, n: i64, x0: *const f64, x1: *const f64, range_stride: i64,
+        fparams: *const f64, fparam_stride: i64, yparams: *const f64, yparam_stride: i64,
+        pts_offsets: *const i64, pts_xy: *const f64, out_estimate: *mut f64, out_delta: *mut f64,
+        out_nevals: *mut u32, out_status: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn gkq_integrate2_batch_host_ex(h: gkq_handle_t, cfg: *const gkq_config, ov: *const gkq_overrides,
+        functor2_id: c_int, yrange_id: c_int, n: i64, x0: *const f64, x1: *const f64, range_stride: i64,
+        fparams: *const f64, fparam_stride: i64, yparams: *const f64, yparam_stride: i64,
+        pts_offsets: *const i64, pts_xy: *const f64, out_estimate: *mut f64, out_delta: *mut f64,
+        out_nevals: *mut u32, out_status: *mut u32) -> c_int;
     pub fn gkq_qk_batch(h: gkq_handle_t, rule: c_int, functor_id: c_int, n: i64, a: *const c_double,
                         b: *const c_double, range_stride: i64, params: *const c_double,
                         param_stride: i64, out4: *mut c_double, stream: *mut c_void) -> c_int;

@@ -195,8 +195,9 @@ int gkq_integrate2_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor
  * optional (NULL = the value of `cfg` for every integral) and has n entries; the tolerance KIND
  * stays cfg->tol.kind.  max_evals[i] is clamped to cfg->max_evals, which sizes the engine's
  * interval lists.  NaN tolerances are not checked here (the reference panics,
- * single/integrator.rs:71).  1-D entries only.
- * gkq_integrate_batch_ex: device pointers; gkq_integrate_batch_host_ex: host pointers. */
+ * single/integrator.rs:71).  For the 2-D entries max_evals[i] is the TOTAL budget of nest i
+ * (IntegrationConfig2::max_evals, double/common.rs:18).
+ * *_batch_ex: device pointers; *_batch_host_ex: host pointers. */
 typedef struct gkq_overrides {
     const double* abs_tol;
     const double* rel_tol;
@@ -212,6 +213,19 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
                                 int64_t range_stride, const double* params, int64_t param_stride,
                                 const int64_t* pts_offsets, const double* pts, double* out_estimate,
                                 double* out_delta, uint32_t* out_nevals, uint32_t* out_status);
+
+int gkq_integrate2_batch_ex(gkq_handle_t h, const gkq_config* cfg, const gkq_overrides* ov,
+                            int functor2_id, int yrange_id, int64_t n, const double* x0,
+                            const double* x1, int64_t range_stride, const double* fparams,
+                            int64_t fparam_stride, const double* yparams, int64_t yparam_stride,
+                            const int64_t* pts_offsets, const double* pts_xy, double* out_estimate,
+                            double* out_delta, uint32_t* out_nevals, uint32_t* out_status, void* stream);
+int gkq_integrate2_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq_overrides* ov,
+                                 int functor2_id, int yrange_id, int64_t n, const double* x0,
+                                 const double* x1, int64_t range_stride, const double* fparams,
+                                 int64_t fparam_stride, const double* yparams, int64_t yparam_stride,
+                                 const int64_t* pts_offsets, const double* pts_xy, double* out_estimate,
+                                 double* out_delta, uint32_t* out_nevals, uint32_t* out_status);
 
 /* ---- rule level -------------------------------------------------------------------------
  * replaces: single::qk17 / qk25 / qk33 / qk41 / qk49 / qk57 (single/qk/mod.rs:28-73) -> QKResult

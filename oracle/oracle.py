@@ -57,7 +57,7 @@ def lib():
         L.gkqo_integrate2_batch.argtypes = [
             C.c_int, C.c_int, C.c_int, C.c_int64, dp, dp, C.c_int64, dp, C.c_int64, dp, C.c_int64,
             i64p, dp, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_uint64, dp, dp, u32p, u32p,
-            C.c_int, C.c_int]
+            C.c_int, C.c_int, dp, dp, C.POINTER(C.c_uint64)]
         L.gkqo_qk.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, dp, dp]
         L.gkqo_integrate_one.argtypes = [
             C.c_int, C.c_int, C.c_double, C.c_double, dp, dp, C.c_int64, C.c_int, C.c_double,
@@ -185,7 +185,8 @@ def integrate_batch(algo, functor, a, b, params=None, points=None, pts_offsets=N
 
 def integrate2_batch(algo, functor2, yrange, x0, x1, fparams=None, yparams=None, points=None,
                      pts_offsets=None, tol=("abs_or_rel", 1.49e-8, 1.49e-8), max_evals=100000,
-                     nthreads=0, n=None, swap_xy=False):
+                     nthreads=0, n=None, swap_xy=False, abs_tol_each=None, rel_tol_each=None,
+                     max_evals_each=None):
     """points: list of (x, y) pairs shared by the batch, or flat [m,2] array with pts_offsets.
     swap_xy: the DynamicX form -- the algorithms see g(x, y) = f(y, x); ranges and points are given
     in (outer, inner) order, as the reference passes them on after its own swap."""
@@ -225,11 +226,15 @@ def integrate2_batch(algo, functor2, yrange, x0, x1, fparams=None, yparams=None,
     nev = np.empty(n, dtype=np.uint32)
     st = np.empty(n, dtype=np.uint32)
     k, ta, tr = tol_tuple(tol)
+    ate = None if abs_tol_each is None else np.ascontiguousarray(abs_tol_each, dtype=np.float64)
+    rte = None if rel_tol_each is None else np.ascontiguousarray(rel_tol_each, dtype=np.float64)
+    mee = None if max_evals_each is None else np.ascontiguousarray(max_evals_each, dtype=np.uint64)
     rc = lib().gkqo_integrate2_batch(
         algo, fid, yid, n, _dp(aa), _dp(bb), rs, _dp(fp), fs, _dp(yp), ys, po_p, _dp(pts), npts,
         k, ta, tr, max_evals, _dp(est), _dp(dlt),
         nev.ctypes.data_as(C.POINTER(C.c_uint32)), st.ctypes.data_as(C.POINTER(C.c_uint32)), nthreads,
-        1 if swap_xy else 0)
+        1 if swap_xy else 0, None if ate is None else _dp(ate), None if rte is None else _dp(rte),
+        None if mee is None else mee.ctypes.data_as(C.POINTER(C.c_uint64)))
     assert rc == 0, rc
     return dict(estimate=est, delta=dlt, nevals=nev, status=st)
 

@@ -160,6 +160,10 @@ struct Batch2Args {
     uint32_t* out_status;
     int nthreads;
     int swap_xy = 0;  // DynamicX: the algorithms see g(x, y) = f(y, x) (double/algorithm/qags.rs:36-37)
+    // per-integral tolerance values / total budget (an Integrator2 configured anew per integral)
+    const double* abs_tol_each = nullptr;
+    const double* rel_tol_each = nullptr;
+    const uint64_t* max_evals_each = nullptr;
 };
 
 // double/algorithm/qags.rs:36-37, qagp.rs:41-42: `let mut g = |x, y| f.apply((y, x));`
@@ -187,6 +191,9 @@ void run_batch2(const Batch2Args& A) {
         Config2 cfg;
         cfg.tol = A.tol;
         cfg.max_evals = A.max_evals;
+        if (A.abs_tol_each) cfg.tol.abs_ = A.abs_tol_each[i];
+        if (A.rel_tol_each) cfg.tol.rel_ = A.rel_tol_each[i];
+        if (A.max_evals_each) cfg.max_evals = A.max_evals_each[i] < A.max_evals ? A.max_evals_each[i] : A.max_evals;
         if (A.pts_offsets) {
             cfg.points_xy = A.pts_xy + 2 * A.pts_offsets[i];
             cfg.npoints = (size_t)(A.pts_offsets[i + 1] - A.pts_offsets[i]);
@@ -352,13 +359,17 @@ int gkqo_integrate2_batch(int algo, int functor2_id, int yrange_id, int64_t n, c
                           const int64_t* pts_offsets, const double* pts_xy, int64_t npts,
                           int tol_kind, double tol_abs, double tol_rel, uint64_t max_evals,
                           double* out_estimate, double* out_delta, uint32_t* out_nevals,
-                          uint32_t* out_status, int nthreads, int swap_xy) {
+                          uint32_t* out_status, int nthreads, int swap_xy, const double* abs_tol_each,
+                          const double* rel_tol_each, const uint64_t* max_evals_each) {
     if (yrange_id < 0 || yrange_id >= YR_COUNT) return -1;
     Batch2Args A{algo,       yrange_id,     n,          x0,         x1,         range_stride,
                  fparams,    fparam_stride, yparams,    yparam_stride, pts_offsets, pts_xy,
                  npts,       Tolerance{tol_kind, tol_abs, tol_rel}, max_evals,
                  out_estimate, out_delta,   out_nevals, out_status, nthreads};
     A.swap_xy = swap_xy;
+    A.abs_tol_each = abs_tol_each;
+    A.rel_tol_each = rel_tol_each;
+    A.max_evals_each = max_evals_each;
     return Dispatch2<0>::go(functor2_id, A);
 }
 

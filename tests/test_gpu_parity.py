@@ -500,6 +500,49 @@ def test_double_dynamic_x(eng, mode, monkeypatch):
     assert r.value.estimate == ref["estimate"][0] and r.value.nevals == ref["nevals"][0]
 
 
+@pytest.mark.parametrize("mode", ["1", "2"], ids=["thread_per_outer", "pool"])
+def test_double_per_integral_tolerance_and_budget(eng, mode, monkeypatch):
+    """Per-nest tolerance values and TOTAL budgets (IntegrationConfig2, double/common.rs:14-32, set anew
+    for every integral of a sweep): bit-exact against the oracle, device and host entry."""
+    import torch
+    from gkquad_b200 import Tolerance
+    from gkquad_b200.workloads import WORKLOADS
+    from gpu_common import compare
+    from oracle import oracle as O
+    monkeypatch.setenv("GKQ_NESTED_MODE", mode)
+    rng = np.random.default_rng(5)
+    W = WORKLOADS["D1"]
+    n = 160
+    p = W.make_params(0, n)
+    off = np.arange(n + 1, dtype=np.int64)
+    pxy = np.ascontiguousarray(p.T)
+    rel = 10.0 ** rng.uniform(-7, -2, n)
+    me = rng.choice([0, 49, 50, 1250, 1300, 5000, 20000, 60000, 100000], n).astype(np.uint64)
+    ref = O.integrate2_batch(ALGO["QAGP"], W.functor, W.yrange, W.a, W.b, fparams=p, yparams=W.yparams, points=pxy,
+                             pts_offsets=off, tol=("rel", 1e-6), max_evals=100000, n=n, rel_tol_each=rel,
+                             max_evals_each=me)
+    assert len(np.unique(ref["status"])) >= 2
+    g = eng.integrate2_batch(W.functor, W.yrange, W.a, W.b, fparams=p, yparams=W.yparams, algo=ALGO["QAGP"],
+                             tol=Tolerance.Relative(1e-6), max_evals=100000, pts_offsets=off, pts_xy=pxy, n=n,
+                             rel_tol_each=rel, max_evals_each=me)
+    compare(g, ref, Tolerance.Relative(1e-6), exact=True, label="D1 host")
+    g = eng.integrate2_batch(W.functor, W.yrange, W.a, W.b, fparams=torch.as_tensor(p, device="cuda:0"),
+                             yparams=W.yparams, algo=ALGO["QAGP"], tol=Tolerance.Relative(1e-6), max_evals=100000,
+                             pts_offsets=torch.as_tensor(off, device="cuda:0"),
+                             pts_xy=torch.as_tensor(pxy, device="cuda:0"), n=n,
+                             rel_tol_each=rel, max_evals_each=me.astype(np.int64))
+    compare(g, ref, Tolerance.Relative(1e-6), exact=True, label="D1 device")
+    # QAGS2 over a rectangle with absolute tolerances
+    n = 64
+    ab = 10.0 ** rng.uniform(-13, -4, n)
+    me = rng.choice([100, 288, 289, 700, 3000, 100000], n).astype(np.uint64)
+    ref = O.integrate2_batch(ALGO["QAGS"], "g4", "const", 0.0, 2.0, yparams=[0.0, 3.0], tol=("abs", 1e-9),
+                             max_evals=100000, n=n, abs_tol_each=ab, max_evals_each=me)
+    g = eng.integrate2_batch("g4", "const", 0.0, 2.0, yparams=[0.0, 3.0], algo=ALGO["QAGS"],
+                             tol=Tolerance.Absolute(1e-9), max_evals=100000, n=n, abs_tol_each=ab, max_evals_each=me)
+    compare(g, ref, Tolerance.Absolute(1e-9), exact=True, label="g4 host")
+
+
 def test_api_mirror_on_gpu(eng):
     """The host-side mirror of gkquad's API (single::integral, Integrator builder, integral2)."""
     from gkquad_b200 import Tolerance, double, single
