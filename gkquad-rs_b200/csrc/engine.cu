@@ -1300,7 +1300,7 @@ int gkq_integrate2_batch_ex(gkq_handle_t h, const gkq_config* cfg, const gkq_ove
     if (functor2_id < 0 || functor2_id >= F2_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown 2-D functor id");
     if (yrange_id < 0 || yrange_id >= YR_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown y-range functor id");
     if (n < 0 || n > 0xffffffffll) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "n out of range");
-    if (cfg->algo < 0 || cfg->algo > 2) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown algorithm");
+    if (cfg->algo < 0 || cfg->algo > 3) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown algorithm");
     if (range_stride != 0 && range_stride != 1) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "range_stride must be 0 or 1");
     if (cfg->max_evals > 0x7fffffffull) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "max_evals must fit in 31 bits");
     if (cfg->npoints < 0 || (cfg->npoints > 0 && !cfg->points)) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "points is NULL");
@@ -1353,6 +1353,30 @@ int gkq_integrate2_batch_ex(gkq_handle_t h, const gkq_config* cfg, const gkq_ove
     GKQ_CUDA(h, cudaMemsetAsync(S.ctl, 0, sizeof(Control), st));
     h->stats.batches += 1;
     h->stats.integrals += (uint64_t)n;
+
+    if (cfg->algo == GKQ_ALGO_QAG) {
+        // QAG2 (deprecated in the reference, double/algorithm/qag.rs): never looks at points; one
+        // thread per outer integral (k_nested<.., 2>): available, not tuned
+        const Launch2D& L = h->l2[functor2_id];
+        const unsigned long long outer_need = 2ull + (cfg->max_evals / 17ull) / 50ull;
+        const unsigned long long inner_need = 2ull + cfg->max_evals / 50ull;
+        if (inner_need > (1ull << 24)) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
+        const int cap_total = (int)(outer_need + inner_need);
+        int grid = persistent_grid(h, 1, cap_total, 2 * 2 + 110, BLOCK);
+        if (grid < 1) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
+        const long long nblocks = (n + BLOCK - 1) / BLOCK;
+        if ((long long)grid > nblocks) grid = (int)nblocks;
+        Batch2D Q = P;
+        SlabGeom g;
+        if ((rc = ensure_slab(h, (unsigned long long)grid * BLOCK, cap_total, 2 * 2 + 110, g))) return rc;
+        Q.slab = g;
+        Q.cap_outer = (int)outer_need;
+        Q.cap_inner = (int)inner_need;
+        prof_begin(h, "k_nested<QAG2>", st);
+        L.run_qag(Q, grid, st);
+        prof_end(h, st);
+        return launch_check(h, "k_nested<QAG2>");
+    }
 
     // which algorithm(s) run, and over which integrals
     bool run_s = false, run_p = false, split = false;

@@ -204,6 +204,108 @@ __device__ __noinline__ Res seq_qags(G& g, double a, double b, const Tol& tol,
     return r;
 }
 
+// Sequential QAG for one thread (deprecated in the reference): single/algorithm/qag.rs:65-248.
+template <int MODE, int U, class G>
+__device__ __noinline__ Res seq_qag(G& g, double a, double b, const Tol& tol, unsigned long long max_evals,
+                                    unsigned long long& ws_cap, const Slab& S) {
+    Res r;
+    r.est = 0.;
+    r.dlt = F64_MAX;
+    r.nev = 0;
+    r.st = ST_INSUFFICIENT_ITERATION;
+    r.rsv_kind = RSV_NONE;
+    r.rsv_n = 0;
+    if (max_evals < 17) return r;  // qag.rs:76-78
+    QK q;
+    uint32_t nevals = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {  // initial_integral, qag.rs:185-234
+        if (pass == 0) {
+            nevals += 17;
+            q = rule_any<MODE, 8, U>(g, a, b);
+        } else {
+            nevals += 25;
+            q = rule_any<MODE, 12, U>(g, a, b);
+        }
+        r.est = q.estimate;
+        r.dlt = q.delta;
+        r.nev = nevals;
+        if (q.estimate != q.estimate) {
+            r.st = ST_NAN;
+            return r;
+        }
+        const double tolerance = tol.to_abs(fabs(q.estimate));
+        if ((q.delta <= tolerance && q.delta != q.asc) || q.delta == 0.0) {
+            r.st = ST_NONE;
+            return r;
+        }
+        const double round_off = 50. * F64_EPSILON * q.absvalue;  // :217
+        if (q.delta <= round_off && q.delta > tolerance) {
+            r.st = ST_ROUNDOFF_ERROR;
+            return r;
+        }
+        if (max_evals < (unsigned long long)(42 + pass * 25)) {
+            r.st = ST_INSUFFICIENT_ITERATION;
+            return r;
+        }
+        if (pass == 0 && q.delta > tolerance * 1024.) break;
+    }
+    double area = q.estimate, deltasum = q.delta;
+    const unsigned long long max_iters = (max_evals - nevals) / 50ull;
+    Lane s;
+    lane_reset_common(s);
+    ws_cap = reserve_cap(ws_cap, max_iters + 1ull);  // :97-98
+    s.limit = (int)ws_cap;
+    ws_push(S, s, a, b, q.estimate, q.delta, 0);
+    int ro1 = 0, ro2 = 0;
+    uint32_t error = ST_NONE;
+#pragma unroll 1
+    for (unsigned long long it = 1; it <= max_iters; ++it) {
+        const int wi = s.wi;
+        const double ia = S.A(wi), ib = S.B(wi), ie = S.E(wi), id = S.D(wi);
+        const int lv = S.LV(wi) + 1;
+        const double center = (ia + ib) * 0.5;
+        QK q1, q2;
+        rule_pair_any<MODE, U>(g, ia, center, ib, q1, q2);
+        nevals += 50;
+        if (q1.estimate != q1.estimate || q2.estimate != q2.estimate) {  // :122-125
+            error = ST_NAN;
+            break;
+        }
+        const double area12 = q1.estimate + q2.estimate;
+        const double delta12 = q1.delta + q2.delta;
+        deltasum += delta12 - id;
+        area += area12 - ie;
+        if (q1.asc != q1.delta && q2.asc != q2.delta) {  // :135-142
+            if (fabs(ie - area12) <= 1e-5 * fabs(area12) && delta12 >= 0.99 * id)
+                ro1 += 1;
+            else
+                ro2 += 1;
+        }
+        const double tolerance = tol.to_abs(fabs(area));
+        if (deltasum > tolerance) {  // :147-162
+            if (ro1 >= 6 || ro2 >= 20)
+                error = ST_ROUNDOFF_ERROR;
+            else if (subrange_too_small(ia, center, ib))
+                error = ST_SUBRANGE_TOO_SMALL;
+            if (error != ST_NONE) {
+                r.est = ws_sum_results(S, s) - ie + q1.estimate + q2.estimate;
+                r.dlt = deltasum;
+                r.nev = nevals;
+                r.st = error;
+                return r;
+            }
+        }
+        ws_update(S, s, ia, center, q1.estimate, q1.delta, center, ib, q2.estimate, q2.delta, lv);
+        if (deltasum <= tolerance) break;  // :170-172
+    }
+    r.est = ws_sum_results(S, s);  // :176
+    r.dlt = deltasum;
+    r.nev = nevals;
+    r.st = error;
+    return r;
+}
+
 // Sequential QAGP for one thread: single/algorithm/qagp.rs:68-372.  `pts` are the user
 // break points (read through `PT(k)`), the range is already transformed.
 template <int MODE, int U, class G, class PointAt>
@@ -402,7 +504,8 @@ struct InnerF {
 
 // The outer integrand of double/algorithm/qags.rs:66-87 / qagp.rs:108-131 with the infinite
 // range wrapper of the outer algorithm folded in (single/util.rs:74-103).
-template <class F2T, bool QAGP>
+// ALG: 0 = QAGS2, 1 = QAGP2, 2 = QAG2 (the inner algorithm; `bool QAGP` arguments convert)
+template <class F2T, int ALG>
 struct OuterIntegrand {
     F2T f;
     YRange yr;
@@ -433,12 +536,13 @@ struct OuterIntegrand {
         g.f.x = x;
         g.f.swap = swap_xy;
         g.transform = ytr;
-        if (QAGP) {
+        if (ALG == 1) {
             const double* p = pts_xy;
             auto user_pt = [p](int k) { return p[2 * k + 1]; };  // every y of the 2-D points
             return seq_qagp<RM_PURE, NESTED_UNROLL>(g, y0, y1, ytr, user_pt, npts, tol,
                                                                  budget, cap, Sin);
         }
+        if (ALG == 2) return seq_qag<RM_PURE, NESTED_UNROLL>(g, y0, y1, tol, budget, cap, Sin);
         return seq_qags<RM_PURE, NESTED_UNROLL>(g, y0, y1, tol, budget, cap, Sin);
     }
     // config1.max_evals = if error.is_some() { 0 } else { config.max_evals - nevals }
@@ -468,8 +572,9 @@ struct OuterIntegrand {
     }
 };
 
-template <class F2T, bool QAGP, int NPARAMS>
+template <class F2T, int ALG, int NPARAMS>
 __global__ void __launch_bounds__(BLOCK) k_nested(const Batch2D P) {
+    constexpr bool QAGP = ALG == 1;
     const unsigned long long t = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x;
     // slab regions of this thread: [outer lists | inner lists]
     Slab Sout, Sin;
@@ -497,7 +602,7 @@ __global__ void __launch_bounds__(BLOCK) k_nested(const Batch2D P) {
             my_npts = (int)(P.pts_offsets[i + 1] - o0);
         }
 
-        OuterIntegrand<F2T, QAGP> G;
+        OuterIntegrand<F2T, ALG> G;
 #pragma unroll
         for (int k = 0; k < MAX_PARAMS; ++k)
             G.f.p[k] = (k < NPARAMS)
@@ -542,6 +647,8 @@ __global__ void __launch_bounds__(BLOCK) k_nested(const Batch2D P) {
                 return xtr ? transform_point(x) : x;
             };
             r = seq_qagp<RM_ORDERED, 1>(G, xa, xb, xtr, user_pt, my_npts, my_tol, outer_evals, outer_cap, Sout);
+        } else if (ALG == 2) {
+            r = seq_qag<RM_ORDERED, 1>(G, xa, xb, my_tol, outer_evals, outer_cap, Sout);
         } else {
             r = seq_qags<RM_ORDERED, 1>(G, xa, xb, my_tol, outer_evals, outer_cap, Sout);
         }
@@ -577,6 +684,7 @@ namespace gkq {
 struct Launch2D {
     void (*run[2])(const Batch2D&, int grid, cudaStream_t);  // [0] QAGS2, [1] QAGP2 (thread per outer integral)
     int (*occupancy[2])();
+    void (*run_qag)(const Batch2D&, int grid, cudaStream_t);  // QAG2: k_nested<.., 2> (BLOCK threads)
     void (*run_pool[2])(const Batch2D&, int grid, cudaStream_t);  // k_nested_pool (PB threads per block)
     int (*occupancy_pool[2])();
 };
@@ -594,6 +702,9 @@ GKQ_F2_LIST(GKQ_DECL_F2)
         };                                                                                        \
         L.run[1] = [](const Batch2D& P, int grid, cudaStream_t st) {                              \
             k_nested<F2<ID>, true, NP><<<grid, BLOCK, 0, st>>>(P);                                \
+        };                                                                                        \
+        L.run_qag = [](const Batch2D& P, int grid, cudaStream_t st) {                             \
+            k_nested<F2<ID>, 2, NP><<<grid, BLOCK, 0, st>>>(P);                                   \
         };                                                                                        \
         L.occupancy[0] = []() {                                                                   \
             int nb = 0;                                                                           \

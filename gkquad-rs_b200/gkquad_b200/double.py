@@ -5,7 +5,7 @@ import math
 from dataclasses import dataclass, field
 
 from .common import Tolerance
-from .engine import ALGO_AUTO, ALGO_QAGP, ALGO_QAGS, default_engine
+from .engine import ALGO_AUTO, ALGO_QAG, ALGO_QAGP, ALGO_QAGS, default_engine
 from .single import Range
 
 
@@ -116,6 +116,11 @@ class QAGS2(Algorithm2):
 class QAGP2(Algorithm2):
     """double/algorithm/qagp.rs:13-139"""
     ALGO = ALGO_QAGP
+
+
+class QAG2(Algorithm2):
+    """double/algorithm/qag.rs:9-100 (deprecated in the reference)."""
+    ALGO = ALGO_QAG
 
 
 class AUTO2(Algorithm2):

@@ -35,7 +35,8 @@ typedef struct gkq_handle_s* gkq_handle_t;
 /* replaces: the Algorithm implementors QAGS / QAGP / AUTO
  * (single/algorithm/{qags.rs:19-63, qagp.rs:20-64, auto.rs:7-35}) and, for the 2-D entry
  * points, QAGS2 / QAGP2 / AUTO2 (double/algorithm/{qags.rs,qagp.rs,auto.rs}). */
-/* GKQ_ALGO_QAG: the reference's deprecated QAG (single/algorithm/qag.rs), 1-D entries only. */
+/* GKQ_ALGO_QAG: the reference's deprecated QAG / QAG2 (single/algorithm/qag.rs,
+ * double/algorithm/qag.rs): available through the same entries, not tuned. */
 typedef enum gkq_algo { GKQ_ALGO_AUTO = 0, GKQ_ALGO_QAGS = 1, GKQ_ALGO_QAGP = 2, GKQ_ALGO_QAG = 3 } gkq_algo;
 
 /* replaces: enum Tolerance (common.rs:9-19) and Tolerance::to_abs (common.rs:34-41). */

@@ -1238,11 +1238,43 @@ Result qagp2(F2& f, const Range& xrange, YR& yrange, const Config2& config) {
     return result;
 }
 
+// double/algorithm/qag.rs:46-100 (deprecated QAG2): the QAGS2 nest with QAG inside and outside.
+template <class F2, class YR>
+Result qag2(F2& f, const Range& xrange, YR& yrange, const Config2& config) {
+    Config config1{config.tol, config.max_evals / 17, nullptr, 0};
+    const Config config2 = config1;
+
+    WorkSpace inner_ws;
+    uint32_t error = ST_NONE;
+    uint64_t nevals = 0;
+
+    auto integrand = [&](double x) -> double {
+        auto integrand2 = [&](double y) -> double { return f(x, y); };
+        config1.max_evals = (error != ST_NONE) ? 0 : (uint64_t)(config.max_evals - nevals);  // :63-67
+        Range yr = yrange(x);
+        Result result = qag(integrand2, yr, config1, inner_ws);
+        if (result.status != ST_NONE) {  // :71-76
+            if (error == ST_NONE) error = result.status;
+            nevals += result.nevals;
+            return std::numeric_limits<double>::quiet_NaN();
+        }
+        nevals += result.nevals;
+        return result.estimate;
+    };
+
+    WorkSpace outer_ws;
+    Result result = qag(integrand, xrange, config2, outer_ws);  // :85
+    result.nevals = nevals;
+    if (error != ST_NONE) result.status = error;
+    return result;
+}
+
 // double/algorithm/auto.rs:15-36
 template <class F2, class YR>
 Result integrate2(int algo, F2& f, const Range& xrange, YR& yrange, const Config2& config) {
     if (algo == ALGO_QAGS) return qags2(f, xrange, yrange, config);
     if (algo == ALGO_QAGP) return qagp2(f, xrange, yrange, config);
+    if (algo == ALGO_QAG) return qag2(f, xrange, yrange, config);
     if (config.npoints == 0) return qags2(f, xrange, yrange, config);
     return qagp2(f, xrange, yrange, config);
 }

@@ -543,6 +543,28 @@ def test_double_per_integral_tolerance_and_budget(eng, mode, monkeypatch):
     compare(g, ref, Tolerance.Absolute(1e-9), exact=True, label="g4 host")
 
 
+def test_qag2_batch_bit_exact(eng):
+    """QAG2 (double/algorithm/qag.rs:46-100, deprecated): nests with per-integral budgets, finite and
+    infinite rectangles and a dynamic y-range -- bit-identical to the oracle."""
+    from gkquad_b200 import Tolerance
+    from gpu_common import compare
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    n = 96
+    me = rng.choice([10, 288, 289, 700, 3000, 20000, 100000], n).astype(np.uint64)
+    cases = [("g4", "const", 0.0, 2.0, [0.0, 3.0], ("abs", 1e-10)),
+             ("g4", "const", 0.0, math.inf, [0.0, math.inf], ("abs", 1e-8)),
+             ("rsqrt3", "const", -1.0, 1.5, [-2.0, 1.0], ("rel", 1e-9)),
+             ("g3", "circle", -0.5, 0.5, [0.25], ("abs", 1e-9))]
+    for f, yr, x0, x1, yq, tol in cases:
+        ref = O.integrate2_batch(ALGO["QAG"], f, yr, x0, x1, yparams=yq, tol=tol, max_evals=100000, n=n,
+                                 max_evals_each=me)
+        g = eng.integrate2_batch(f, yr, x0, x1, yparams=yq, algo=ALGO["QAG"], tol=_tol(tol), max_evals=100000, n=n,
+                                 max_evals_each=me)
+        compare(g, ref, _tol(tol), exact=True, label=f"QAG2 {f}")
+    assert len(np.unique(ref["status"])) >= 2
+
+
 def test_api_mirror_on_gpu(eng):
     """The host-side mirror of gkquad's API (single::integral, Integrator builder, integral2)."""
     from gkquad_b200 import Tolerance, double, single
