@@ -67,6 +67,24 @@ int main() {
             CHECK(std::fabs(r.estimate[i] - truth) <= 1e-10 * std::fabs(truth));
         }
     }
+    {  // the deprecated algorithms: tests/algorithms_double.rs:44-54 (qag_g1) and a QAG run
+        double_::IntegrationConfig2 c2;
+        c2.tolerance = Tolerance::Relative(1e-10);
+        auto r = double_::QAG2().integrate(double_::DeviceIntegrand2{"g1", {}}, double_::Rectangle(0., 1., 0., 1.), c2)[0].unwrap();
+        CHECK(std::fabs(r.estimate - 0.75) <= 1e-15 && r.nevals == 289);
+        auto it = single::Integrator(single::DeviceIntegrand{"lorentz_p", {{1.0}}});
+        it.algorithm(single::QAG()).tolerance(Tolerance::Absolute(1e-10));
+        auto q = it.run({-1.0, 1.0})[0].unwrap();
+        CHECK(std::fabs(q.estimate - PI / 2) <= 1e-10);
+    }
+    {  // DynamicX (double/range.rs:38-75): x in [1, 2] inside, y in [0, 1] outside, f(x, y) = exp(y / x)
+        double_::IntegrationConfig2 c2;
+        c2.tolerance = Tolerance::Relative(1e-9);
+        auto r = double_::QAGS2().integrate(double_::DeviceIntegrand2{"g2", {}},
+                                            double_::DynamicX("const", 0.0, 1.0, {1.0, 2.0}), c2)[0].unwrap();
+        const double truth = 1.4483309393877208;  // scipy.integrate.dblquad, 1e-13
+        CHECK(std::fabs(r.estimate - truth) <= 1e-8 * truth);
+    }
     std::printf("all reference bench assertions hold through the C++ mirror\n");
     return 0;
 }

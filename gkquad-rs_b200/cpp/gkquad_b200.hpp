@@ -195,6 +195,7 @@ private:
 struct QAGS : Algorithm { explicit QAGS(std::size_t ws_cap = 0) : Algorithm(GKQ_ALGO_QAGS, ws_cap) {} };  // qags.rs
 struct QAGP : Algorithm { explicit QAGP(std::size_t ws_cap = 0) : Algorithm(GKQ_ALGO_QAGP, ws_cap) {} };  // qagp.rs
 struct AUTO : Algorithm { AUTO() : Algorithm(GKQ_ALGO_AUTO) {} };                                         // auto.rs
+struct QAG : Algorithm { explicit QAG(std::size_t ws_cap = 0) : Algorithm(GKQ_ALGO_QAG, ws_cap) {} };     // qag.rs (deprecated)
 
 // single/integrator.rs:31-106
 class Integrator {
@@ -238,7 +239,15 @@ struct DynamicY {
     Range xrange;
     std::string yrange;            // registry name: "const" | "zero_to_x" | "circle"
     std::vector<double> yparams;   // its parameters
+    bool swap_xy = false;          // built by DynamicX(): the roles of x and y are exchanged
 };
+// double/range.rs:38-75: y in [y1, y2], x in xrange(y).  The algorithms swap the integrand's
+// arguments and the point coordinates (double/algorithm/qags.rs:29-44, qagp.rs:34-53).
+inline DynamicY DynamicX(const std::string& xrange, double y1, double y2, std::vector<double> xparams = {}) {
+    DynamicY r{Range(y1, y2), xrange, std::move(xparams)};
+    r.swap_xy = true;
+    return r;
+}
 inline DynamicY Rectangle(double x1, double x2, double y1, double y2) {
     if (!(std::isfinite(x1) && std::isfinite(x2) && std::isfinite(y1) && std::isfinite(y2)))
         throw std::invalid_argument("Infinite interval in 2-dimension is not already supported.");  // range.rs:20-22
@@ -273,11 +282,12 @@ public:
         std::vector<double> flat, pts;
         for (const auto& row : f.params) flat.insert(flat.end(), row.begin(), row.end());
         for (const auto& p : cfg.points) {
-            pts.push_back(p.first);
-            pts.push_back(p.second);
+            pts.push_back(range.swap_xy ? p.second : p.first);  // qagp.rs:49
+            pts.push_back(range.swap_xy ? p.first : p.second);
         }
         gkq_config c;
         gkq_config_default(2, &c);
+        c.flags = range.swap_xy ? GKQ_FLAG_SWAP_XY : 0;
         c.algo = algo_;
         c.tol = cfg.tolerance.raw;
         c.max_evals = cfg.max_evals;
@@ -302,6 +312,7 @@ private:
 struct QAGS2 : Algorithm2 { QAGS2() : Algorithm2(GKQ_ALGO_QAGS) {} };
 struct QAGP2 : Algorithm2 { QAGP2() : Algorithm2(GKQ_ALGO_QAGP) {} };
 struct AUTO2 : Algorithm2 { AUTO2() : Algorithm2(GKQ_ALGO_AUTO) {} };
+struct QAG2 : Algorithm2 { QAG2() : Algorithm2(GKQ_ALGO_QAG) {} };  // double/algorithm/qag.rs (deprecated)
 
 // double/integral.rs:9-16
 inline BatchResult integral2(const DeviceIntegrand2& f, const DynamicY& r) { return QAGS2().integrate(f, r, IntegrationConfig2()); }

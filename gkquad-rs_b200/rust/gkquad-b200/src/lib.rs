@@ -150,3 +150,4 @@ macro_rules! algorithm {
 algorithm!(QagsB200, ffi::GKQ_ALGO_QAGS, "replaces gkquad::single::algorithm::QAGS (qags.rs:19-63)");
 algorithm!(QagpB200, ffi::GKQ_ALGO_QAGP, "replaces gkquad::single::algorithm::QAGP (qagp.rs:20-64)");
 algorithm!(AutoB200, ffi::GKQ_ALGO_AUTO, "replaces gkquad::single::algorithm::AUTO (auto.rs:7-35)");
+algorithm!(QagB200, ffi::GKQ_ALGO_QAG, "replaces the deprecated gkquad::single::algorithm::QAG (qag.rs:16-60)");
