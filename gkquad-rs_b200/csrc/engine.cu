@@ -93,6 +93,9 @@ struct gkq_handle_s {
         bool ctl_pending = false;
         size_t cap_n = 0;
         double* abs0 = nullptr;
+        double* park_est = nullptr;   // result0 of loop entrants, parked between the bulk kernels
+        double* park_dlt = nullptr;
+        unsigned int* park_nev = nullptr;
         unsigned int *list25 = nullptr, *listS = nullptr, *listP = nullptr;
         unsigned int* listLoop[2] = {nullptr, nullptr};
         cudaStream_t side = nullptr;  // chain 1 of the QAGS bulk
@@ -235,6 +238,9 @@ int ensure_batch_scratch(gkq_handle_t h, size_t n) {
     int rc;
     size_t have;
     have = S.cap_n; if ((rc = grow(h, S.abs0, have, w))) return rc;
+    have = S.cap_n; if ((rc = grow(h, S.park_est, have, w))) return rc;
+    have = S.cap_n; if ((rc = grow(h, S.park_dlt, have, w))) return rc;
+    have = S.cap_n; if ((rc = grow(h, S.park_nev, have, w))) return rc;
     have = S.cap_n; if ((rc = grow(h, S.list25, have, w))) return rc;
     have = S.cap_n; if ((rc = grow(h, S.listS, have, w))) return rc;
     have = S.cap_n; if ((rc = grow(h, S.listP, have, w))) return rc;
@@ -563,6 +569,9 @@ int gkq_destroy(gkq_handle_t h) {
         cudaFree(s.ctl);
         cudaFreeHost(s.ctl_host);
         cudaFree(s.abs0);
+        cudaFree(s.park_est);
+        cudaFree(s.park_dlt);
+        cudaFree(s.park_nev);
         cudaFree(s.list25);
         cudaFree(s.listS);
         cudaFree(s.listP);
@@ -902,6 +911,9 @@ static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functo
     P.out.status = out_status;
     P.ctl = ctl_zeroed ? ctl_zeroed : S.ctl;
     P.abs0 = S.abs0;
+    P.park_est = S.park_est;
+    P.park_dlt = S.park_dlt;
+    P.park_nev = S.park_nev;
     P.list25 = S.list25;
     P.listLoop[0] = S.listLoop[0];
     P.listLoop[1] = S.listLoop[1];

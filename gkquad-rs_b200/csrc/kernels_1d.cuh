@@ -130,6 +130,11 @@ struct Batch1D {
     // scratch owned by the handle
     Control* ctl;
     double* abs0;               // [n] absvalue of the initial rule (qags.rs:315-376 returns it)
+    // [n] result0 of the loop entrants, parked in handle-owned scratch: the caller's output arrays
+    // are written exactly once per integral (they may live in a peer GPU's memory)
+    double* park_est;
+    double* park_dlt;
+    unsigned int* park_nev;
     unsigned int* list25;       // [n]
     unsigned int* listLoop[2];  // [n] per chain: integrals entering the main loop
     int chain;                  // which chain this launch serves (k_qags_first)
@@ -274,11 +279,14 @@ __global__ void __launch_bounds__(BLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : 3) k
                 else
                     toLoop = true;  // qags.rs:370-372 (`break`) or end of the 2-pass loop
             }
-            // finished integrals get their final answer; loop entrants park result0 in the
-            // output arrays (estimate, delta, nevals) + abs0 until k_adaptive picks them up
-            if (done || toLoop) {
-                write_result(P.out, i, q.estimate, q.delta, nevals, status);
-                if (toLoop) P.abs0[i] = q.absvalue;
+            // finished integrals get their final answer; loop entrants park result0 in scratch
+            // (estimate, delta, nevals, absvalue) until k_qags_first picks them up
+            if (done) write_result(P.out, i, q.estimate, q.delta, nevals, status);
+            if (toLoop) {
+                P.park_est[i] = q.estimate;
+                P.park_dlt[i] = q.delta;
+                P.park_nev[i] = nevals;
+                P.abs0[i] = q.absvalue;
             }
             }
         }
@@ -315,8 +323,8 @@ __global__ void __launch_bounds__(FBLOCK, GKQ_FIRST_MIN_BLOCKS) k_qags_first(con
             double a, b;
             load_range(P, i, a, b, g.transform);
             load_functor(g.f, P, i, NPARAMS);
-            const double est0 = P.out.estimate[i], delta0 = P.out.delta[i];
-            uint32_t nevals = P.out.nevals[i];
+            const double est0 = P.park_est[i], delta0 = P.park_dlt[i];
+            uint32_t nevals = P.park_nev[i];
             const Tol tol = load_tol(P, i);
             const unsigned long long max_evals = load_max_evals(P, i);
             const unsigned long long max_iters = (max_evals - nevals) / 50;
@@ -376,6 +384,9 @@ __global__ void __launch_bounds__(FBLOCK, GKQ_FIRST_MIN_BLOCKS) k_qags_first(con
                         rec.max_evals = max_evals;
                     }
                 }
+            } else {
+                // zero trips: result0 is the answer (qags.rs:274-276, err_ext still f64::MAX)
+                write_result(P.out, i, 0.0 + est0, delta0, nevals, ST_NONE);
             }
         }
         // warp-aggregated append of the record
