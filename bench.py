@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=1 << 20, help="integrals per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--p2p-gather", action="store_true",
+                    help="N > 1: also time the gather fused into the kernels (result stores go over NVLink into "
+                         "rank 0's HBM through torch's symmetric memory); opt-in because its rendezvous is collective")
     return ap.parse_args()
 
 
@@ -368,7 +371,7 @@ def _main(args, real_stdout):
     # straight into RANK 0's buffer over NVLink (peer mapping from torch's symmetric memory), so the
     # transfer overlaps the math store by store and no collective kernel runs at all.
     p2p_gather = None
-    if world > 1:
+    if world > 1 and args.p2p_gather:
         try:
             import torch.distributed._symmetric_memory as symm
             sbuf = symm.empty((NSETS, world, 3 * n), dtype=torch.float64, device=dev)
