@@ -101,7 +101,7 @@ impl EngineB200 {
         let flat: Vec<f64> = f.params.iter().flat_map(|r| r.iter().cloned()).collect();
         let cfg = ffi::gkq_config {
             algo: self.algo,
-            _pad: 0,
+            flags: 0,
             tol: tol_to_ffi(&config.tolerance),
             max_evals: config.max_evals as u64,
             workspace_capacity: 0,
