@@ -220,6 +220,33 @@ def test_full_size_properties(eng):
     assert np.array_equal(gs.estimate, g.estimate[perm]) and np.array_equal(gs.nevals, g.nevals[perm])
 
 
+def test_large_batch_16m(eng):
+    """A batch 16x the headline size through both entries (worklists, straggler records, host chunks and
+    slabs all scale with n): IEEE-exact integrand, so the halves of the batch -- same parameters -- must
+    be bit-identical to each other and to the oracle on a 1M slice."""
+    import torch
+    from gkquad_b200 import Tolerance
+    from gpu_common import compare
+    from oracle import oracle as O
+    m = 1 << 20
+    n = 16 * m
+    rng = np.random.default_rng(1)
+    base = 10.0 ** rng.uniform(0, 3.5, m)
+    p = np.ascontiguousarray(np.tile(base, 16)[None, :])
+    tol = Tolerance.Relative(1e-10)
+    ref = O.integrate_batch(ALGO["QAGS"], "lorentz_p", -1.0, 1.0, p[:, :m], tol=("rel", 1e-10), max_evals=2000, n=m)
+    g = eng.integrate_batch("lorentz_p", -1.0, 1.0, torch.as_tensor(p, device="cuda:0"), algo=ALGO["QAGS"], tol=tol,
+                            n=n).numpy()
+    for k in range(16):
+        s = slice(k * m, (k + 1) * m)
+        assert np.array_equal(g.estimate[s], ref["estimate"]) and np.array_equal(g.nevals[s], ref["nevals"])
+        assert np.array_equal(g.status[s], ref["status"]) and np.array_equal(g.delta[s], ref["delta"])
+    h = eng.integrate_batch("lorentz_p", -1.0, 1.0, p, algo=ALGO["QAGS"], tol=tol, n=n).numpy()
+    assert np.array_equal(h.estimate, g.estimate) and np.array_equal(h.delta, g.delta)
+    assert np.array_equal(h.nevals, g.nevals) and np.array_equal(h.status, g.status)
+    assert len(np.unique(ref["nevals"])) > 4 and (ref["nevals"] > 67).sum() > 1000  # the adaptive tail was exercised
+
+
 # ---- edge cases (SURVEY.md appendix A) against the oracle ------------------------------------------
 EDGE = [
     dict(f="square", a=0.5, b=0.5, algo="QAGS"),
