@@ -31,7 +31,7 @@ struct FunctorInfo {
 enum F1Id : int {
     F1_SQUARE = 0, F1_RECIP_P, F1_LORENTZ_P, F1_EXPCOS_P, F1_GAUSS_P, F1_ABSPOW_P, F1_LOGABS_P,
     F1_F1, F1_F2, F1_F3, F1_F4, F1_F5, F1_F6, F1_EXP_P, F1_SQRT_SHIFT_P, F1_INV_ABS_SHIFT_P,
-    F1_COS_P, F1_SIN_P, F1_COUNT
+    F1_COS_P, F1_SIN_P, F1_SEMICIRCLE_P, F1_SINPOW_P, F1_COUNT
 };
 
 // HEAVY = body calls transcendental libdevice routines: the rule loop is then only partly
@@ -82,6 +82,11 @@ GKQ_F1(F1_SQRT_SHIFT_P, false, return sqrt(x - p[0]);)
 GKQ_F1(F1_INV_ABS_SHIFT_P, false, return 1.0 / fabs(x - p[0]);)
 GKQ_F1P(F1_COS_P, true, return m.cos(p[0] * x);)
 GKQ_F1P(F1_SIN_P, true, return m.sin(p[0] * x);)
+GKQ_F1(F1_SEMICIRCLE_P, false, return sqrt(p[0] - x * x);)                  // examples/sphere.rs:11 (p0 = 1)
+// examples/wallis_integral.rs:13: (x * PI).sin().powi(m), m = p0; powi = compiler-rt __powidf2
+GKQ_F1(F1_SINPOW_P, true, double s = m.sin(x * 3.141592653589793); int n = (int)p[0];
+       double r = 1.0; for (int k = n < 0 ? -n : n;;) { if (k & 1) r *= s; k >>= 1; if (k == 0) break; s *= s; }
+       return n < 0 ? 1.0 / r : r;)
 #undef GKQ_F1
 #undef GKQ_F1P
 #undef GKQ_F1_IMPL
@@ -89,7 +94,7 @@ GKQ_F1P(F1_SIN_P, true, return m.sin(p[0] * x);)
 // ---- 2-D ------------------------------------------------------------------------------
 enum F2Id : int {
     F2_XY = 0, F2_RECIP_XY_P, F2_RSQRT3, F2_G1, F2_G2, F2_G3, F2_G4, F2_GP1, F2_GP2, F2_GP3,
-    F2_D1_P, F2_COUNT
+    F2_D1_P, F2_HEMISPHERE_P, F2_COUNT
 };
 template <int ID> struct F2;
 #define GKQ_F2(ID, HEAVY_, BODY)                                                      \
@@ -118,6 +123,7 @@ GKQ_F2(F2_GP1, false, return 1.0 / sqrt(fabs(x) + fabs(y));)              // fun
 GKQ_F2(F2_GP2, false, return x / (x * x + y * y);)                        // functions.rs:58-60
 GKQ_F2(F2_GP3, false, return 0.5 / sqrt(x * x + y * y);)                  // functions.rs:62-64
 GKQ_F2(F2_D1_P, false, return 1.0 / sqrt(fabs(x - p[0]) + fabs(y - p[1]));)  // D1
+GKQ_F2(F2_HEMISPHERE_P, false, return sqrt(p[0] - x * x - y * y);)        // examples/sphere.rs:23 (p0 = 1)
 #undef GKQ_F2
 
 // ---- y-range functors: run-time switch (evaluated once per inner integral) -------------
@@ -163,7 +169,9 @@ struct YRange {
     X(F1_SQRT_SHIFT_P, "sqrt_shift_p", 1, 2.0)       \
     X(F1_INV_ABS_SHIFT_P, "inv_abs_shift_p", 1, 2.0) \
     X(F1_COS_P, "cos_p", 1, 28.0)            \
-    X(F1_SIN_P, "sin_p", 1, 28.0)
+    X(F1_SIN_P, "sin_p", 1, 28.0)            \
+    X(F1_SEMICIRCLE_P, "semicircle_p", 1, 3.0)       \
+    X(F1_SINPOW_P, "sinpow_p", 1, 34.0)
 
 #define GKQ_F2_LIST(X)                       \
     X(F2_XY, "xy", 0, 1.0)                   \
@@ -176,7 +184,8 @@ struct YRange {
     X(F2_GP1, "gp1", 0, 3.0)                 \
     X(F2_GP2, "gp2", 0, 4.0)                 \
     X(F2_GP3, "gp3", 0, 5.0)                 \
-    X(F2_D1_P, "d1_p", 2, 5.0)
+    X(F2_D1_P, "d1_p", 2, 5.0)               \
+    X(F2_HEMISPHERE_P, "hemisphere_p", 1, 5.0)
 
 #define GKQ_YR_LIST(X)                       \
     X(YR_CONST, "const", 2, 0.0)             \

@@ -21,5 +21,7 @@ namespace gkq {
 #define GKQ_PICK_F1_INV_ABS_SHIFT_P(ID, NAME, NP, FL)
 #define GKQ_PICK_F1_COS_P(ID, NAME, NP, FL)
 #define GKQ_PICK_F1_SIN_P(ID, NAME, NP, FL)
+#define GKQ_PICK_F1_SEMICIRCLE_P(ID, NAME, NP, FL) GKQ_INSTANTIATE_F1(ID, NAME, NP, FL)
+#define GKQ_PICK_F1_SINPOW_P(ID, NAME, NP, FL) GKQ_INSTANTIATE_F1(ID, NAME, NP, FL)
 GKQ_F1_LIST(GKQ_PICK)
 }  // namespace gkq

@@ -13,5 +13,6 @@ namespace gkq {
 #define GKQ_PICK_F2_GP2(ID, NAME, NP, FL)
 #define GKQ_PICK_F2_GP3(ID, NAME, NP, FL)
 #define GKQ_PICK_F2_D1_P(ID, NAME, NP, FL)
+#define GKQ_PICK_F2_HEMISPHERE_P(ID, NAME, NP, FL) GKQ_INSTANTIATE_F2(ID, NAME, NP, FL)
 GKQ_F2_LIST(GKQ_PICK)
 }  // namespace gkq

@@ -39,7 +39,9 @@ enum F1Id : int {
     F1_INV_ABS_SHIFT_P = 15,  // 1/|x-p0|: +inf at a node  (appendix A, inf is not NaN)
     F1_COS_P = 16,      // cos(p0*x)                   budget-exhaustion case (section 0.4)
     F1_SIN_P = 17,      // sin(p0*x)
-    F1_COUNT = 18,
+    F1_SEMICIRCLE_P = 18,   // sqrt(p0 - x*x)           examples/sphere.rs:11
+    F1_SINPOW_P = 19,   // sin(pi x)^p0 (powi)         examples/wallis_integral.rs:13
+    F1_COUNT = 20,
 };
 
 static const FunctorInfo F1_TABLE[F1_COUNT] = {
@@ -49,7 +51,7 @@ static const FunctorInfo F1_TABLE[F1_COUNT] = {
     {F1_F3, "f3", 0},           {F1_F4, "f4", 0},             {F1_F5, "f5", 0},
     {F1_F6, "f6", 0},           {F1_EXP_P, "exp_p", 1},       {F1_SQRT_SHIFT_P, "sqrt_shift_p", 1},
     {F1_INV_ABS_SHIFT_P, "inv_abs_shift_p", 1},               {F1_COS_P, "cos_p", 1},
-    {F1_SIN_P, "sin_p", 1},
+    {F1_SIN_P, "sin_p", 1},     {F1_SEMICIRCLE_P, "semicircle_p", 1}, {F1_SINPOW_P, "sinpow_p", 1},
 };
 
 template <int ID>
@@ -78,6 +80,10 @@ GKQO_F1(F1_SQRT_SHIFT_P, return std::sqrt(x - p[0]);)
 GKQO_F1(F1_INV_ABS_SHIFT_P, return 1.0 / std::fabs(x - p[0]);)
 GKQO_F1(F1_COS_P, return std::cos(p[0] * x);)
 GKQO_F1(F1_SIN_P, return std::sin(p[0] * x);)
+GKQO_F1(F1_SEMICIRCLE_P, return std::sqrt(p[0] - x * x);)
+GKQO_F1(F1_SINPOW_P, double s = std::sin(x * 3.141592653589793); int n = (int)p[0];
+        double r = 1.0; for (int k = n < 0 ? -n : n;;) { if (k & 1) r *= s; k >>= 1; if (k == 0) break; s *= s; }
+        return n < 0 ? 1.0 / r : r;)
 #undef GKQO_F1
 
 // ---- 2-D ----------------------------------------------------------------------------
@@ -93,14 +99,15 @@ enum F2Id : int {
     F2_GP2 = 8,         // x/(x*x+y*y)                 functions.rs:58-60
     F2_GP3 = 9,         // 0.5/sqrt(x*x+y*y)           functions.rs:62-64
     F2_D1_P = 10,       // 1/sqrt(|x-p0|+|y-p1|)       D1 (section 8d cfg-5)
-    F2_COUNT = 11,
+    F2_HEMISPHERE_P = 11,   // sqrt(p0 - x*x - y*y)    examples/sphere.rs:23
+    F2_COUNT = 12,
 };
 
 static const FunctorInfo F2_TABLE[F2_COUNT] = {
     {F2_XY, "xy", 0},   {F2_RECIP_XY_P, "recip_xy_p", 1}, {F2_RSQRT3, "rsqrt3", 0},
     {F2_G1, "g1", 0},   {F2_G2, "g2", 0},                 {F2_G3, "g3", 0},
     {F2_G4, "g4", 0},   {F2_GP1, "gp1", 0},               {F2_GP2, "gp2", 0},
-    {F2_GP3, "gp3", 0}, {F2_D1_P, "d1_p", 2},
+    {F2_GP3, "gp3", 0}, {F2_D1_P, "d1_p", 2},             {F2_HEMISPHERE_P, "hemisphere_p", 1},
 };
 
 template <int ID>
@@ -123,6 +130,7 @@ GKQO_F2(F2_GP1, return 1.0 / std::sqrt(std::fabs(x) + std::fabs(y));)
 GKQO_F2(F2_GP2, return x / (x * x + y * y);)
 GKQO_F2(F2_GP3, return 0.5 / std::sqrt(x * x + y * y);)
 GKQO_F2(F2_D1_P, return 1.0 / std::sqrt(std::fabs(x - p[0]) + std::fabs(y - p[1]));)
+GKQO_F2(F2_HEMISPHERE_P, return std::sqrt(p[0] - x * x - y * y);)
 #undef GKQO_F2
 
 // ---- y-range functors (double/range.rs:77-112: DynamicY's closure) -------------------

@@ -592,6 +592,21 @@ def test_qag2_batch_bit_exact(eng):
     assert len(np.unique(ref["status"])) >= 2
 
 
+def test_reference_examples(eng):
+    """examples/sphere.rs and examples/wallis_integral.rs restated on the host mirror (examples/*.py)."""
+    import importlib.util
+    from pathlib import Path
+    ROOT = Path(__file__).resolve().parent.parent
+    mods = {}
+    for name in ("sphere", "wallis_integral"):
+        spec = importlib.util.spec_from_file_location(name, ROOT / "examples" / f"{name}.py")
+        mods[name] = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mods[name])
+    v1, v2, v3 = mods["sphere"].main()
+    assert v1 == 2.0 and abs(v2 - math.pi) <= 1.49e-8 * math.pi * 2 and abs(v3 - 4.0 * math.pi / 3.0) <= 1e-6
+    assert abs(mods["wallis_integral"].main(2000) - 36722.362174233774391) < 1.0
+
+
 def test_api_mirror_on_gpu(eng):
     """The host-side mirror of gkquad's API (single::integral, Integrator builder, integral2)."""
     from gkquad_b200 import Tolerance, double, single
