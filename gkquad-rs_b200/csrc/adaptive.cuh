@@ -38,15 +38,22 @@ struct Slab {
     int* w;
     unsigned long long stride;
     int cap;
-    GKQ_DEV double& A(int k) const { return d[(unsigned long long)k * stride]; }
-    GKQ_DEV double& B(int k) const { return d[(unsigned long long)(cap + k) * stride]; }
-    GKQ_DEV double& E(int k) const { return d[(unsigned long long)(2 * cap + k) * stride]; }
-    GKQ_DEV double& D(int k) const { return d[(unsigned long long)(3 * cap + k) * stride]; }
-    GKQ_DEV double& EPS(int k) const { return d[(unsigned long long)(4 * cap + k) * stride]; }
-    GKQ_DEV double& R3(int k) const { return d[(unsigned long long)(4 * cap + 52 + k) * stride]; }
-    GKQ_DEV double& PTS(int k) const { return d[(unsigned long long)(4 * cap + 55 + k) * stride]; }
-    GKQ_DEV int& LV(int k) const { return w[(unsigned long long)k * stride]; }
-    GKQ_DEV int& ORD(int k) const { return w[(unsigned long long)(cap + k) * stride]; }
+    // -DGKQ_BOUNDS_CHECK: a debug build that traps on any list / table index outside its slot
+    // range (compute-sanitizer is not available on every pool); run the GPU tests against it.
+#ifdef GKQ_BOUNDS_CHECK
+    GKQ_DEV void chk(int k, int n) const { if (k < 0 || k >= n) __trap(); }
+#else
+    GKQ_DEV void chk(int, int) const {}
+#endif
+    GKQ_DEV double& A(int k) const { chk(k, cap); return d[(unsigned long long)k * stride]; }
+    GKQ_DEV double& B(int k) const { chk(k, cap); return d[(unsigned long long)(cap + k) * stride]; }
+    GKQ_DEV double& E(int k) const { chk(k, cap); return d[(unsigned long long)(2 * cap + k) * stride]; }
+    GKQ_DEV double& D(int k) const { chk(k, cap); return d[(unsigned long long)(3 * cap + k) * stride]; }
+    GKQ_DEV double& EPS(int k) const { chk(k, 52); return d[(unsigned long long)(4 * cap + k) * stride]; }
+    GKQ_DEV double& R3(int k) const { chk(k, 3); return d[(unsigned long long)(4 * cap + 52 + k) * stride]; }
+    GKQ_DEV double& PTS(int k) const { chk(k, 1 << 20); return d[(unsigned long long)(4 * cap + 55 + k) * stride]; }
+    GKQ_DEV int& LV(int k) const { chk(k, cap); return w[(unsigned long long)k * stride]; }
+    GKQ_DEV int& ORD(int k) const { chk(k, cap); return w[(unsigned long long)(cap + k) * stride]; }
 };
 __host__ __device__ inline unsigned long long slab_doubles(int cap, int npts_max) {
     return 4ull * cap + 55ull + (unsigned long long)npts_max;
