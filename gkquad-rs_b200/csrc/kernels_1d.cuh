@@ -216,6 +216,9 @@ struct RuleUnroll {
 #ifndef GKQ_INIT17_MIN_BLOCKS
 #define GKQ_INIT17_MIN_BLOCKS 4
 #endif
+#ifndef GKQ_INIT25_MIN_BLOCKS
+#define GKQ_INIT25_MIN_BLOCKS 3
+#endif
 // the persistent kernel: its loop also holds the list / epsilon-table code, so the rule is unrolled
 // less than in the flat kernels (instruction cache; profiles/)
 #ifndef GKQ_ADAPT_UNROLL_LIGHT
@@ -233,7 +236,7 @@ struct InitUnroll {
 // ---- QAGS initial passes -------------------------------------------------------------------
 // PASS 0: N = 8 (qk17) over the whole batch (or `worklist`); PASS 1: N = 12 (qk25) over list25.
 template <class F, int N, int NPARAMS>
-__global__ void __launch_bounds__(BLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : 3) k_qags_init(const Batch1D P) {
+__global__ void __launch_bounds__(BLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : GKQ_INIT25_MIN_BLOCKS) k_qags_init(const Batch1D P) {
     constexpr int PASS = (N == 8) ? 0 : 1;
     long long total;
     if (PASS == 0)
@@ -290,8 +293,10 @@ __global__ void __launch_bounds__(BLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : 3) k
             }
             }
         }
+#ifndef GKQ_EXPERIMENT_NO_APPEND  // (timing experiment only: results of the later passes are wrong)
         if (PASS == 0) list_append(to25, (unsigned int)i, P.list25, &P.ctl->count25);
         list_append(toLoop, (unsigned int)i, P.listLoop[PASS], &P.ctl->chain[PASS].countLoop);
+#endif
     }
 }
 

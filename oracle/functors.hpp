@@ -41,7 +41,11 @@ enum F1Id : int {
     F1_SIN_P = 17,      // sin(p0*x)
     F1_SEMICIRCLE_P = 18,   // sqrt(p0 - x*x)           examples/sphere.rs:11
     F1_SINPOW_P = 19,   // sin(pi x)^p0 (powi)         examples/wallis_integral.rs:13
-    F1_COUNT = 20,
+    // oracle-only probe (not in the product registry): S1's integrand with cos() moved one ulp up,
+    // i.e. "the reference linked against a libm that is 1 ulp off" -- tools/libm_sensitivity.py uses
+    // it to measure how often gkquad's own status / nevals flip under ulp-level libm differences
+    F1_EXPCOS_P_ULP = 20,
+    F1_COUNT = 21,
 };
 
 static const FunctorInfo F1_TABLE[F1_COUNT] = {
@@ -52,6 +56,7 @@ static const FunctorInfo F1_TABLE[F1_COUNT] = {
     {F1_F6, "f6", 0},           {F1_EXP_P, "exp_p", 1},       {F1_SQRT_SHIFT_P, "sqrt_shift_p", 1},
     {F1_INV_ABS_SHIFT_P, "inv_abs_shift_p", 1},               {F1_COS_P, "cos_p", 1},
     {F1_SIN_P, "sin_p", 1},     {F1_SEMICIRCLE_P, "semicircle_p", 1}, {F1_SINPOW_P, "sinpow_p", 1},
+    {F1_EXPCOS_P_ULP, "expcos_p_ulp", 2},
 };
 
 template <int ID>
@@ -84,6 +89,7 @@ GKQO_F1(F1_SEMICIRCLE_P, return std::sqrt(p[0] - x * x);)
 GKQO_F1(F1_SINPOW_P, double s = std::sin(x * 3.141592653589793); int n = (int)p[0];
         double r = 1.0; for (int k = n < 0 ? -n : n;;) { if (k & 1) r *= s; k >>= 1; if (k == 0) break; s *= s; }
         return n < 0 ? 1.0 / r : r;)
+GKQO_F1(F1_EXPCOS_P_ULP, return std::exp(-p[0] * x) * std::nextafter(std::cos(p[1] * x), 2.0);)
 #undef GKQO_F1
 
 // ---- 2-D ----------------------------------------------------------------------------

