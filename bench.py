@@ -36,13 +36,15 @@ UNIT = "integrals/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="S1")
     ap.add_argument("--batch", type=int, default=1 << 20, help="integrals per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pipeline-depth", type=int, default=2,
+                    help="handles / streams the independent batches alternate between (1 = one handle, one stream)")
     ap.add_argument("--p2p-gather", action="store_true",
                     help="N > 1: also time the gather fused into the kernels (result stores go over NVLink into "
                          "rank 0's HBM through torch's symmetric memory); opt-in because its rendezvous is collective")
@@ -88,9 +90,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout=3.0):
+        """Block until nvidia-smi has attached to the driver and delivered its first row."""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, t_begin=None, t_end=None):
+        """Rows that arrived between t_begin and t_end + one sampling period (perf_counter values of
+        the timed region); all rows when the region was too short to catch one."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -99,9 +109,12 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        rows = [r for t, r in self.rows if t_begin is None or t_begin <= t <= t_end + 0.12]
+        if not rows:
+            rows = [r for _, r in self.rows]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -220,7 +233,11 @@ def _main(args, real_stdout):
     assert W.dim == 1, "bench.py times the 1-D hot path (the 2-D configs are parity-test cases)"
     n = args.batch
     algo = {"AUTO": 0, "QAGS": 1, "QAGP": 2}[W.algo]
-    eng = gk.Engine(local_rank)
+    # throughput mode: `depth` handles on `depth` streams, batch k on lane k % depth (BatchPipeline);
+    # lane 0's handle also serves the per-kernel profiling pass and the host entry (e2e)
+    pipe = gk.BatchPipeline(local_rank, depth=args.pipeline_depth)
+    DEPTH = pipe.depth
+    eng = pipe.engines[0]
     from gkquad_b200 import distributed as D
 
     # 2 groups x G independent batches are cycled through, so that a step never finds its inputs or
@@ -252,8 +269,8 @@ def _main(args, real_stdout):
             out = (row[:n], row[n:2 * n], ints[:n], ints[n:])
             p_dev = torch.as_tensor(p_host, device=dev)
             # the call is marshalled once (an Integrator owns integrand + config and is run many times)
-            plan = eng.plan_batch(W.functor, W.a, W.b, p_dev, out=out, **kw)
-            sets.append(dict(p_host=p_host, p_dev=p_dev, kw=kw, plan=plan, out=out, group=gi))
+            plan = pipe.plan_batch(s % DEPTH, W.functor, W.a, W.b, p_dev, out=out, **kw)
+            sets.append(dict(p_host=p_host, p_dev=p_dev, kw=kw, plan=plan, out=out, group=gi, lane=s % DEPTH))
     p_host = sets[0]["p_host"]
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
 
@@ -266,21 +283,24 @@ def _main(args, real_stdout):
         S = sets[s]
         Gp = groups[S["group"]]
         if s % G == 0 and Gp["done"] is not None:  # the gather that last read this group must be over
-            torch.cuda.current_stream().wait_event(Gp["done"])
+            for ls in pipe.streams:
+                ls.wait_event(Gp["done"])
             Gp["done"] = None
-        S["plan"].run()
+        pipe.run(S["plan"], S["lane"])
         if gather and s % G == G - 1:
-            ev = torch.cuda.Event()
-            ev.record()
-            comm.wait_event(ev)
+            for ls in pipe.streams:
+                ev = torch.cuda.Event()
+                ev.record(ls)
+                comm.wait_event(ev)
             with torch.cuda.stream(comm):
-                eng.join()  # the gather also waits for the deferred remainders of the group
+                for e in pipe.engines:
+                    e.join()  # the gather also waits for the deferred remainders of the group
                 dist.all_gather_into_tensor(Gp["gathered"], Gp["packed"])
                 Gp["done"] = torch.cuda.Event()
                 Gp["done"].record()
 
     def join():
-        eng.join()  # outstanding deferred remainders
+        pipe.join()  # outstanding deferred remainders; the current stream waits for every lane
         if world > 1:
             torch.cuda.current_stream().wait_stream(comm)
 
@@ -292,13 +312,20 @@ def _main(args, real_stdout):
 
     # throughput pipelining of independent batches: the latency-bound remainders of several batches
     # are finished by one launch (deferred join); every step is complete before the end event
-    eng.set_deferred_join(True)
     last_gathered = torch.empty(world, 3 * n, dtype=torch.float64, device=dev) if world > 1 else None
 
     steps = args.steps
     if world > 1 and steps % G:
         steps += G - steps % G  # whole groups (the per-step-gather leg gathers group-wise)
-    for k in range(max(2 * NSETS, args.warmup, 3)):
+    # nvidia-smi is started BEFORE the warm-up: while it attaches to the driver, CUDA launches of this
+    # process stall for milliseconds, which must not fall into the timed region
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first()
+    # (at least two deferred-join cycles of 8 batches per lane: every scratch buffer has reached its
+    # steady-state size before the timed region)
+    for k in range(max(18 * DEPTH, 2 * NSETS, args.warmup, 3)):
         step(k, world > 1)
     join()
     if world > 1:
@@ -308,25 +335,26 @@ def _main(args, real_stdout):
     # ---- timed region: EXACTLY K steps between barrier + synchronize, device-timed -------------
     # The path shards with no data-path collective: each rank's results stay in its HBM; the job ends
     # with the final gather of the last batch (inside the region).
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    eng.reset_stats()
+    pipe.reset_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0.record()
+    pipe.fork()  # the lanes start behind the start event
+    t_region0 = time.perf_counter()
     for k in range(steps):
         step(k, False)
-    join()
+    t_enq = (time.perf_counter() - t_region0) / steps
+    join()  # ... and the end event behind every lane
     if world > 1:
         final_gather(steps - 1)
     e1.record()
     torch.cuda.synchronize()
+    t_region1 = time.perf_counter()
     if world > 1:
         dist.barrier()
-    launches = eng.stats()["kernel_launches"]  # our kernels only (NCCL's are not counted)
+    launches = pipe.kernel_launches()  # our kernels only (NCCL's are not counted)
     total_ms = e0.elapsed_time(e1)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     conv = sum(float((S["out"][3] == 0).sum().item()) for S in sets) / NSETS  # mean per step
@@ -338,7 +366,7 @@ def _main(args, real_stdout):
     converged = float(conv_local.item())
     ms_per_step = total_ms / steps
     value = converged / (ms_per_step * 1e-3)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
 
     # ---- N > 1 only: the same K steps with EVERY batch gathered to every rank (group-wise, on a side
     # stream).  Reported next to `value`: at this per-GPU rate a full gather needs 24 B x 6e9/s x (N-1)
@@ -349,6 +377,7 @@ def _main(args, real_stdout):
         dist.barrier()
         torch.cuda.synchronize()
         g0.record()
+        pipe.fork()
         for k in range(steps):
             step(k, True)
         join()
@@ -362,7 +391,9 @@ def _main(args, real_stdout):
                            "gathered_bytes_per_step_per_gpu": int(24 * n * world),
                            "note": "every batch all_gathered (24 B/integral) inside the timed region, group-wise on a "
                                    "side stream; bound by NVLink ingress, not by the integration kernels"}
-    eng.set_deferred_join(False)
+    torch.cuda.synchronize()
+    for e in pipe.engines:
+        e.set_deferred_join(False)
     p_dev, kw = sets[0]["p_dev"], sets[0]["kw"]
     est, dlt, nev, st = sets[0]["out"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # L2 flush for the profiling pass
@@ -528,9 +559,11 @@ def _main(args, real_stdout):
                        "batch_per_gpu": n, "global_batch": n * world,
                        "parallelism": f"shard{world}" + ("+final_nccl_all_gather" if world > 1 else ""),
                        "l2": "8 independent batches cycled (320 MB of inputs+outputs > 126 MB L2); no flush needed",
-                       "pipeline": "deferred join: the stragglers (integrals needing > 1 bisection step) of up to 8 "
-                                   "steps are finished by one launch of the persistent kernel; all K steps "
-                                   "complete inside the timed region",
+                       "pipeline": f"BatchPipeline depth {DEPTH}: independent batches alternate between {DEPTH} handles "
+                                   f"on {DEPTH} streams (the single-wave survivor kernels of one batch fill the "
+                                   "ramps and tails of the other); deferred join: the stragglers (integrals "
+                                   "needing > 1 bisection step) of up to 8 steps of a lane are finished by one "
+                                   "launch of the persistent kernel; all K steps complete inside the timed region",
                        "gather": ("no data-path collective: every rank keeps its shard's results in its own HBM; "
                                   "one final all_gather of the last batch (24 B/integral) inside the timed region; "
                                   "`per_step_gather` is the same run with every batch gathered") if world > 1
@@ -538,6 +571,7 @@ def _main(args, real_stdout):
                        "converged_fraction": converged / (n * world),
                        "mean_nevals": float(nev_h.mean())},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "host_enqueue_ms_per_step": t_enq * 1e3,
             "roofline": roofline, "cpu_baseline": cpu,
         }
         if per_step_gather is not None:

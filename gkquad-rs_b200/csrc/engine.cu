@@ -391,6 +391,16 @@ int flush_records(gkq_handle_t h, cudaStream_t stream, bool patch) {
     if ((rc = slab_geom(h, R.slab_d, R.slab_d_elems, R.slab_w, R.slab_w_elems, (unsigned long long)grid * ABLOCK,
                         cap, 0, Q.slab)))
         return rc;
+    if (h->deferred && !patch) {
+        // deferred mode ping-pongs between the two record buffers: size the twin's slab now, so that
+        // its first flush (in the caller's steady state) allocates nothing
+        gkq_handle_s::RecBuf& O = h->rb[h->rb_cur ^ 1];
+        SlabGeom unused;
+        if (!O.tail_pending && O.ncalls == 0 &&
+            (rc = slab_geom(h, O.slab_d, O.slab_d_elems, O.slab_w, O.slab_w_elems,
+                            (unsigned long long)grid * ABLOCK, cap, 0, unused)))
+            return rc;
+    }
     Q.tol = R.tol;
     Q.max_evals = R.max_evals;
     Q.ws_capacity = R.ws_capacity;
@@ -771,7 +781,7 @@ static int run_qags_bulk(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, 
     P.rctl = R.rctl;
     P.call_slot = slot;
 
-    const long long nblocks = (P.n + BLOCK - 1) / BLOCK;
+    const long long nblocks = (P.n + IBLOCK - 1) / IBLOCK;
     prof_begin(h, "k_qags_init<qk17>", st);
     L.qags_init17(P, (int)nblocks, st);
     prof_end(h, st);

@@ -155,23 +155,23 @@ struct YRange {
     X(F1_SQUARE, "square", 0, 1.0)           \
     X(F1_RECIP_P, "recip_p", 1, 1.0)         \
     X(F1_LORENTZ_P, "lorentz_p", 1, 4.0)     \
-    X(F1_EXPCOS_P, "expcos_p", 2, 59.0)     \
+    X(F1_EXPCOS_P, "expcos_p", 2, 61.0)     \
     X(F1_GAUSS_P, "gauss_p", 1, 31.0)        \
     X(F1_ABSPOW_P, "abspow_p", 2, 120.0)     \
     X(F1_LOGABS_P, "logabs_p", 1, 45.0)      \
     X(F1_F1, "f1", 0, 172.0)                 \
     X(F1_F2, "f2", 0, 172.0)                 \
-    X(F1_F3, "f3", 0, 55.0)                 \
+    X(F1_F3, "f3", 0, 59.0)                 \
     X(F1_F4, "f4", 0, 53.0)                  \
     X(F1_F5, "f5", 0, 50.0)                  \
     X(F1_F6, "f6", 0, 6.0)                   \
     X(F1_EXP_P, "exp_p", 1, 30.0)            \
     X(F1_SQRT_SHIFT_P, "sqrt_shift_p", 1, 2.0)       \
     X(F1_INV_ABS_SHIFT_P, "inv_abs_shift_p", 1, 2.0) \
-    X(F1_COS_P, "cos_p", 1, 28.0)            \
-    X(F1_SIN_P, "sin_p", 1, 28.0)            \
+    X(F1_COS_P, "cos_p", 1, 30.0)            \
+    X(F1_SIN_P, "sin_p", 1, 30.0)            \
     X(F1_SEMICIRCLE_P, "semicircle_p", 1, 3.0)       \
-    X(F1_SINPOW_P, "sinpow_p", 1, 34.0)
+    X(F1_SINPOW_P, "sinpow_p", 1, 36.0)
 
 #define GKQ_F2_LIST(X)                       \
     X(F2_XY, "xy", 0, 1.0)                   \

@@ -216,6 +216,10 @@ struct RuleUnroll {
 #ifndef GKQ_INIT17_MIN_BLOCKS
 #define GKQ_INIT17_MIN_BLOCKS 4
 #endif
+#ifndef GKQ_INIT_BLOCK
+#define GKQ_INIT_BLOCK 256
+#endif
+constexpr int IBLOCK = GKQ_INIT_BLOCK;
 #ifndef GKQ_INIT25_MIN_BLOCKS
 #define GKQ_INIT25_MIN_BLOCKS 3
 #endif
@@ -236,7 +240,7 @@ struct InitUnroll {
 // ---- QAGS initial passes -------------------------------------------------------------------
 // PASS 0: N = 8 (qk17) over the whole batch (or `worklist`); PASS 1: N = 12 (qk25) over list25.
 template <class F, int N, int NPARAMS>
-__global__ void __launch_bounds__(BLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : GKQ_INIT25_MIN_BLOCKS) k_qags_init(const Batch1D P) {
+__global__ void __launch_bounds__(IBLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : GKQ_INIT25_MIN_BLOCKS) k_qags_init(const Batch1D P) {
     constexpr int PASS = (N == 8) ? 0 : 1;
     long long total;
     if (PASS == 0)
@@ -244,9 +248,9 @@ __global__ void __launch_bounds__(BLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : GKQ_
     else
         total = (long long)P.ctl->count25;
 
-    for (long long k = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    for (long long k = (long long)blockIdx.x * IBLOCK + threadIdx.x;
          k - threadIdx.x % 32 < total;  // keep whole warps in the loop for the ballots below
-         k += (long long)gridDim.x * BLOCK) {
+         k += (long long)gridDim.x * IBLOCK) {
         const bool valid = k < total;
         long long i = 0;
         bool to25 = false, toLoop = false;
@@ -952,10 +956,10 @@ GKQ_F1_LIST(GKQ_DECL_F1)
     template <> Launch1D make_launch1d<ID>() {                                                       \
         Launch1D L;                                                                                  \
         L.qags_init17 = [](const Batch1D& P, int grid, cudaStream_t st) {                            \
-            k_qags_init<F1<ID>, 8, NP><<<grid, BLOCK, 0, st>>>(P);                                   \
+            k_qags_init<F1<ID>, 8, NP><<<grid, IBLOCK, 0, st>>>(P);                                   \
         };                                                                                           \
         L.qags_init25 = [](const Batch1D& P, int grid, cudaStream_t st) {                            \
-            k_qags_init<F1<ID>, 12, NP><<<grid, BLOCK, 0, st>>>(P);                                  \
+            k_qags_init<F1<ID>, 12, NP><<<grid, IBLOCK, 0, st>>>(P);                                  \
         };                                                                                           \
         L.qags_first = [](const Batch1D& P, int grid, cudaStream_t st) {                             \
             k_qags_first<F1<ID>, NP><<<grid, FBLOCK, 0, st>>>(P);                                    \
@@ -1002,7 +1006,7 @@ GKQ_F1_LIST(GKQ_DECL_F1)
         };                                                                                           \
         L.occupancy_init25 = []() {                                                                  \
             int nb = 0;                                                                              \
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_qags_init<F1<ID>, 12, NP>, BLOCK, 0); \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_qags_init<F1<ID>, 12, NP>, IBLOCK, 0); \
             return nb;                                                                               \
         };                                                                                           \
         return L;                                                                                    \

@@ -12,3 +12,4 @@ from .common import (BatchResult, IntegrationResult, RuntimeError, RuntimeError_
                      Tolerance)
 from .engine import ALGO_AUTO, ALGO_QAG, ALGO_QAGP, ALGO_QAGS, BatchPlan, Engine, default_engine  # noqa: F401
 from ._ffi import GkqError, functor_table  # noqa: F401
+from .pipeline import BatchPipeline  # noqa: F401

@@ -1,0 +1,77 @@
+"""BatchPipeline: throughput mode for a stream of independent batches.
+
+One batch of the QAGS path is a short chain of kernels (17-point pass over everything, 25-point pass
+and first bisection step over the compacted survivors, one persistent launch for the stragglers).
+The survivor kernels are single-wave launches: their ramp, their tail and the SMs that drew one
+block fewer leave a fifth of the machine idle while they run.  Batches are independent, so the
+cure is to keep two of them in flight: `depth` handles (a handle owns its scratch, worklists and
+straggler records, and is not shared between streams -- include/gkquad_b200.h, "Threading") on
+`depth` CUDA streams, batch k on lane k % depth, every lane in deferred-join mode.  The kernels of
+one batch then fill the holes of the other (measured on B200, workload S1, 1 M integrals per batch:
+157 -> 129 us per batch at depth 2, 125 us at depth 4; tools/two_stream_probe.py).
+
+This is host-side orchestration only (the rayon-style "several Integrators at work" of the
+reference's users); every lane runs exactly the calls a single Engine would.
+"""
+from __future__ import annotations
+
+from .engine import Engine
+
+
+class BatchPipeline:
+    def __init__(self, device: int = 0, depth: int = 2):
+        import torch
+        assert depth >= 1
+        self.device = int(device)
+        self.engines = [Engine(device) for _ in range(depth)]
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(depth)]
+        for e in self.engines:
+            e.set_deferred_join(True)
+
+    @property
+    def depth(self):
+        return len(self.engines)
+
+    def plan_batch(self, lane: int, *args, **kw):
+        """Marshal a batch call on lane `lane` (see Engine.plan_batch); run it with run()."""
+        plan = self.engines[lane].plan_batch(*args, **kw)
+        return plan
+
+    def run(self, plan, lane: int):
+        """Enqueue a plan made by plan_batch(lane, ...) on its lane's stream.  Its outputs are complete
+        after join() (or once the lane's stream and the lane's Engine.join() are)."""
+        import torch
+        with torch.cuda.stream(self.streams[lane]):
+            plan.run()
+
+    def fork(self):
+        """Order every lane behind the work already queued on the current stream."""
+        import torch
+        ev = torch.cuda.Event()
+        ev.record()
+        for s in self.streams:
+            s.wait_event(ev)
+
+    def join(self):
+        """Finish the deferred remainders of every lane and order the current stream behind all lanes."""
+        import torch
+        for e, s in zip(self.engines, self.streams):
+            with torch.cuda.stream(s):
+                e.join()
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def kernel_launches(self):
+        return sum(e.stats()["kernel_launches"] for e in self.engines)
+
+    def reset_stats(self):
+        for e in self.engines:
+            e.reset_stats()
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize(self.device)
+        for e in self.engines:
+            e.set_deferred_join(False)
+            e.close()

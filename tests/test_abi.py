@@ -47,13 +47,16 @@ def test_registry_matches_oracle_registry():
     from oracle import oracle as O
     for dim in (1, 2, 0):
         ours = [(i, n, p) for i, n, p, _ in _ffi.functor_table(dim)]
-        assert ours == O.functor_table(dim), dim
+        # (the oracle may carry extra probe functors behind the shared ids, e.g. `expcos_p_ulp`:
+        # tools/libm_sensitivity.py)
+        theirs = [row for row in O.functor_table(dim) if not row[1].endswith("_ulp")]
+        assert ours == theirs and theirs == O.functor_table(dim)[:len(theirs)], dim
     L = _ffi.lib()
     assert L.gkq_functor_lookup(1, b"expcos_p") == 3
     assert L.gkq_functor_lookup(1, b"no_such_functor") < 0
     assert L.gkq_functor_count(7) < 0
     # every transcendental functor carries a measured flop count (profiles/functor_flops_r01.md)
-    assert dict((n, f) for _, n, _, f in _ffi.functor_table(1))["expcos_p"] == 59.0
+    assert dict((n, f) for _, n, _, f in _ffi.functor_table(1))["expcos_p"] == 61.0
 
 
 def test_no_device_means_no_compute():

@@ -661,3 +661,32 @@ def test_deferred_join_pipelining(eng):
     for g, r in zip(got, ref):
         assert np.array_equal(g.estimate, r.estimate) and np.array_equal(g.delta, r.delta)
         assert np.array_equal(g.nevals, r.nevals) and np.array_equal(g.status, r.status)
+
+
+def test_batch_pipeline_matches_single_engine(eng):
+    """BatchPipeline (several handles on several streams, deferred join) returns bit for bit what one
+    Engine returns for the same batches, whatever the interleaving."""
+    import torch
+    import gkquad_b200 as gk
+    from gkquad_b200.workloads import WORKLOADS
+    W = WORKLOADS["S3"]  # heavy tail: plenty of straggler records
+    n = 100_000
+    nb = 6
+    ps = [torch.as_tensor(W.make_params(k * n, n), device="cuda:0") for k in range(nb)]
+    want = [eng.integrate_batch(W.functor, W.a, W.b, p, algo=ALGO[W.algo], tol=W.tol, n=n).numpy() for p in ps]
+    pipe = gk.BatchPipeline(0, depth=3)
+    try:
+        plans = [pipe.plan_batch(k % 3, W.functor, W.a, W.b, ps[k], algo=ALGO[W.algo], tol=W.tol, n=n)
+                 for k in range(nb)]
+        pipe.fork()
+        for rep in range(2):  # the second pass overwrites the same outputs while lanes overlap
+            for k in range(nb):
+                pipe.run(plans[k], k % 3)
+        pipe.join()
+        torch.cuda.synchronize()
+        for k in range(nb):
+            g = plans[k].result.numpy()
+            assert np.array_equal(g.estimate, want[k].estimate) and np.array_equal(g.delta, want[k].delta)
+            assert np.array_equal(g.nevals, want[k].nevals) and np.array_equal(g.status, want[k].status)
+    finally:
+        pipe.close()
