@@ -171,7 +171,7 @@ struct YRange {
     X(F1_COS_P, "cos_p", 1, 30.0)            \
     X(F1_SIN_P, "sin_p", 1, 30.0)            \
     X(F1_SEMICIRCLE_P, "semicircle_p", 1, 3.0)       \
-    X(F1_SINPOW_P, "sinpow_p", 1, 36.0)
+    X(F1_SINPOW_P, "sinpow_p", 1, 40.0)
 
 #define GKQ_F2_LIST(X)                       \
     X(F2_XY, "xy", 0, 1.0)                   \
