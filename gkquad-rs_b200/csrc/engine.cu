@@ -122,6 +122,7 @@ struct gkq_handle_s {
         RecCtl* rctl_host = nullptr;      // pinned
         Outputs* call_outs = nullptr;     // device [MAX_CALLS]
         Outputs* call_outs_pin = nullptr;  // pinned mirror
+        int flushed_calls = 0;            // calls covered by the flush whose count is still to be read back
         int ncalls = 0;                   // calls that appended since the last flush
         size_t n_bound = 0;               // upper bound of the records they may have appended
         int fid = -1;                     // configuration the pending records were produced under
@@ -141,6 +142,13 @@ struct gkq_handle_s {
     };
     RecBuf rb[2];
     int rb_cur = 0;
+    // deferred mode: the remainder of a full record buffer runs on this stream, beside the caller's
+    // next batches (which append to the twin buffer); gkq_join orders the caller's stream behind it
+    cudaStream_t s_tail = nullptr;
+    // records per call seen by completed flushes (sizes the next remainder launch: a persistent grid
+    // with more warps than records only takes registers away from the bulk kernels running beside it)
+    double rec_per_call = -1.0;
+    int rec_est_fid = -1;
 
     // host-entry pipeline (gkq_integrate_batch_host)
     static constexpr int MAX_CHUNKS = 64;
@@ -386,11 +394,30 @@ int flush_records(gkq_handle_t h, cudaStream_t stream, bool patch) {
     if (grid < 1) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
     const long long ablocks = ((long long)R.n_bound + ABLOCK - 1) / ABLOCK;
     if ((long long)grid > ablocks) grid = (int)(ablocks > 0 ? ablocks : 1);
+    const int full_grid = grid;  // (sizes the slabs: the estimate below may grow again)
+    // how many records did completed flushes of this configuration find per call?
+    for (int c = 0; c < 2; ++c) {
+        gkq_handle_s::RecBuf& B = h->rb[c];
+        if (B.flushed_calls > 0 && cudaEventQuery(B.ev_tail) == cudaSuccess) {
+            h->rec_per_call = (double)B.rctl_host->count / B.flushed_calls;
+            h->rec_est_fid = B.fid;
+            B.flushed_calls = 0;
+        }
+    }
+    if (!patch && h->deferred && h->rec_per_call >= 0.0 && h->rec_est_fid == fid) {
+        // one warp per expected record (+25 %): same latency as the full grid while the queue is this
+        // short, a fraction of its registers; a longer queue than expected still drains correctly
+        const double warps = h->rec_per_call * R.ncalls * 1.25 + 64.0;
+        const long long blocks = (long long)(warps / (ABLOCK / 32)) + 1;
+        if (blocks < (long long)grid) grid = (int)blocks;
+    }
     Batch1D Q;
     memset(&Q, 0, sizeof Q);
-    if ((rc = slab_geom(h, R.slab_d, R.slab_d_elems, R.slab_w, R.slab_w_elems, (unsigned long long)grid * ABLOCK,
+    // (the slab keeps the size of the full grid; the geometry handed to the kernel is that of this launch)
+    if ((rc = slab_geom(h, R.slab_d, R.slab_d_elems, R.slab_w, R.slab_w_elems, (unsigned long long)full_grid * ABLOCK,
                         cap, 0, Q.slab)))
         return rc;
+    Q.slab.stride = (unsigned long long)grid * ABLOCK;
     if (h->deferred && !patch) {
         // deferred mode ping-pongs between the two record buffers: size the twin's slab now, so that
         // its first flush (in the caller's steady state) allocates nothing
@@ -398,7 +425,7 @@ int flush_records(gkq_handle_t h, cudaStream_t stream, bool patch) {
         SlabGeom unused;
         if (!O.tail_pending && O.ncalls == 0 &&
             (rc = slab_geom(h, O.slab_d, O.slab_d_elems, O.slab_w, O.slab_w_elems,
-                            (unsigned long long)grid * ABLOCK, cap, 0, unused)))
+                            (unsigned long long)full_grid * ABLOCK, cap, 0, unused)))
             return rc;
     }
     Q.tol = R.tol;
@@ -416,8 +443,10 @@ int flush_records(gkq_handle_t h, cudaStream_t stream, bool patch) {
     L.qags_loop(Q, grid, stream);
     prof_end(h, stream);
     if ((rc = launch_check(h, "k_adaptive<QAGS>"))) return rc;
-    if (h->profiling)
+    if (h->profiling || (h->deferred && !patch)) {
         GKQ_CUDA(h, cudaMemcpyAsync(R.rctl_host, R.rctl, sizeof(RecCtl), cudaMemcpyDeviceToHost, stream));
+        R.flushed_calls = R.ncalls;
+    }
     GKQ_CUDA(h, cudaEventRecord(R.ev_tail, stream));
     R.tail_pending = true;
     R.ncalls = 0;
@@ -437,7 +466,7 @@ int records_begin(gkq_handle_t h, cudaStream_t st, int fid, const Batch1D& P, si
                           R.tol.rel_tol == P.tol.rel_tol && R.max_evals == P.max_evals &&
                           R.ws_capacity == P.ws_capacity;
         if (R.ncalls > 0 && (!same || (!patch && R.ncalls >= gkq_handle_s::MAX_CALLS) || R.n_bound + n > R.cap))
-            if ((rc = flush_records(h, st, patch))) return rc;
+            if ((rc = flush_records(h, (h->deferred && !patch) ? h->s_tail : st, patch))) return rc;
     }
     gkq_handle_s::RecBuf& R = h->rb[h->rb_cur];
     if (R.ncalls == 0) {
@@ -551,6 +580,7 @@ int gkq_create(int device, gkq_handle_t* out) {
         ev(&R.ev_bulk);
         ev(&R.ev_tail);
     }
+    strm(&h->s_tail);
     strm(&h->s_in);
     strm(&h->s_compute);
     strm(&h->s_compute2);
@@ -616,7 +646,7 @@ int gkq_destroy(gkq_handle_t h) {
     if (h->ev_c2) cudaEventDestroy(h->ev_c2);
     prof_clear(h);
     for (auto e : h->prof_pool) cudaEventDestroy(e);
-    for (cudaStream_t s : {h->s_in, h->s_compute, h->s_compute2, h->s_out, h->s_out2})
+    for (cudaStream_t s : {h->s_tail, h->s_in, h->s_compute, h->s_compute2, h->s_out, h->s_out2})
         if (s) cudaStreamDestroy(s);
     delete h;
     return GKQ_OK;
