@@ -213,15 +213,19 @@ struct RuleUnroll {
 #ifndef GKQ_INIT_UNROLL_HEAVY
 #define GKQ_INIT_UNROLL_HEAVY 1
 #endif
-#ifndef GKQ_INIT17_MIN_BLOCKS
-#define GKQ_INIT17_MIN_BLOCKS 4
-#endif
+// 128-thread blocks, 6 per SM: a cap of 80 registers (the transcendental bodies use 74) lets ptxas keep
+// the node pair's abscissae and arguments instead of recomputing them (9 % fewer instructions per
+// pair than at 64 registers), and 24 warps per SM are enough -- 8, 10 and 12 warps per scheduler
+// all measured the same or slower (profiles/S1_r01.md, tuning log)
 #ifndef GKQ_INIT_BLOCK
-#define GKQ_INIT_BLOCK 256
+#define GKQ_INIT_BLOCK 128
 #endif
 constexpr int IBLOCK = GKQ_INIT_BLOCK;
+#ifndef GKQ_INIT17_MIN_BLOCKS
+#define GKQ_INIT17_MIN_BLOCKS 6
+#endif
 #ifndef GKQ_INIT25_MIN_BLOCKS
-#define GKQ_INIT25_MIN_BLOCKS 3
+#define GKQ_INIT25_MIN_BLOCKS 6
 #endif
 // the persistent kernel: its loop also holds the list / epsilon-table code, so the rule is unrolled
 // less than in the flat kernels (instruction cache; profiles/)
