@@ -244,13 +244,16 @@ int gkq_functor_eval_batch(gkq_handle_t h, int functor_id, int64_t n, const doub
 
 /* Deferred-join mode (throughput pipelining of independent batches).  By default a batch call is
  * fully ordered on `stream`.  With deferred join enabled, gkq_integrate_batch still enqueues every
- * bulk kernel on `stream`, but the latency-bound remainder of a QAGS batch (the persistent kernels
- * that walk the few integrals needing many bisection steps) runs on a handle-owned stream and
- * overlaps whatever is enqueued next -- typically the bulk of the NEXT batch, which uses the
- * handle's second scratch context (two batches in flight).  The outputs of a batch are complete
- * only after gkq_join(h, stream) (makes `stream` wait for all outstanding remainders) or gkq_sync.
+ * bulk kernel on `stream`, but the latency-bound remainders of QAGS batches (the few integrals
+ * that need many bisection steps) accumulate as self-contained records; when the record buffer is
+ * full (8 batches) ONE launch of the persistent kernel finishes them on a handle-owned stream,
+ * beside whatever is enqueued next (the following batches append to the twin buffer).  The outputs
+ * of a batch are complete only after gkq_join(h, stream) (finishes the pending records and makes
+ * `stream` wait for all outstanding remainders) or gkq_sync.
  * The reference has no counterpart (it is synchronous); an Integrator-level sweep over many
- * parameter batches is where this applies. */
+ * parameter batches is where this applies.  A handle serves ONE stream at a time; to keep two
+ * batches in flight (the single-wave survivor kernels of one fill the ramps and tails of the
+ * other: +20 % on B200) drive two handles on two streams, as the host mirrors' BatchPipeline does. */
 int gkq_set_deferred_join(gkq_handle_t h, int enable);
 int gkq_join(gkq_handle_t h, void* stream);
 
