@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=1 << 20, help="integrals per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--pipeline-depth", type=int, default=2,
+    ap.add_argument("--pipeline-depth", type=int, default=3,
                     help="handles / streams the independent batches alternate between (1 = one handle, one stream)")
     ap.add_argument("--p2p-gather", action="store_true",
                     help="N > 1: also time the gather fused into the kernels (result stores go over NVLink into "

@@ -670,23 +670,38 @@ def test_batch_pipeline_matches_single_engine(eng):
     import gkquad_b200 as gk
     from gkquad_b200.workloads import WORKLOADS
     W = WORKLOADS["S3"]  # heavy tail: plenty of straggler records
-    n = 100_000
+    n = 60_000
     nb = 6
     ps = [torch.as_tensor(W.make_params(k * n, n), device="cuda:0") for k in range(nb)]
     want = [eng.integrate_batch(W.functor, W.a, W.b, p, algo=ALGO[W.algo], tol=W.tol, n=n).numpy() for p in ps]
-    pipe = gk.BatchPipeline(0, depth=3)
-    try:
-        plans = [pipe.plan_batch(k % 3, W.functor, W.a, W.b, ps[k], algo=ALGO[W.algo], tol=W.tol, n=n)
-                 for k in range(nb)]
-        pipe.fork()
-        for rep in range(2):  # the second pass overwrites the same outputs while lanes overlap
+    for depth in (3, 1):
+        pipe = gk.BatchPipeline(0, depth=depth)
+        try:
+            plans = [pipe.plan_batch(k % depth, W.functor, W.a, W.b, ps[k], algo=ALGO[W.algo], tol=W.tol, n=n)
+                     for k in range(nb)]
+            pipe.fork()
+            # 18 batches per lane: two record buffers fill up and are finished on the lane's tail stream
+            # (the second one with a grid sized by the first one's record count) before the final join
+            for rep in range(3 * depth):
+                for k in range(nb):
+                    pipe.run(plans[k], k % depth)
+            pipe.join()
+            torch.cuda.synchronize()
             for k in range(nb):
-                pipe.run(plans[k], k % 3)
-        pipe.join()
-        torch.cuda.synchronize()
-        for k in range(nb):
-            g = plans[k].result.numpy()
-            assert np.array_equal(g.estimate, want[k].estimate) and np.array_equal(g.delta, want[k].delta)
-            assert np.array_equal(g.nevals, want[k].nevals) and np.array_equal(g.status, want[k].status)
-    finally:
-        pipe.close()
+                g = plans[k].result.numpy()
+                assert np.array_equal(g.estimate, want[k].estimate) and np.array_equal(g.delta, want[k].delta)
+                assert np.array_equal(g.nevals, want[k].nevals) and np.array_equal(g.status, want[k].status)
+            # fresh outputs, one more round: what the tail-stream launches wrote is what is read here
+            for k in range(nb):
+                r = plans[k].result
+                for t in (r.estimate, r.delta, r.nevals, r.status):
+                    t.zero_()
+            for k in range(nb):
+                pipe.run(plans[k], k % depth)
+            pipe.join()
+            torch.cuda.synchronize()
+            for k in range(nb):
+                g = plans[k].result.numpy()
+                assert np.array_equal(g.estimate, want[k].estimate) and np.array_equal(g.status, want[k].status)
+        finally:
+            pipe.close()
