@@ -167,3 +167,21 @@ def test_batch_matches_single_calls():
     truth = (p0 * (1 - np.exp(-p0) * np.cos(p1)) + p1 * np.exp(-p0) * np.sin(p1)) / (p0 ** 2 + p1 ** 2)
     assert np.all(np.abs(r["estimate"] - truth) <= 1e-10 * np.abs(truth) + 1e-15)
     assert np.all(r["status"] == 0)
+
+
+def test_ulp_probe_functor_stays_within_tolerance():
+    """`expcos_p_ulp` (oracle-only: S1's integrand with cos() moved one ulp up, the probe behind
+    tools/libm_sensitivity.py) must agree with `expcos_p` far inside the requested tolerance wherever
+    both converge -- what changes under a 1-ulp libm difference is the occasional status / nevals."""
+    import numpy as np
+    from oracle import oracle as O
+    n = 20000
+    rng = np.random.default_rng(7)
+    p = np.stack([0.5 + 1.5 * rng.random(n), 1.0 + 9.0 * rng.random(n)])
+    kw = dict(params=p, tol=("rel", 1e-10), max_evals=2000, n=n)
+    r0 = O.integrate_batch(O.ALGO_QAGS, "expcos_p", 0.0, 1.0, **kw)
+    r1 = O.integrate_batch(O.ALGO_QAGS, "expcos_p_ulp", 0.0, 1.0, **kw)
+    ok = (r0["status"] == 0) & (r1["status"] == 0)
+    assert ok.sum() >= n - 20
+    assert np.all(np.abs(r0["estimate"] - r1["estimate"])[ok] <= 1e-10 * np.abs(r0["estimate"])[ok])
+    assert (r0["nevals"] != r1["nevals"]).sum() <= 5
