@@ -500,7 +500,15 @@ def _main(args, real_stdout):
             "flops_per_eval": w_eval, "kernels": kernels,
             "whole_step": {"achieved": whole_tflops, "frac": whole_tflops / (peak_flops / 1e12)},
             "hbm": {"algorithmic_bytes_per_step": int(n * (8 * p_host.shape[0] + 24)),
-                    "note": "HBM is two orders of magnitude from binding (SURVEY.md section 8d)"},
+                    "note": "HBM is two orders of magnitude from binding (SURVEY.md section 8d)",
+                    # north_star's "worklist compaction pass" is not a pass here: survivors are appended to
+                    # the worklists by warp-aggregated atomics inside the rule kernels (4 B written per
+                    # survivor, 4 B read back by the consumer kernel)
+                    "compaction": {"survivor_ids_bytes_per_step": int(8 * (n25 + cl[0] + cl[1])),
+                                   "survivors_qk25": int(n25), "survivors_loop": int(cl[0] + cl[1]),
+                                   "note": "fused into k_qags_init / k_qags_first (ballot + popc + one atomic per "
+                                           "warp per list); removing the appends altogether shortens "
+                                           "k_qags_init<qk17> by 4 % (profiles/S1_r01.md)"}},
         }
 
     # ---- e2e: the public host entry (gkq_integrate_batch_host) with pinned host buffers ----------
