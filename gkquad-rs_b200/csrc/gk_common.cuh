@@ -226,6 +226,68 @@ GKQ_DEV QK qk_reduce(const double (&fv1)[N], const double (&fv2)[N], double f_ce
     return q;
 }
 
+// qk_reduce over samples kept in SHARED memory, one column per thread: sample j of the lower / upper
+// half at fv[j * stride] / fv[(N + j) * stride] (stride = threads per block, conflict-free).  Same
+// operations in the same order as qk_reduce.
+template <int N>
+GKQ_DEV QK qk_reduce_smem(const double* fv, int stride, double f_center, double a, double b) {
+    using R = Rule<N>;
+    const double half_length = 0.5 * (b - a);
+    const double abs_half_length = fabs(half_length);
+    double result_gauss = 0.;
+    double result_kronrod = f_center * R::WCK;
+    double result_abs = fabs(result_kronrod);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const double f1 = fv[j * stride], f2 = fv[(N + j) * stride];
+        double fsum = f1 + f2;
+        result_kronrod += R::wgk(j) * fsum;
+        result_abs += R::wgk(j) * (fabs(f1) + fabs(f2));
+        if ((j & 1) == 0) result_gauss += R::wg(j >> 1) * fsum;
+    }
+    const double mean = result_kronrod * 0.5;
+    double result_asc = R::WCK * fabs(f_center - mean);
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+        result_asc += R::wgk(j) * (fabs(fv[j * stride] - mean) + fabs(fv[(N + j) * stride] - mean));
+
+    double err = (result_kronrod - result_gauss) * half_length;
+    result_kronrod *= half_length;
+    result_abs *= abs_half_length;
+    result_asc *= abs_half_length;
+    QK q;
+    q.estimate = result_kronrod;
+    q.delta = rescale_error(err, result_abs, result_asc);
+    q.absvalue = result_abs;
+    q.asc = result_asc;
+    return q;
+}
+// The rule for a transcendental body in the flat kernels: one node pair per loop trip, the 2N
+// samples parked in the thread's shared-memory column instead of local memory (local memory
+// competes for L1 with itself -- 176 B x 768 threads per SM -- and its misses and write-backs go
+// to L2: ncu showed 10 M L2 sectors of local traffic per launch of the qk17 pass).
+template <int N, bool TR, class G>
+GKQ_DEV QK qk_rule_smem_fixed(const G& g, double a, double b, double* fv, int stride) {
+    using R = Rule<N>;
+    const double center = 0.5 * (a + b);
+    const double half_length = 0.5 * (b - a);
+#pragma unroll 1
+    for (int j = 0; j < N; ++j) {
+        double abscissa = half_length * R::xgk(j);
+        double f1, f2;
+        g.template pair_t<TR>(center - abscissa, center + abscissa, f1, f2);
+        fv[j * stride] = f1;
+        fv[(N + j) * stride] = f2;
+    }
+    const double f_center = g.template at<TR>(center);
+    return qk_reduce_smem<N>(fv, stride, f_center, a, b);
+}
+template <int N, class G>
+GKQ_DEV QK qk_rule_smem(const G& g, double a, double b, double* fv, int stride) {
+    if (g.transform) return qk_rule_smem_fixed<N, true>(g, a, b, fv, stride);
+    return qk_rule_smem_fixed<N, false>(g, a, b, fv, stride);
+}
+
 // The Gauss-Kronrod rule of single/qk/naive.rs:32-106 for ONE thread: the thread evaluates
 // all 2N+1 nodes itself and accumulates the Kronrod / Gauss / |f| sums and the asc pass in
 // the reference's order (j = 0..N-1 from the centre outwards), so results are bit-equal

@@ -246,6 +246,10 @@ struct InitUnroll {
 template <class F, int N, int NPARAMS>
 __global__ void __launch_bounds__(IBLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : GKQ_INIT25_MIN_BLOCKS) k_qags_init(const Batch1D P) {
     constexpr int PASS = (N == 8) ? 0 : 1;
+#ifndef GKQ_FV_LOCAL
+    // transcendental bodies: the 2N samples of the rule live in the thread's shared-memory column
+    __shared__ double s_fv[F::HEAVY ? 2 * N * IBLOCK : 1];
+#endif
     long long total;
     if (PASS == 0)
         total = P.worklist ? (long long)*P.worklist_count : P.n;
@@ -267,7 +271,15 @@ __global__ void __launch_bounds__(IBLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : GKQ
             if (PASS == 0 && P.max_evals_each && load_max_evals(P, i) < 17ull) {  // qags.rs:86-88
                 write_result(P.out, i, 0.0, F64_MAX, 0u, ST_INSUFFICIENT_ITERATION);
             } else {
+#ifndef GKQ_FV_LOCAL
+            QK q;
+            if constexpr (F::HEAVY)
+                q = qk_rule_smem<N>(g, a, b, s_fv + threadIdx.x, IBLOCK);
+            else
+                q = qk_rule_hoisted<N, InitUnroll<F, N>::value>(g, a, b);
+#else
             const QK q = qk_rule_hoisted<N, InitUnroll<F, N>::value>(g, a, b);
+#endif
             const uint32_t nevals = (PASS == 0) ? 17u : 42u;
 
             // initial_integral, pass i = PASS (qags.rs:336-372)
@@ -324,6 +336,9 @@ __global__ void __launch_bounds__(IBLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : GKQ
 constexpr int FBLOCK = GKQ_FIRST_BLOCK;
 template <class F, int NPARAMS>
 __global__ void __launch_bounds__(FBLOCK, GKQ_FIRST_MIN_BLOCKS) k_qags_first(const Batch1D P) {
+#ifndef GKQ_FV_LOCAL
+    __shared__ double s_fv[F::HEAVY ? 24 * FBLOCK : 1];
+#endif
     const long long total = (long long)P.ctl->chain[P.chain].countLoop;
     for (long long k = (long long)blockIdx.x * FBLOCK + threadIdx.x; k - threadIdx.x % 32 < total;
          k += (long long)gridDim.x * FBLOCK) {
@@ -343,8 +358,19 @@ __global__ void __launch_bounds__(FBLOCK, GKQ_FIRST_MIN_BLOCKS) k_qags_first(con
             const unsigned long long max_iters = (max_evals - nevals) / 50;
             if (max_iters >= 1) {  // else: zero trips, result0 already is the answer (qags.rs:274-276)
                 const double center = (a + b) * 0.5;
+#ifndef GKQ_FV_LOCAL
+                QK q1, q2;
+                if constexpr (F::HEAVY) {
+                    q1 = qk_rule_smem<12>(g, a, center, s_fv + threadIdx.x, FBLOCK);
+                    q2 = qk_rule_smem<12>(g, center, b, s_fv + threadIdx.x, FBLOCK);
+                } else {
+                    q1 = qk_rule<12, RuleUnroll<F, 12>::value>(g, a, center);
+                    q2 = qk_rule<12, RuleUnroll<F, 12>::value>(g, center, b);
+                }
+#else
                 const QK q1 = qk_rule<12, RuleUnroll<F, 12>::value>(g, a, center);
                 const QK q2 = qk_rule<12, RuleUnroll<F, 12>::value>(g, center, b);
+#endif
                 nevals += 50;
                 if (q1.estimate != q1.estimate || q2.estimate != q2.estimate) {
                     // break before the update: sum_results() over the one-interval list
