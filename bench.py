@@ -491,10 +491,10 @@ def _main(args, real_stdout):
             "bound": "fp64", "kernel": dom["kernel"], "achieved": dom["tflops"], "peak": peak_flops / 1e12,
             "unit": "TFLOP/s", "frac": dom["tflops"] / (peak_flops / 1e12),
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of that kernel, from the ncu
-            # --set full capture of this workload (profiles/ncu_S1_kernels_r01c_raw.csv: 39.5 MB read +
-            # 24.4 MB written, against 16.8 MB of parameters in and ~21 MB of results / parked state /
+            # --set full capture of this workload (profiles/ncu_S1_kernels_r01d_raw.csv: 37.9 MB read +
+            # 21.1 MB written, against 16.8 MB of parameters in and ~21 MB of results / parked state /
             # worklists out: partial-sector result stores make L2 fetch the rest of their lines); bytes
-            "traffic": 63.9e6 if (args.workload == "S1" and n == 1 << 20 and dom["kernel"] == "k_qags_init<qk17>") else None,
+            "traffic": 59.0e6 if (args.workload == "S1" and n == 1 << 20 and dom["kernel"] == "k_qags_init<qk17>") else None,
             "peak_source": "measured in this run: dependent-chain DFMA micro-kernel over all SMs "
                            "(MEASURED_PEAKS.json carries no FP64 figure; BASELINE.md section 3)",
             "flops_per_eval": w_eval, "kernels": kernels,
