@@ -820,8 +820,9 @@ static int run_qags_bulk(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, 
     if (h->occ_init25[fid] < 0) h->occ_init25[fid] = L.occupancy_init25();
     long long g25 = (long long)h->sm_count * (h->occ_init25[fid] > 0 ? h->occ_init25[fid] : 1);
     if (g25 > nblocks) g25 = nblocks;
-    // the first-step kernel has its own shape: enough resident threads for the loop entrants of a
-    // typical batch to run as ONE wave (a grid-stride second trip doubles its time)
+    // the first-step kernel has its own shape: a persistent grid of 128-thread blocks that holds
+    // (nearly) all loop entrants of a typical batch at once; the few threads that take a second
+    // grid-stride trip overlap the other kernels in flight
     long long gfirst = (long long)h->sm_count * GKQ_FIRST_MIN_BLOCKS;
     const long long nb_first = (P.n + FBLOCK - 1) / FBLOCK;
     if (gfirst > nb_first) gfirst = nb_first;

@@ -330,8 +330,10 @@ __global__ void __launch_bounds__(IBLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : GKQ
 #ifndef GKQ_FIRST_BLOCK
 #define GKQ_FIRST_BLOCK 128
 #endif
+// 6 blocks per SM (80 registers): with batches pipelined (BatchPipeline) the single wave that 7 blocks
+// at 72 registers bought matters less than their spills (step 0.1185 -> 0.1172 ms, profiles/S1_r01.md)
 #ifndef GKQ_FIRST_MIN_BLOCKS
-#define GKQ_FIRST_MIN_BLOCKS 7
+#define GKQ_FIRST_MIN_BLOCKS 6
 #endif
 constexpr int FBLOCK = GKQ_FIRST_BLOCK;
 template <class F, int NPARAMS>
