@@ -641,6 +641,20 @@ def test_cpp_mirror_reference_benches():
     assert "all reference bench assertions hold" in out.stdout
 
 
+def test_cpp_pipeline_example():
+    """Throughput mode from compiled host code (cpp/example_pipeline.cpp: three handles on three
+    streams over the C ABI, device-resident S1 batches): every converged integral of every batch is
+    within the requested tolerance of the closed form."""
+    import json
+    import subprocess
+    exe = Path(__file__).resolve().parent.parent / "gkquad-rs_b200" / "cpp" / "example_pipeline"
+    assert exe.exists(), "build it: make -C gkquad-rs_b200"
+    out = subprocess.run([str(exe), "3", "200000", "60"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr + out.stdout
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["outside_tolerance_of_closed_form"] == 0 and line["converged_fraction"] > 0.999, line
+
+
 def test_deferred_join_pipelining(eng):
     """gkq_set_deferred_join: back-to-back independent batches (remainders overlapping the next
     batch's bulk, alternating scratch contexts) give exactly the results of ordered calls."""
