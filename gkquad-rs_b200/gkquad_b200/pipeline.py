@@ -25,6 +25,7 @@ class BatchPipeline:
         self.device = int(device)
         self.engines = [Engine(device) for _ in range(depth)]
         self.streams = [torch.cuda.Stream(device=device) for _ in range(depth)]
+        self._raw = [s.cuda_stream for s in self.streams]  # cudaStream_t handles for the C ABI
         for e in self.engines:
             e.set_deferred_join(True)
 
@@ -40,9 +41,7 @@ class BatchPipeline:
     def run(self, plan, lane: int):
         """Enqueue a plan made by plan_batch(lane, ...) on its lane's stream.  Its outputs are complete
         after join() (or once the lane's stream and the lane's Engine.join() are)."""
-        import torch
-        with torch.cuda.stream(self.streams[lane]):
-            plan.run()
+        plan.run(self._raw[lane])
 
     def fork(self):
         """Order every lane behind the work already queued on the current stream."""
@@ -55,9 +54,8 @@ class BatchPipeline:
     def join(self):
         """Finish the deferred remainders of every lane and order the current stream behind all lanes."""
         import torch
-        for e, s in zip(self.engines, self.streams):
-            with torch.cuda.stream(s):
-                e.join()
+        for e, raw in zip(self.engines, self._raw):
+            e._check(e.L.gkq_join(e.h, raw))
         cur = torch.cuda.current_stream(self.device)
         for s in self.streams:
             cur.wait_stream(s)
