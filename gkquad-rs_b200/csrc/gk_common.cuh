@@ -182,40 +182,6 @@ struct Wrapped {
             f2 = f2 * c2 * c2;
         }
     }
-    // The same two samples on the branch-free path ONLY, with the caller's sticky FastMath: the caller
-    // tests m.ok once per rule and re-evaluates the whole rule through at<TR>() if an argument left
-    // the fast range (rule kernels: no branch per node pair, so the loop body is one basic block).
-    template <bool TR>
-    GKQ_DEV void pair_fast(double x1, double x2, double& f1, double& f2, FastMath& m) const {
-        double c1 = 1., c2 = 1.;
-        if (TR) {
-            c1 = 1. / (1. - fabs(x1));
-            c2 = 1. / (1. - fabs(x2));
-            x1 = x1 * c1;
-            x2 = x2 * c2;
-        }
-        if constexpr (F::PAIRWISE) {
-            const D2 r = f.eval(D2{x1, x2}, m);
-            f1 = r.a;
-            f2 = r.b;
-        } else {
-            f1 = f.eval(x1, m);
-            f2 = f.eval(x2, m);
-        }
-        if (TR) {
-            f1 = f1 * c1 * c1;
-            f2 = f2 * c2 * c2;
-        }
-    }
-    template <bool TR>
-    GKQ_DEV double at_fast(double x, FastMath& m) const {
-        if (TR) {
-            double coef = 1. / (1. - fabs(x));
-            double x2 = x * coef;
-            return f.eval(x2, m) * coef * coef;
-        }
-        return f.eval(x, m);
-    }
     GKQ_DEV void pair(double x1, double x2, double& f1, double& f2) const {
         if (transform)
             pair_t<true>(x1, x2, f1, f2);
@@ -300,36 +266,20 @@ GKQ_DEV QK qk_reduce_smem(const double* fv, int stride, double f_center, double 
 // samples parked in the thread's shared-memory column instead of local memory (local memory
 // competes for L1 with itself -- 176 B x 768 threads per SM -- and its misses and write-backs go
 // to L2: ncu showed 10 M L2 sectors of local traffic per launch of the qk17 pass).
-#ifndef GKQ_SMEM_UNROLL
-#define GKQ_SMEM_UNROLL 1
-#endif
-constexpr int SMEM_UNROLL = GKQ_SMEM_UNROLL;  // node pairs per loop trip
 template <int N, bool TR, class G>
 GKQ_DEV QK qk_rule_smem_fixed(const G& g, double a, double b, double* fv, int stride) {
     using R = Rule<N>;
     const double center = 0.5 * (a + b);
     const double half_length = 0.5 * (b - a);
-    FastMath m;  // sticky over the whole rule
-#pragma unroll SMEM_UNROLL
+#pragma unroll 1
     for (int j = 0; j < N; ++j) {
         double abscissa = half_length * R::xgk(j);
         double f1, f2;
-        g.template pair_fast<TR>(center - abscissa, center + abscissa, f1, f2, m);
+        g.template pair_t<TR>(center - abscissa, center + abscissa, f1, f2);
         fv[j * stride] = f1;
         fv[(N + j) * stride] = f2;
     }
-    double f_center = g.template at_fast<TR>(center, m);
-    if (!m.ok) {
-        // rare: some argument left the range of the branch-free kernels (|x| >= 708 for exp, >= 2^30
-        // for sin / cos, non-finite): every sample again through the always-valid path
-#pragma unroll 1
-        for (int j = 0; j < N; ++j) {
-            double abscissa = half_length * R::xgk(j);
-            fv[j * stride] = g.template at<TR>(center - abscissa);
-            fv[(N + j) * stride] = g.template at<TR>(center + abscissa);
-        }
-        f_center = g.template at<TR>(center);
-    }
+    const double f_center = g.template at<TR>(center);
     return qk_reduce_smem<N>(fv, stride, f_center, a, b);
 }
 template <int N, class G>
