@@ -8,7 +8,7 @@ cure is to keep two of them in flight: `depth` handles (a handle owns its scratc
 straggler records, and is not shared between streams -- include/gkquad_b200.h, "Threading") on
 `depth` CUDA streams, batch k on lane k % depth, every lane in deferred-join mode.  The kernels of
 one batch then fill the holes of the other (measured on B200, workload S1, 1 M integrals per batch:
-157 -> 129 us per batch at depth 2, 125 us at depth 4; tools/two_stream_probe.py).
+142 -> 123 us per batch at depth 2, 118 us at depth 3; tools/bench_depth_sweep.sh, tools/two_stream_probe.py).
 
 This is host-side orchestration only (the rayon-style "several Integrators at work" of the
 reference's users); every lane runs exactly the calls a single Engine would.
