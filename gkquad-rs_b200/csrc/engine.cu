@@ -156,6 +156,8 @@ struct gkq_handle_s {
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_done[MAX_CHUNKS] = {};
     cudaEvent_t ev_c2 = nullptr;
     bool host_records_primed = false;  // the host pipeline has reset the record counters itself
+    int host_tail_fid = -1;            // functor and straggler share of the last QAGS host call
+    double host_tail_share = 0.0;
     size_t stage_bytes = 0;
     char* stage_dev = nullptr;
     double* fixed_pin = nullptr;  // pinned copy of the shared (stride-0) range / parameters
@@ -1277,9 +1279,41 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
     unsigned long long nrec = 0;
     gkq_handle_s::RecBuf& R = h->rb[rbi];
     const bool have_records = rc == GKQ_OK && is_qags && h->rb_cur == rbi && R.ncalls > 0;
+    bool heavy_tail = false;
     if (have_records) {
         GKQ_CUDA(h, cudaEventRecord(h->ev_c2, h->s_compute2));
         GKQ_CUDA(h, cudaStreamWaitEvent(h->s_compute, h->ev_c2, 0));
+        // How many stragglers does the bulk leave?  A handful (smooth integrands) travels as a compact
+        // patch that the CPU applies; when a large share of the batch needs the persistent kernel
+        // (e.g. every integral of an infinite-range batch takes > 1 bisection step) patching a million
+        // scattered entries on one host core would dominate the call: the remainder then writes into
+        // the staged result arrays and those are copied out once more as a whole.  Both paths are
+        // correct for any count; which one is taken follows the share the PREVIOUS host call of this
+        // functor saw (asking the device now would stall the enqueue behind the bulk: measured -5 %
+        // on the smooth headline workload).
+        heavy_tail = h->host_tail_fid == functor_id && h->host_tail_share > 1.0 / 16.0;
+    }
+    if (have_records && heavy_tail) {
+        const Outputs whole = {d_est, d_dlt, d_nev, d_st};  // record indices are batch-wide (idx_offset)
+        for (int c = 0; c < R.ncalls; ++c) R.call_outs_pin[c] = whole;
+        GKQ_CUDA(h, cudaMemcpyAsync(R.call_outs, R.call_outs_pin, sizeof(Outputs) * (size_t)R.ncalls,
+                                    cudaMemcpyHostToDevice, h->s_compute));
+        GKQ_CUDA(h, cudaEventRecord(R.ev_bulk, h->s_compute));  // (flush_records orders itself behind it)
+        if ((rc = flush_records(h, h->s_compute, false)) == GKQ_OK) {
+            // the whole-array copies go last on s_out: behind the remainder and behind the chunk copies
+            // of both copy-out streams, which target the same host arrays
+            GKQ_CUDA(h, cudaEventRecord(h->ev_c2, h->s_out2));
+            GKQ_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_c2, 0));
+            GKQ_CUDA(h, cudaStreamWaitEvent(h->s_out, R.ev_tail, 0));
+            GKQ_CUDA(h, cudaMemcpyAsync(out_estimate, d_est, N * 8, cudaMemcpyDeviceToHost, h->s_out));
+            GKQ_CUDA(h, cudaMemcpyAsync(out_delta, d_dlt, N * 8, cudaMemcpyDeviceToHost, h->s_out));
+            GKQ_CUDA(h, cudaMemcpyAsync(out_nevals, d_nev, N * 4, cudaMemcpyDeviceToHost, h->s_out));
+            GKQ_CUDA(h, cudaMemcpyAsync(out_status, d_st, N * 4, cudaMemcpyDeviceToHost, h->s_out));
+            GKQ_CUDA(h, cudaMemcpyAsync(R.rctl_host, R.rctl, sizeof(RecCtl), cudaMemcpyDeviceToHost, h->s_compute));
+            R.tail_pending = false;  // (the stream synchronisations below cover it)
+            R.flushed_calls = 0;
+        }
+    } else if (have_records) {
         if ((rc = flush_records(h, h->s_compute, true)) == GKQ_OK) {
             GKQ_CUDA(h, cudaMemcpyAsync(R.rctl_host, R.rctl, sizeof(RecCtl), cudaMemcpyDeviceToHost, h->s_compute));
             // most batches leave a handful of stragglers: fetch a first slice together with the count
@@ -1311,7 +1345,11 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
     if (rc) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess)
         return fail(h, GKQ_ERR_CUDA, "host pipeline failed: a stream reported an error");
-    if (have_records) {
+    if (have_records) {  // what this call saw steers the next one
+        h->host_tail_fid = functor_id;
+        h->host_tail_share = (double)R.rctl_host->count / (double)N;
+    }
+    if (have_records && !heavy_tail) {
         PatchView hv = patch_view(R.patch_pin, R.patch_cap);
         for (unsigned long long k = 0; k < nrec; ++k) {
             const unsigned long long i = hv.idx[k];

@@ -197,6 +197,27 @@ def test_host_entry_matches_device_entry(eng):
     assert np.array_equal(g2.estimate, g_dev.estimate)
 
 
+@pytest.mark.parametrize("wname", ["I1", "S3", "I2"])
+def test_host_entry_heavy_tail(eng, wname):
+    """Host entry when a large share of the batch needs the persistent kernel (every integral of an
+    infinite-range batch takes more than one bisection step): the remainder writes into the staged
+    arrays, which are copied out whole, instead of a million-entry patch applied by the CPU.  Bit for
+    bit the device entry's results; also across the threshold between the two paths."""
+    import torch
+    from gkquad_b200.workloads import WORKLOADS
+    W = WORKLOADS[wname]
+    for n in (70_001, 300_001):
+        p = W.make_params(0, n)
+        g_host = eng.integrate_batch(W.functor, W.a, W.b, p, algo=ALGO[W.algo], tol=W.tol, n=n)
+        g_dev = eng.integrate_batch(W.functor, W.a, W.b, torch.as_tensor(p, device="cuda:0"), algo=ALGO[W.algo],
+                                    tol=W.tol, n=n).numpy()
+        assert np.array_equal(g_host.estimate, g_dev.estimate) and np.array_equal(g_host.delta, g_dev.delta)
+        assert np.array_equal(g_host.nevals, g_dev.nevals) and np.array_equal(g_host.status, g_dev.status)
+        # again: the second call reuses the other record buffer and the staging area
+        g_host2 = eng.integrate_batch(W.functor, W.a, W.b, p, algo=ALGO[W.algo], tol=W.tol, n=n)
+        assert np.array_equal(g_host2.estimate, g_dev.estimate) and np.array_equal(g_host2.nevals, g_dev.nevals)
+
+
 def test_full_size_properties(eng):
     """BASELINE cfg-2 size (1M, S1): properties that need no oracle -- closed-form truth within
     tolerance, reversed range negates exactly, results independent of batch position."""
