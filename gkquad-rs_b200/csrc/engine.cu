@@ -479,7 +479,13 @@ int records_begin(gkq_handle_t h, cudaStream_t st, int fid, const Batch1D& P, si
         }
         // deferred mode batches the remainders of up to 8 calls into one launch (every integral of
         // a call may become a record, so room for 8 n records is kept: 144 B each)
-        const size_t want = (h->deferred && !patch && !h->profiling) ? 8 * n : n;
+        // (... but never more than 2^23 records, 1.5 GB, beyond what one call needs: large batches
+        // do not need the amortisation, and several handles may share the device)
+        size_t want = n;
+        if (h->deferred && !patch && !h->profiling) {
+            const size_t lim = n > ((size_t)1 << 23) ? n : ((size_t)1 << 23);
+            want = 8 * n < lim ? 8 * n : lim;
+        }
         if (want > R.cap) {
             GKQ_CUDA(h, cudaStreamSynchronize(st));  // nothing may still read the old buffer
             if ((rc = grow(h, R.recs, R.cap, want))) return rc;
