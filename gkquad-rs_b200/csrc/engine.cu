@@ -400,10 +400,14 @@ int flush_records(gkq_handle_t h, cudaStream_t stream, bool patch) {
     // how many records did completed flushes of this configuration find per call?
     for (int c = 0; c < 2; ++c) {
         gkq_handle_s::RecBuf& B = h->rb[c];
-        if (B.flushed_calls > 0 && cudaEventQuery(B.ev_tail) == cudaSuccess) {
+        if (B.flushed_calls == 0) continue;
+        const cudaError_t q = cudaEventQuery(B.ev_tail);
+        if (q == cudaSuccess) {
             h->rec_per_call = (double)B.rctl_host->count / B.flushed_calls;
             h->rec_est_fid = B.fid;
             B.flushed_calls = 0;
+        } else if (q == cudaErrorNotReady) {
+            (void)cudaGetLastError();  // "still running" must not surface in the next launch_check
         }
     }
     if (!patch && h->deferred && h->rec_per_call >= 0.0 && h->rec_est_fid == fid) {

@@ -740,3 +740,29 @@ def test_batch_pipeline_matches_single_engine(eng):
                 assert np.array_equal(g.estimate, want[k].estimate) and np.array_equal(g.status, want[k].status)
         finally:
             pipe.close()
+
+
+def test_deferred_remainders_overlap_small_batches(eng):
+    """Tiny batches in deferred mode: record buffers fill up and are finished on the tail stream faster
+    than a remainder launch runs (75 us), so flushes overlap their predecessors and the engine's
+    cudaEventQuery sees "not ready".  Results stay bit-identical to ordered calls."""
+    import torch
+    import gkquad_b200 as gk
+    from gkquad_b200.workloads import WORKLOADS
+    W = WORKLOADS["S3"]
+    n = 2048
+    p = torch.as_tensor(W.make_params(0, n), device="cuda:0")
+    want = eng.integrate_batch(W.functor, W.a, W.b, p, algo=ALGO[W.algo], tol=W.tol, n=n).numpy()
+    pipe = gk.BatchPipeline(0, depth=1)
+    try:
+        plan = pipe.plan_batch(0, W.functor, W.a, W.b, p, algo=ALGO[W.algo], tol=W.tol, n=n)
+        pipe.fork()
+        for _ in range(400):
+            pipe.run(plan, 0)
+        pipe.join()
+        torch.cuda.synchronize()
+        g = plan.result.numpy()
+        assert np.array_equal(g.estimate, want.estimate) and np.array_equal(g.delta, want.delta)
+        assert np.array_equal(g.nevals, want.nevals) and np.array_equal(g.status, want.status)
+    finally:
+        pipe.close()
