@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/gkquad_b200.h"
+#include "engine_internal.h"
 #include "kernels_1d.cuh"
 #include "kernels_2d.cuh"
 
@@ -35,6 +36,29 @@ __global__ void __launch_bounds__(BLOCK) k_fill_result(long long n, Outputs O, d
                                                        uint32_t nev, uint32_t st) {
     const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (i < n) write_result(O, i, est, dlt, nev, st);
+}
+
+// The same over a device-built worklist (AUTO split of a CSR batch).
+__global__ void __launch_bounds__(BLOCK) k_fill_result_list(const unsigned int* list, const unsigned long long* count,
+                                                            Outputs O, double est, double dlt, uint32_t nev, uint32_t st) {
+    const unsigned long long total = *count;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x; k < total;
+         k += (unsigned long long)gridDim.x * BLOCK)
+        write_result(O, (long long)list[k], est, dlt, nev, st);
+}
+
+// GKQ_FLAG_VALIDATE_INPUTS: any NaN among the first `n` entries of up to five optional arrays?
+__global__ void __launch_bounds__(BLOCK) k_any_nan(long long n, const double* a0, const double* a1, const double* a2,
+                                                   const double* a3, unsigned int* flag) {
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    bool bad = false;
+    if (i < n) {
+        if (a0) bad = bad || a0[i] != a0[i];
+        if (a1) bad = bad || a1[i] != a1[i];
+        if (a2) bad = bad || a2[i] != a2[i];
+        if (a3) bad = bad || a3[i] != a3[i];
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
 // AUTO over a CSR batch (auto.rs:29-33): integrals without points -> QAGS worklist, with
@@ -85,6 +109,8 @@ struct gkq_handle_s {
     std::string err;
     gkq_stats stats{};
     bool deferred = false;  // gkq_set_deferred_join
+    gkq_comm_s* comm = nullptr;            // gkq_comm_init (comm.cu)
+    unsigned long long max_evals_seen = 0;  // largest cfg->max_evals of any call (gkq_gather packs nevals in 29 bits)
 
     // Bulk scratch: two contexts, so the host pipeline can run chunks on two compute streams.
     struct Scratch {
@@ -123,6 +149,7 @@ struct gkq_handle_s {
         Outputs* call_outs = nullptr;     // device [MAX_CALLS]
         Outputs* call_outs_pin = nullptr;  // pinned mirror
         int flushed_calls = 0;            // calls covered by the flush whose count is still to be read back
+        int flushed_fid = -1;             // functor of that flush (R.fid may be reused before the count arrives)
         int ncalls = 0;                   // calls that appended since the last flush
         size_t n_bound = 0;               // upper bound of the records they may have appended
         int fid = -1;                     // configuration the pending records were produced under
@@ -290,6 +317,15 @@ int check_tol(gkq_handle_t h, const gkq_tolerance& t) {
     return 0;
 }
 
+// NaN anywhere in a host array?  (the reference panics on NaN ranges / tolerances / points:
+// single/common.rs:94, single/integrator.rs:71,86-90)
+bool host_has_nan(const double* p, size_t n) {
+    if (!p) return false;
+    bool bad = false;
+    for (size_t i = 0; i < n; ++i) bad |= p[i] != p[i];
+    return bad;
+}
+
 int upload_shared_points(gkq_handle_t h, const double* pts, size_t count, cudaStream_t st) {
     if (count == 0) return 0;
     gkq_handle_s::Scratch& s = h->sc[h->cur];
@@ -334,6 +370,23 @@ int launch_check(gkq_handle_t h, const char* what) {
     }
     h->stats.kernel_launches += 1;
     return 0;
+}
+
+// GKQ_FLAG_VALIDATE_INPUTS on a device entry: one small kernel + one stream synchronisation.
+int validate_device_inputs(gkq_handle_t h, cudaStream_t st, long long n, long long n_range, const double* a,
+                           const double* b, const double* abs_each, const double* rel_each) {
+    gkq_handle_s::Scratch& S = h->sc[h->cur];
+    unsigned int* flag = (unsigned int*)&S.ctl->pad[0];  // zeroed with the control block
+    k_any_nan<<<(int)((n_range + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(n_range, a, b, nullptr, nullptr, flag);
+    if (abs_each || rel_each)
+        k_any_nan<<<(int)((n + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(n, abs_each, rel_each, nullptr, nullptr, flag);
+    int rc;
+    if ((rc = launch_check(h, "k_any_nan"))) return rc;
+    GKQ_CUDA(h, cudaMemcpyAsync(S.ctl_host, S.ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
+    GKQ_CUDA(h, cudaStreamSynchronize(st));
+    if (S.ctl_host->pad[0] != 0ull)
+        return fail(h, GKQ_ERR_NAN_INPUT, "NaN in a range bound or in a per-integral tolerance");
+    return GKQ_OK;
 }
 
 // Bracket a kernel launch with events on its own stream when profiling is on.
@@ -404,7 +457,7 @@ int flush_records(gkq_handle_t h, cudaStream_t stream, bool patch) {
         const cudaError_t q = cudaEventQuery(B.ev_tail);
         if (q == cudaSuccess) {
             h->rec_per_call = (double)B.rctl_host->count / B.flushed_calls;
-            h->rec_est_fid = B.fid;
+            h->rec_est_fid = B.flushed_fid;
             B.flushed_calls = 0;
         } else if (q == cudaErrorNotReady) {
             (void)cudaGetLastError();  // "still running" must not surface in the next launch_check
@@ -452,6 +505,7 @@ int flush_records(gkq_handle_t h, cudaStream_t stream, bool patch) {
     if (h->profiling || (h->deferred && !patch)) {
         GKQ_CUDA(h, cudaMemcpyAsync(R.rctl_host, R.rctl, sizeof(RecCtl), cudaMemcpyDeviceToHost, stream));
         R.flushed_calls = R.ncalls;
+        R.flushed_fid = fid;
     }
     GKQ_CUDA(h, cudaEventRecord(R.ev_tail, stream));
     R.tail_pending = true;
@@ -482,7 +536,7 @@ int records_begin(gkq_handle_t h, cudaStream_t st, int fid, const Batch1D& P, si
             R.tail_pending = false;
         }
         // deferred mode batches the remainders of up to 8 calls into one launch (every integral of
-        // a call may become a record, so room for 8 n records is kept: 144 B each)
+        // a call may become a record, so room for 8 n records is kept: sizeof(StragglerRec) each)
         // (... but never more than 2^23 records, 1.5 GB, beyond what one call needs: large batches
         // do not need the amortisation, and several handles may share the device)
         size_t want = n;
@@ -513,15 +567,19 @@ int records_begin(gkq_handle_t h, cudaStream_t st, int fid, const Batch1D& P, si
         R.patch_cap = R.cap;
         h->stats.scratch_bytes += patch_bytes(R.cap);
     }
+    // (device entry: k_qags_first publishes the call's output arrays in slot `slot` of R.call_outs
+    // from its kernel parameters -- Batch1D::call_outs_w; patched results never look the call up)
     slot = (unsigned int)R.ncalls;
-    if (!patch) {  // (patched results never look the owning call up)
-        R.call_outs_pin[slot] = P.out;
-        GKQ_CUDA(h, cudaMemcpyAsync(R.call_outs + slot, R.call_outs_pin + slot, sizeof(Outputs), cudaMemcpyHostToDevice, st));
-    }
     return GKQ_OK;
 }
 
 }  // namespace
+
+int gkq_internal_fail(gkq_handle_t h, int code, const char* msg) { return fail(h, code, msg ? msg : ""); }
+gkq_comm_s*& gkq_internal_comm_slot(gkq_handle_t h) { return h->comm; }
+int gkq_internal_device(gkq_handle_t h) { return h->device; }
+unsigned long long gkq_internal_max_evals_seen(gkq_handle_t h) { return h->max_evals_seen; }
+void gkq_internal_count_launch(gkq_handle_t h) { h->stats.kernel_launches += 1; }
 
 // ---- C ABI -----------------------------------------------------------------------------------
 extern "C" {
@@ -616,6 +674,7 @@ int gkq_destroy(gkq_handle_t h) {
     if (!h) return GKQ_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    gkq_comm_destroy(h);
     for (int c = 0; c < 2; ++c) {
         gkq_handle_s::Scratch& s = h->sc[c];
         cudaFree(s.ctl);
@@ -812,7 +871,11 @@ static int run_qags_bulk(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, 
     gkq_handle_s::Scratch& S = h->sc[h->cur];
     if (P.max_evals < 17) {  // qags.rs:86-88 -- only reachable without a worklist split
         const int grid = (int)((P.n + BLOCK - 1) / BLOCK);
-        if (P.worklist) return fail(h, GKQ_ERR_UNSUPPORTED, "max_evals < 17 with a CSR AUTO batch");
+        if (P.worklist) {  // the QAGS subset of a CSR AUTO batch (the QAGP subset applies qagp.rs:79-81 itself)
+            k_fill_result_list<<<grid < 1184 ? grid : 1184, BLOCK, 0, st>>>(P.worklist, P.worklist_count, P.out, 0.0,
+                                                                           F64_MAX, 0u, ST_INSUFFICIENT_ITERATION);
+            return launch_check(h, "k_fill_result_list");
+        }
         k_fill_result<<<grid, BLOCK, 0, st>>>(P.n, P.out, 0.0, F64_MAX, 0u, ST_INSUFFICIENT_ITERATION);
         return launch_check(h, "k_fill_result");
     }
@@ -822,6 +885,7 @@ static int run_qags_bulk(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, 
     P.recs = R.recs;
     P.rctl = R.rctl;
     P.call_slot = slot;
+    P.call_outs_w = patch ? nullptr : R.call_outs;
 
     const long long nblocks = (P.n + IBLOCK - 1) / IBLOCK;
     prof_begin(h, "k_qags_init<qk17>", st);
@@ -934,6 +998,7 @@ static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functo
         return fail(h, GKQ_ERR_INVALID_ARGUMENT, "NULL array argument");
     if (F1_TABLE[functor_id].nparams > 0 && !params) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "params is NULL");
     if (pts_offsets && !pts) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "pts is NULL");
+    if (cfg->max_evals > h->max_evals_seen) h->max_evals_seen = cfg->max_evals;
 
     GKQ_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -977,6 +1042,8 @@ static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functo
     const Launch1D& L = h->l1[functor_id];
     h->stats.batches += 1;
     h->stats.integrals += (uint64_t)n;
+    if ((cfg->flags & GKQ_FLAG_VALIDATE_INPUTS) && !patch)
+        if ((rc = validate_device_inputs(h, st, n, range_stride ? n : 1, a, b, P.abs_tol_each, P.rel_tol_each))) return rc;
 
     bool did_qags = false;
     if (cfg->algo == GKQ_ALGO_QAG) {
@@ -1135,6 +1202,15 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
     if (np > 0 && !params) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "params is NULL");
     const int np_batch = param_stride ? np : 0;  // per-integral parameter rows
     int rc;
+    // the data is visible to the CPU here: refuse what the reference refuses to construct
+    // (Range::new, single/common.rs:94; Tolerance, single/integrator.rs:71)
+    if (host_has_nan(a, range_stride ? (size_t)n : 1) || host_has_nan(b, range_stride ? (size_t)n : 1))
+        return fail(h, GKQ_ERR_NAN_INPUT, "cannot create Range object from Range which contains NaN value.");
+    if (ov_host) {
+        const bool need_abs = cfg->tol.kind != GKQ_TOL_RELATIVE, need_rel = cfg->tol.kind != GKQ_TOL_ABSOLUTE;
+        if ((need_abs && host_has_nan(ov_host->abs_tol, (size_t)n)) || (need_rel && host_has_nan(ov_host->rel_tol, (size_t)n)))
+            return fail(h, GKQ_ERR_NAN_INPUT, "Tolerance must not contain NAN.");
+    }
     // records pending from deferred device-entry calls are finished first (they own the buffers)
     if (h->rb[0].ncalls || h->rb[1].ncalls || h->rb[0].tail_pending || h->rb[1].tail_pending) {
         if ((rc = gkq_join(h, h->s_compute))) return rc;
@@ -1255,6 +1331,29 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
 
     // ---- phase 2: bulk kernels + result copies, chunk by chunk ------------------------------------
     rc = GKQ_OK;
+    // Whatever way this function is left (every GKQ_CUDA below may return early), the handle must not
+    // keep half-updated pipeline state: the "primed" flag, the current scratch context and -- on
+    // failure -- the record buffer this call was appending to (drained streams, counters reset).
+    struct HostCallGuard {
+        gkq_handle_s* h;
+        int rbi;
+        bool ok = false;
+        ~HostCallGuard() {
+            h->host_records_primed = false;
+            h->cur = 0;
+            if (ok) return;
+            for (cudaStream_t s : {h->s_in, h->s_compute, h->s_compute2, h->s_out, h->s_out2}) (void)cudaStreamSynchronize(s);
+            (void)cudaGetLastError();
+            for (int c = 0; c < 2; ++c) {
+                gkq_handle_s::RecBuf& B = h->rb[c];
+                B.ncalls = 0;
+                B.n_bound = 0;
+                B.flushed_calls = 0;
+                B.tail_pending = false;
+            }
+            h->rb_cur = rbi;
+        }
+    } guard{h, rbi};
     h->host_records_primed = is_qags;  // records_begin must not reset the counters again
     for (int c = 0; c < nchunks && rc == GKQ_OK; ++c) {
         const int64_t off = c_off[c], m = c_len[c];
@@ -1369,6 +1468,7 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
             out_status[i] = hv.st[k];
         }
     }
+    guard.ok = true;
     if (trace && !tev.empty()) {
         // events: [0] start; per chunk h2d_begin, h2d_end (phase 1); then per chunk compute_begin,
         // compute_end, d2h_begin, d2h_end (phase 2)
@@ -1416,6 +1516,7 @@ int gkq_integrate2_batch_ex(gkq_handle_t h, const gkq_config* cfg, const gkq_ove
     if (F2_TABLE[functor2_id].nparams > 0 && !fparams) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "fparams is NULL");
     if (YR_TABLE[yrange_id].nparams > 0 && !yparams) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "yparams is NULL");
     if (pts_offsets && !pts_xy) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "pts_xy is NULL");
+    if (cfg->max_evals > h->max_evals_seen) h->max_evals_seen = cfg->max_evals;
 
     GKQ_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -1454,6 +1555,8 @@ int gkq_integrate2_batch_ex(gkq_handle_t h, const gkq_config* cfg, const gkq_ove
     GKQ_CUDA(h, cudaMemsetAsync(S.ctl, 0, sizeof(Control), st));
     h->stats.batches += 1;
     h->stats.integrals += (uint64_t)n;
+    if (cfg->flags & GKQ_FLAG_VALIDATE_INPUTS)
+        if ((rc = validate_device_inputs(h, st, n, range_stride ? n : 1, x0, x1, P.abs_tol_each, P.rel_tol_each))) return rc;
 
     if (cfg->algo == GKQ_ALGO_QAG) {
         // QAG2 (deprecated in the reference, double/algorithm/qag.rs): never looks at points; one
@@ -1619,6 +1722,14 @@ int gkq_integrate2_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gk
     const int np = F2_TABLE[functor2_id].nparams, nq = YR_TABLE[yrange_id].nparams;
     const size_t npairs = pts_offsets ? (size_t)pts_offsets[n] : 0;
     if ((np > 0 && !fparams) || (nq > 0 && !yparams)) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "params is NULL");
+    if (!cfg) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "cfg is NULL");
+    if (host_has_nan(x0, range_stride ? (size_t)n : 1) || host_has_nan(x1, range_stride ? (size_t)n : 1))
+        return fail(h, GKQ_ERR_NAN_INPUT, "cannot create Range object from Range which contains NaN value.");
+    if (ov_host) {
+        const bool need_abs = cfg->tol.kind != GKQ_TOL_RELATIVE, need_rel = cfg->tol.kind != GKQ_TOL_ABSOLUTE;
+        if ((need_abs && host_has_nan(ov_host->abs_tol, (size_t)n)) || (need_rel && host_has_nan(ov_host->rel_tol, (size_t)n)))
+            return fail(h, GKQ_ERR_NAN_INPUT, "Tolerance must not contain NAN.");
+    }
     // single-shot staging (2-D batches are compute-heavy: copies are negligible)
     const size_t N = (size_t)n;
     const size_t nx = range_stride ? N : 1, nfp = fparam_stride ? N : 1, nyp = yparam_stride ? N : 1;

@@ -144,6 +144,10 @@ struct Batch1D {
     unsigned int call_slot;         // slot of this call in `call_outs`
     unsigned long long idx_offset;  // added to the integral index stored in a record (host pipeline chunks)
     const Outputs* call_outs;       // [slots] output arrays of the calls that own the records
+    // device entry: k_qags_first itself publishes this call's output arrays in its slot of the table
+    // (kernel parameters -> device memory, stream-ordered; no host staging buffer that a later call
+    // could overwrite while an earlier copy is still queued)
+    Outputs* call_outs_w;
     PatchView patch;                // patch.idx != nullptr: finished stragglers go to the patch
     const unsigned int* worklist;        // optional subset of integrals (AUTO split) or nullptr
     const unsigned long long* worklist_count;  // device count for `worklist`
@@ -342,6 +346,7 @@ __global__ void __launch_bounds__(FBLOCK, GKQ_FIRST_MIN_BLOCKS) k_qags_first(con
     __shared__ double s_fv[F::HEAVY ? 24 * FBLOCK : 1];
 #endif
     const long long total = (long long)P.ctl->chain[P.chain].countLoop;
+    if (P.call_outs_w && blockIdx.x == 0 && threadIdx.x == 0) P.call_outs_w[P.call_slot] = P.out;
     for (long long k = (long long)blockIdx.x * FBLOCK + threadIdx.x; k - threadIdx.x % 32 < total;
          k += (long long)gridDim.x * FBLOCK) {
         bool survive = false;
@@ -590,6 +595,7 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
                 } else {
                     lane_reset_common(s);
                     double a, b;
+                    bool continue_refill = false;
                     if (!QAGP) {
                         // resume after iteration 1 from the straggler record
                         const StragglerRec& r = P.recs[my];
@@ -640,6 +646,12 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
                     } else {
                         s.idx = P.worklist ? (long long)P.worklist[my] : (long long)my;
                         load_range(P, s.idx, a, b, s.transform);
+                        if (a != a || b != b) {
+                            // a NaN bound cannot exist in the reference (Range::new refuses it,
+                            // single/common.rs:94); defined here instead of a silent (0, 0, 0, None)
+                            write_result(P.out, s.idx, a + b, F64_MAX, 0u, ST_NAN);
+                            continue_refill = true;
+                        }
                         load_functor(g.f, P, s.idx, NPARAMS);
                         g.transform = s.transform;
                         const double* up;
@@ -661,7 +673,9 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
                             my_rel_tol = t.rel_tol;
                             my_max_evals = load_max_evals(P, s.idx);
                         }
-                        if (my_max_evals < (unsigned long long)s.nint * 25ull) {  // qagp.rs:79-81
+                        if (continue_refill) {
+                            // (nothing to do: the lane stays idle and asks again next trip)
+                        } else if (my_max_evals < (unsigned long long)s.nint * 25ull) {  // qagp.rs:79-81
                             write_result(P.out, s.idx, 0.0, F64_MAX, 0u, ST_INSUFFICIENT_ITERATION);
                         } else {
                             // ws.reserve(nint + (max_evals - nint*25)/50)   qagp.rs:83-84

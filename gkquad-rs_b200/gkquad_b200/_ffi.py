@@ -55,7 +55,10 @@ SYMBOLS = [
     "gkq_functor_eval_batch",
     "gkq_set_deferred_join", "gkq_join", "gkq_sync", "gkq_get_stats", "gkq_reset_stats", "gkq_set_profiling", "gkq_get_profile",
     "gkq_measure_fp64_peak",
+    "gkq_comm_get_unique_id", "gkq_comm_init", "gkq_comm_destroy", "gkq_comm_info", "gkq_shard_size",
+    "gkq_shard_index", "gkq_gather", "gkq_gather_range",
 ]
+GKQ_COMM_ID_BYTES = 128
 
 _lib = None
 
@@ -105,6 +108,17 @@ def lib():
     L.gkq_set_profiling.argtypes = [vp, C.c_int]
     L.gkq_get_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
     L.gkq_measure_fp64_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.gkq_comm_get_unique_id.argtypes = [vp]
+    L.gkq_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.gkq_comm_destroy.argtypes = [vp]
+    L.gkq_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.gkq_shard_size.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int64]
+    L.gkq_shard_size.restype = C.c_int64
+    L.gkq_shard_index.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64]
+    L.gkq_shard_index.restype = C.c_int64
+    L.gkq_gather.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, dp, dp, u32p, u32p, dp, dp, u32p, u32p, vp]
+    L.gkq_gather_range.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int64, dp, dp, u32p, u32p,
+                                   dp, dp, u32p, u32p, vp]
     _lib = L
     return L
 

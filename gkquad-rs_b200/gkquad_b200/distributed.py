@@ -1,10 +1,13 @@
 """Multi-GPU plumbing: batches of independent integrals shard statically across the ranks of one
-node (one process per GPU) and only the results are exchanged -- ONE all-gather of 24 bytes per
-integral (estimate f64 | delta f64 | nevals u32, status u32) over NCCL / NVLink.  There is no
-data-path collective during the computation.
+node (one process per GPU) and only the results are exchanged.  There is no data-path collective
+during the computation.
 
-torch.distributed is used for the plumbing only; with CPU tensors the same code runs over gloo
-(tests/test_distributed_cpu.py)."""
+The product path is inside the library: `init_comm` joins every rank's Engine to an NCCL
+communicator through the C ABI (gkq_comm_get_unique_id / gkq_comm_init; torch.distributed only
+carries the 128-byte id) and `Engine.gather` = gkq_gather moves 20 bytes per integral over NVLink
+and un-permutes them on the device.  `gather_results` below is the same exchange written with
+torch.distributed collectives (24 bytes per integral); with CPU tensors it runs over gloo and is how
+the host-side shard / un-permute logic is tested without GPUs (tests/test_distributed_cpu.py)."""
 from __future__ import annotations
 
 import numpy as np
@@ -69,3 +72,17 @@ def unpack_global(gathered, n_total: int, world: int, n_pad: int, block: int = B
         nev[idx] = ints[:m]
         st[idx] = ints[n_pad:n_pad + m]
     return est, dlt, nev, st
+
+
+def init_comm(engine, group=None):
+    """Join `engine` (this rank's handle) to the library's own NCCL communicator: rank 0 creates the
+    id, torch.distributed broadcasts it, every rank calls gkq_comm_init (collective)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world == 1:
+        engine.comm_init(1, 0, None)
+        return
+    box = [engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    engine.comm_init(world, rank, box[0])

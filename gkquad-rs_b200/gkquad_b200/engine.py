@@ -55,6 +55,7 @@ class Engine:
         if rc != 0:
             raise _ffi.GkqError(rc, self.L.gkq_last_error(None).decode())
         self.h = h
+        self.nranks, self.rank = 1, 0
         self._tables = {d: _ffi.functor_table(d) for d in (0, 1, 2)}
 
     def close(self):
@@ -373,6 +374,53 @@ class Engine:
             self._ptr(yp), ys, self._ptr(po), self._ptr(pv), self._ptr(est), self._ptr(dlt), self._ptr(nev),
             self._ptr(st)))
         return BatchResult(est, dlt, nev, st)
+
+    # ---- multi-GPU (gkq_comm_* / gkq_gather: NCCL inside the library) --------------------------
+    def comm_unique_id(self) -> bytes:
+        """128 bytes to hand to every rank's comm_init (made on ONE rank, carried by the host)."""
+        buf = C.create_string_buffer(_ffi.GKQ_COMM_ID_BYTES)
+        self._check(self.L.gkq_comm_get_unique_id(buf))
+        return bytes(buf.raw)
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes | None = None):
+        """Collective: one handle per GPU joins the communicator (nranks == 1 needs no id / no NCCL)."""
+        if nranks > 1:
+            assert unique_id is not None and len(unique_id) == _ffi.GKQ_COMM_ID_BYTES
+        self._comm_id = C.create_string_buffer(unique_id or b"", _ffi.GKQ_COMM_ID_BYTES)
+        self._check(self.L.gkq_comm_init(self.h, int(nranks), int(rank), self._comm_id))
+        self.nranks, self.rank = int(nranks), int(rank)
+
+    def comm_destroy(self):
+        self._check(self.L.gkq_comm_destroy(self.h))
+
+    def shard_size(self, n_total: int, rank: int | None = None, block: int = 4096) -> int:
+        return int(self.L.gkq_shard_size(int(n_total), self.nranks, self.rank if rank is None else rank, block))
+
+    def gather(self, res, n_total: int, *, root: int = 0, block: int = 4096, out=None, stream=None,
+               local_offset: int | None = None, local_count: int | None = None):
+        """gkq_gather / gkq_gather_range: `res` = (estimate, delta, nevals, status) device tensors of this
+        rank's shard (shard order).  Returns (estimate, delta, nevals, status) in GLOBAL order on the
+        receiving rank(s) (root, or every rank when root < 0), None elsewhere.  Asynchronous on `stream`
+        (default: torch's current stream)."""
+        import torch
+        est, dlt, nev, st = res
+        receiver = root < 0 or root == self.rank
+        if receiver and out is None:
+            dev = f"cuda:{self.device}"
+            out = (torch.empty(n_total, dtype=torch.float64, device=dev), torch.empty(n_total, dtype=torch.float64, device=dev),
+                   torch.empty(n_total, dtype=torch.int32, device=dev), torch.empty(n_total, dtype=torch.int32, device=dev))
+        g = out if receiver else (None, None, None, None)
+        stream = self._stream() if stream is None else stream
+        if local_offset is None:
+            self._check(self.L.gkq_gather(self.h, int(n_total), int(block), int(root), self._ptr(est), self._ptr(dlt),
+                                          self._ptr(nev), self._ptr(st), self._ptr(g[0]), self._ptr(g[1]),
+                                          self._ptr(g[2]), self._ptr(g[3]), stream))
+        else:
+            self._check(self.L.gkq_gather_range(self.h, int(n_total), int(block), int(root), int(local_offset),
+                                                int(local_count), self._ptr(est), self._ptr(dlt), self._ptr(nev),
+                                                self._ptr(st), self._ptr(g[0]), self._ptr(g[1]), self._ptr(g[2]),
+                                                self._ptr(g[3]), stream))
+        return out if receiver else None
 
     # ---- accounting -------------------------------------------------------------------------
     def set_deferred_join(self, on: bool):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GKQ_ABI_VERSION 1
+#define GKQ_ABI_VERSION 2
 
 typedef struct gkq_handle_s* gkq_handle_t;
 
@@ -101,6 +101,15 @@ typedef struct gkq_config {
  * f(inner, outer); x0/x1 are the OUTER (y) range, the range functor yields the inner (x) range and
  * points are given as (outer, inner) pairs -- the host mirrors do the swapping. */
 #define GKQ_FLAG_SWAP_XY 1
+/* Device entries only see pointers, so they cannot refuse NaN inputs for free the way the reference
+ * does when a Range / Tolerance is constructed (single/common.rs:94, single/integrator.rs:71).  With
+ * this flag a device entry first checks the range bounds and the per-integral tolerances of
+ * gkq_overrides on the device (one small kernel + ONE synchronisation of `stream`) and returns
+ * GKQ_ERR_NAN_INPUT before anything is integrated.  Without it: a NaN bound gives that integral
+ * status NanValueEncountered (QAGS: after its 17 samples; QAGP: estimate NaN, delta f64::MAX,
+ * 0 evaluations); a NaN tolerance makes every `delta <= tolerance` test false for that integral.
+ * The host entries (host pointers) always check and need no flag. */
+#define GKQ_FLAG_VALIDATE_INPUTS 2
 
 /* Fills *cfg with the reference's defaults: dim 1 -> IntegrationConfig::default(),
  * dim 2 -> IntegrationConfig2::default(). */
@@ -195,8 +204,8 @@ int gkq_integrate2_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor
  * (single/integrator.rs:69-84 called once per integral in a parameter sweep).  Each array is
  * optional (NULL = the value of `cfg` for every integral) and has n entries; the tolerance KIND
  * stays cfg->tol.kind.  max_evals[i] is clamped to cfg->max_evals, which sizes the engine's
- * interval lists.  NaN tolerances are not checked here (the reference panics,
- * single/integrator.rs:71).  For the 2-D entries max_evals[i] is the TOTAL budget of nest i
+ * interval lists.  NaN tolerances: rejected with GKQ_ERR_NAN_INPUT by the host entries and,
+ * with GKQ_FLAG_VALIDATE_INPUTS, by the device entries (the reference panics, single/integrator.rs:71).  For the 2-D entries max_evals[i] is the TOTAL budget of nest i
  * (IntegrationConfig2::max_evals, double/common.rs:18).
  * *_batch_ex: device pointers; *_batch_host_ex: host pointers. */
 typedef struct gkq_overrides {
@@ -256,6 +265,48 @@ int gkq_functor_eval_batch(gkq_handle_t h, int functor_id, int64_t n, const doub
  * other: +20 % on B200) drive two handles on two streams, as the host mirrors' BatchPipeline does. */
 int gkq_set_deferred_join(gkq_handle_t h, int enable);
 int gkq_join(gkq_handle_t h, void* stream);
+
+/* ---- multi-GPU: static shard + one gather of results -------------------
+ * replaces: nothing inside gkquad (it is single-threaded); this is what a host that runs
+ * Algorithm::integrate / Algorithm2::integrate (single/algorithm/mod.rs:16-23,
+ * double/algorithm/mod.rs:7-10) over a batch larger than one GPU binds: one process (or thread) and
+ * one handle per GPU, a STATIC block-cyclic partition of the batch and no exchange while it is
+ * integrated -- only the results travel.
+ *
+ *   partition    integral i belongs to rank (i / block) mod nranks; position j of rank r's shard is
+ *                integral gkq_shard_index(n_total, nranks, r, block, j); every rank integrates its
+ *                gkq_shard_size(..) integrals with the ordinary batch entries (heavy-tailed work --
+ *                QAGP, 2-D -- balances statically because consecutive blocks go to different ranks).
+ *   communicator gkq_comm_get_unique_id on one rank, the 128 bytes carried to the others by the
+ *                host's own means (MPI, a file, torch.distributed ...), gkq_comm_init on every rank
+ *                (collective).  NCCL is loaded at run time (libnccl.so.2; env GKQ_NCCL_LIB overrides);
+ *                nranks == 1 needs no NCCL at all.
+ *   gkq_gather   collective, asynchronous on `stream`: packs the local shard's results to 20 bytes
+ *                per integral (estimate f64 | delta f64 | nevals << 3 | status u32 -- cfg->max_evals
+ *                must stay below 2^29), moves them over NVLink (grouped ncclSend / ncclRecv to
+ *                `root`, or ncclAllGather when root < 0) and un-permutes them into GLOBAL integral
+ *                order on the receiving rank(s): g_* are device arrays of n_total entries there and
+ *                ignored elsewhere.  est / dlt / nev / st are the device arrays the shard's results
+ *                were written to (shard order).  On a side stream the gather of one batch overlaps
+ *                the kernels of the next.
+ *   gkq_gather_range  the same for shard positions [local_offset, local_offset + local_count) only
+ *                (every rank passes the same range; local_offset a multiple of 4), so that a batch
+ *                computed in chunks can be gathered chunk by chunk behind the kernels and only the
+ *                last chunk's transfer is exposed. */
+#define GKQ_COMM_ID_BYTES 128
+int gkq_comm_get_unique_id(void* id_out /* [GKQ_COMM_ID_BYTES] */);
+int gkq_comm_init(gkq_handle_t h, int nranks, int rank, const void* unique_id);
+int gkq_comm_destroy(gkq_handle_t h);
+int gkq_comm_info(gkq_handle_t h, int* nranks, int* rank);
+int64_t gkq_shard_size(int64_t n_total, int nranks, int rank, int64_t block);
+int64_t gkq_shard_index(int64_t n_total, int nranks, int rank, int64_t block, int64_t j);
+int gkq_gather(gkq_handle_t h, int64_t n_total, int64_t block, int root, const double* est,
+               const double* dlt, const uint32_t* nev, const uint32_t* st, double* g_est,
+               double* g_dlt, uint32_t* g_nev, uint32_t* g_st, void* stream);
+int gkq_gather_range(gkq_handle_t h, int64_t n_total, int64_t block, int root, int64_t local_offset,
+                     int64_t local_count, const double* est, const double* dlt, const uint32_t* nev,
+                     const uint32_t* st, double* g_est, double* g_dlt, uint32_t* g_nev,
+                     uint32_t* g_st, void* stream);
 
 /* ---- stream helpers / accounting --------------------------------------------------------- */
 int gkq_sync(gkq_handle_t h, void* stream);

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     L = _ffi.lib()
     for s in _header_symbols():
         assert hasattr(L, s), f"libgkquad_b200.so does not export {s}"
-    assert L.gkq_abi_version() == 1
+    assert L.gkq_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
