@@ -4,16 +4,24 @@
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA engine via the C ABI)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
 
-One "step" = one pass of the hot path over one batch of synthetic parameterised integrands
-(workload S1 = BASELINE.json configs[1]: 1M smooth integrands exp(-p0 x) cos(p1 x) on [0,1],
-QAGS, Tolerance::Relative(1e-10), max_evals 2000).  Weak scaling: every rank owns a block-cyclic
-shard of N x batch integrals; results stay sharded, the job ends with one NCCL gather (see _main).
+One "step" = one pass of the hot path over one batch of synthetic parameterised integrands.
+Headline (top-level keys) = BASELINE.json configs[1], workload S1: 1M smooth integrands
+exp(-p0 x) cos(p1 x) on [0,1] per GPU, QAGS, Tolerance::Relative(1e-10), max_evals 2000.  Weak
+scaling: every rank owns a block-cyclic shard of N x batch integrals; results stay sharded, the job
+ends with one gather to rank 0 through the library's own NCCL path (gkq_gather_range, chunked behind
+the kernels of the last batch).
 
-Prints ONE JSON line on rank 0 (see DESIGN.md section 7 for every field).
+The `configs` block of the same JSON line carries every BASELINE.json configuration at full size
+(cfg-1 `simple` CPU row; cfg-3 P0 + P1; cfg-4 I0 + I1; cfg-5 D0 + D1 at 100k, block-cyclic sharded
+across the ranks and gathered every step), each with value, ms_per_step, roofline, e2e, cpu_baseline
+and parity_vs_cpu computed on the outputs the TIMED region wrote.
+
+Prints ONE JSON line on rank 0 (DESIGN.md section 7 describes every field).
 """
 from __future__ import annotations
 
 import argparse
+import csv
 import json
 import os
 import subprocess
@@ -31,6 +39,11 @@ for p in (ROOT, ROOT / "gkquad-rs_b200"):
 
 METRIC = "converged integrals/sec (QAGS, rel_tol 1e-10)"
 UNIT = "integrals/s"
+ALGO = {"AUTO": 0, "QAGS": 1, "QAGP": 2}
+SHARD_BLOCK = 4096
+# (name in `configs`, workload, integrals: per GPU for 1-D / in total for 2-D)
+SECONDARY = [("cfg3_P0", "P0", 1 << 20), ("cfg3_P1", "P1", 1 << 20), ("cfg4_I0", "I0", 1 << 20),
+             ("cfg4_I1", "I1", 1 << 20), ("cfg5_D0", "D0", 100_000), ("cfg5_D1", "D1", 100_000)]
 
 
 def parse():
@@ -43,29 +56,35 @@ def parse():
     ap.add_argument("--batch", type=int, default=1 << 20, help="integrals per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--configs", default="all", help="'all', 'none' or a comma list of names of the `configs` block")
     ap.add_argument("--e2e-threads", type=int, default=2,
                     help="host threads (one handle each) that make the blocking host-entry calls of the e2e leg")
     ap.add_argument("--pipeline-depth", type=int, default=3,
                     help="handles / streams the independent batches alternate between (1 = one handle, one stream)")
-    ap.add_argument("--p2p-gather", action="store_true",
-                    help="N > 1: also time the gather fused into the kernels (result stores go over NVLink into "
-                         "rank 0's HBM through torch's symmetric memory); opt-in because its rendezvous is collective")
+    ap.add_argument("--gather-chunks", type=int, default=4,
+                    help="N > 1: the last batch is computed and gathered in this many chunks (only the last chunk's transfer is exposed)")
     return ap.parse_args()
 
 
-def shard_params(W, batch, rank, world, offset=0):
-    """Block-cyclic shard (SURVEY.md section 8e) of the global batch of world*batch integrals;
-    every rank regenerates its own parameters from the counter-based generator (`offset` shifts
-    the counters: a different batch of the same family)."""
+def workload_config(W, n, world):
+    """The `config` object: identical in both arms (ours / --impl reference) for the same N."""
+    return {"workload": f"{W.name}: {W.description}; {W.algo}, {W.tol}, max_evals {W.max_evals}",
+            "batch_per_gpu": n, "global_batch": n * world, "parallelism": f"shard{world}",
+            "l2": "8 independent batches cycled (320 MB of inputs+outputs > 126 MB L2); no flush needed"}
+
+
+def shard_params(W, batch, rank, world, offset=0, total=None):
+    """Block-cyclic shard of the global batch; every rank regenerates its own
+    parameters from the counter-based generator (`offset` shifts the counters: another batch of the
+    same family).  total = global batch size (default world * batch)."""
     from gkquad_b200.workloads import block_cyclic_shard
-    idx = block_cyclic_shard(batch * world, rank, world) + offset
-    # the generator is indexed by the global integral number: build per-block and concatenate
+    idx = block_cyclic_shard(batch * world if total is None else total, rank, world, SHARD_BLOCK)
     blocks = []
-    B = 4096
-    for s in range(0, len(idx), B):
-        start = int(idx[s])
-        cnt = min(B, len(idx) - s)
-        blocks.append(W.make_params(start, cnt))
+    B = SHARD_BLOCK
+    for s in range(0, len(idx), B):  # the generator is indexed by the global integral number
+        blocks.append(W.make_params(int(idx[s]) + offset, min(B, len(idx) - s)))
+    if not blocks:
+        return W.make_params(0, 0), idx
     return np.ascontiguousarray(np.concatenate(blocks, axis=1)), idx
 
 
@@ -134,62 +153,101 @@ def tol_to_oracle(t):
             3: ("abs_and_rel", t.abs_tol, t.rel_tol)}[t.kind]
 
 
-def cpu_leg(W, p, n, seconds_target=6.0, nthreads=0):
-    """The reference's CPU implementation of the path = the golden-vector-pinned oracle port
-    (gkquad itself needs a Rust toolchain, absent here), all host threads, on the same batch."""
+# ---- the reference's CPU implementation of the path = the golden-vector-pinned oracle port ---------
+def oracle_call(W, p, n, nthreads=0):
+    """One pass of the oracle over a batch of workload W (1-D or 2-D); returns the result dict."""
     from oracle import oracle as O
-    algo = {"AUTO": 0, "QAGS": 1, "QAGP": 2}[W.algo]
-    kw = dict(params=p, tol=tol_to_oracle(W.tol), max_evals=W.max_evals, n=n, nthreads=nthreads)
-    if W.points and W.points != "param0":
+    kw = dict(tol=tol_to_oracle(W.tol), max_evals=W.max_evals, n=n, nthreads=nthreads)
+    if W.dim == 1:
+        if W.points == "param0":
+            kw.update(pts_offsets=np.arange(n + 1, dtype=np.int64), points=np.ascontiguousarray(p[0]))
+        elif W.points:
+            kw["points"] = W.points
+        return O.integrate_batch(ALGO[W.algo], W.functor, W.a, W.b, params=p, **kw)
+    if W.points == "param01":
+        kw.update(pts_offsets=np.arange(n + 1, dtype=np.int64), points=np.ascontiguousarray(p.T))
+    elif W.points:
         kw["points"] = W.points
-    O.integrate_batch(algo, W.functor, W.a, W.b, **{**kw, "n": min(n, 65536), "params": p[:, :min(n, 65536)]})
+    return O.integrate2_batch(ALGO[W.algo], W.functor, W.yrange, W.a, W.b, fparams=p, yparams=W.yparams, **kw)
+
+
+def cpu_leg(W, p, n, seconds_target=6.0, min_reps=3, max_reps=50):
+    """The oracle on all host threads over the same batch: (converged integrals/s of the best pass,
+    threads, passes, last result)."""
+    from oracle import oracle as O
+    m = min(n, 65536)
+    oracle_call(W, np.ascontiguousarray(p[:, :m]), m)  # warm-up (page faults, thread pool)
     reps, t0, best = 0, time.perf_counter(), 1e30
-    conv = 0
     while True:
         t1 = time.perf_counter()
-        r = O.integrate_batch(algo, W.functor, W.a, W.b, **kw)
-        dt = time.perf_counter() - t1
-        best = min(best, dt)
-        conv = int((r["status"] == 0).sum())
+        r = oracle_call(W, p, n)
+        best = min(best, time.perf_counter() - t1)
         reps += 1
-        if reps >= 3 and time.perf_counter() - t0 > seconds_target:
+        if (reps >= min_reps and time.perf_counter() - t0 > seconds_target) or reps >= max_reps:
             break
-        if reps >= 50:
-            break
-    return conv / best, O.num_threads() if nthreads == 0 else nthreads, reps, r
+    return int((r["status"] == 0).sum()) / best, O.num_threads(), reps, r
+
+
+def parity(W, g_est, g_nev, g_st, ref):
+    """Mismatch counts of engine outputs against the oracle on the same integrals."""
+    est = ref["estimate"]
+    tol_abs = np.abs(W.tol.to_abs(np.abs(est)))
+    ok = ref["status"] == 0
+    both_nan = np.isnan(g_est) & np.isnan(est)
+    diff = np.where(both_nan, 0.0, np.abs(g_est - est))
+    return {"n": int(len(est)), "status_mismatch": int((g_st != ref["status"]).sum()),
+            "nevals_mismatch": int((g_nev != ref["nevals"]).sum()),
+            "out_of_tolerance": int((diff[ok] > tol_abs[ok] + 1e-300).sum()),
+            "bit_equal_estimates": int(((g_est == est) | both_nan).sum())}
+
+
+def cfg1_simple():
+    """BASELINE configs[0]: the reference's own CPU-runnable case -- `simple`: x^2 on [0,1] with the
+    Integrator defaults (benches/single.rs:10-17; README.md:45 quotes 88.351 ns per call on an
+    i5-8265U).  The oracle's ns/call on ONE thread of this host, in a compiled loop."""
+    from oracle import oracle as O
+    n = 1 << 20
+    t_best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        r = O.integrate_batch(0, "square", 0.0, 1.0, tol=("abs_or_rel", 1.49e-8, 1.49e-8), max_evals=2000, n=n, nthreads=1)
+        t_best = min(t_best, time.perf_counter() - t0)
+    one = O.integrate_one(0, "square", 0.0, 1.0)
+    return {"workload": "simple: x^2 on [0,1], Integrator defaults (AUTO -> QAGS, AbsOrRel(1.49e-8, 1.49e-8), max_evals 2000)",
+            "impl": "CPU oracle port, 1 thread, compiled loop over 2^20 calls",
+            "ns_per_call": t_best / n * 1e9, "reference_readme_ns_per_call": 88.351,
+            "reference_readme_cpu": "i5-8265U (README.md:45)",
+            "result": [one["estimate"], one["delta"], int(one["nevals"]), int(one["status"])],
+            "all_calls_identical": bool((r["nevals"] == 17).all() and (r["status"] == 0).all()
+                                        and (r["estimate"] == one["estimate"]).all())}
 
 
 def run_reference(args, rank, world, real_stdout):
-    """--impl reference: the reference's CPU path on the host cores (rank 0 only)."""
+    """--impl reference: the reference's CPU path on the host cores (rank 0 only), on the global batch
+    of our arm's config."""
     if rank != 0:
         return
     from gkquad_b200.workloads import WORKLOADS
-    W = WORKLOADS[args.workload]
-    n = args.batch
-    p = W.make_params(0, n)
     from oracle import oracle as O
-    algo = {"AUTO": 0, "QAGS": 1, "QAGP": 2}[W.algo]
-    kw = dict(params=p, tol=tol_to_oracle(W.tol), max_evals=W.max_evals, n=n, nthreads=0)
-    if W.points and W.points != "param0":
-        kw["points"] = W.points
-    for _ in range(max(1, args.warmup)):
-        r = O.integrate_batch(algo, W.functor, W.a, W.b, **kw)
+    W = WORKLOADS[args.workload]
+    n = args.batch * world
+    p = W.make_params(0, n)
+    for _ in range(max(1, min(args.warmup, 3))):
+        r = oracle_call(W, p, n)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r = O.integrate_batch(algo, W.functor, W.a, W.b, **kw)
+        r = oracle_call(W, p, n)
     dt = (time.perf_counter() - t0) / args.steps
-    conv = int((r["status"] == 0).sum())
-    val = conv / dt
+    val = int((r["status"] == 0).sum()) / dt
     cores = O.num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{W.name}: {W.description}; {W.algo}, {W.tol}, max_evals {W.max_evals}",
-                   "batch": n, "parallelism": f"{cores} host threads"},
+        "config": workload_config(W, args.batch, world),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"the full {n}-integral batch per step (golden-vector-pinned C++ port of "
-                                   "gkquad's CPU path; gkquad itself needs a Rust toolchain, absent here)"},
+                         "sample": f"the full {n}-integral global batch per step, {cores} host threads (golden-vector-pinned "
+                                   "C++ port of gkquad's CPU path; gkquad itself needs a Rust toolchain, absent here)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -211,6 +269,31 @@ def emit(real_stdout, line):
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
+def ncu_traffic(kernel_regex):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel whose ncu name matches
+    `kernel_regex`, read from the newest committed `ncu --set full` raw CSV under profiles/ that has
+    it (bytes; None when no capture of that kernel is committed)."""
+    import re
+    best = None
+    for f in sorted((ROOT / "profiles").glob("ncu_*_raw.csv"), key=lambda q: q.name, reverse=True):
+        try:
+            rows = list(csv.reader(open(f)))
+            h = rows[0]
+            ik, ir, iw = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+            units = rows[1]
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            for row in rows[2:]:
+                if re.search(kernel_regex, row[ik]):
+                    best = {"bytes": float(row[ir]) * scale.get(units[ir], 1.0) + float(row[iw]) * scale.get(units[iw], 1.0),
+                            "read_bytes": float(row[ir]) * scale.get(units[ir], 1.0), "source": f"profiles/{f.name}"}
+                    break
+        except Exception:
+            continue
+        if best:
+            return best
+    return None
+
+
 def _main(args, real_stdout):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -229,96 +312,112 @@ def _main(args, real_stdout):
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     import gkquad_b200 as gk
+    from gkquad_b200 import distributed as D
     from gkquad_b200.workloads import WORKLOADS
 
     W = WORKLOADS[args.workload]
-    assert W.dim == 1, "bench.py times the 1-D hot path (the 2-D configs are parity-test cases)"
+    assert W.dim == 1, "the headline is a 1-D workload; the 2-D configurations run in the `configs` block"
     n = args.batch
-    algo = {"AUTO": 0, "QAGS": 1, "QAGP": 2}[W.algo]
+    algo = ALGO[W.algo]
     # throughput mode: `depth` handles on `depth` streams, batch k on lane k % depth (BatchPipeline);
-    # lane 0's handle also serves the per-kernel profiling pass and the host entry (e2e)
+    # lane 0's handle also serves the per-kernel profiling pass, the host entry (e2e) and the gathers
     pipe = gk.BatchPipeline(local_rank, depth=args.pipeline_depth)
     DEPTH = pipe.depth
     eng = pipe.engines[0]
-    from gkquad_b200 import distributed as D
+    D.init_comm(eng)  # gkq_comm_init: the library's own NCCL communicator (torch only carries the id)
 
     # 2 groups x G independent batches are cycled through, so that a step never finds its inputs or
     # outputs in the 126 MB L2 (8 x (16 MB in + 24 MB out) = 320 MB): "inputs larger than L2".
-    # For N > 1 the results of a group are gathered with ONE all_gather (24 B/integral, packed) on a
-    # side stream while the other group is being computed.
     G, NGROUPS = 4, 2
     NSETS = G * NGROUPS
-    groups = []
     sets = []
-    for gi in range(NGROUPS):
-        packed = torch.zeros(G, 3 * n, dtype=torch.float64, device=dev)
-        gathered = torch.empty(world, G, 3 * n, dtype=torch.float64, device=dev) if world > 1 else None
-        groups.append(dict(packed=packed, gathered=gathered, done=None))
-        for si in range(G):
-            s = gi * G + si
-            p_host, idx = shard_params(W, n, rank, world, offset=s * n * world)
-            kw = dict(algo=algo, tol=W.tol, max_evals=W.max_evals, n=n)
-            if W.points and W.points != "param0":
-                kw["points"] = W.points
-            elif W.points == "param0":
-                from gkquad_b200.workloads import csr_points_from_param0
-                off, pts = csr_points_from_param0(p_host)
-                kw["pts_offsets"] = torch.as_tensor(off, device=dev)
-                kw["pts"] = torch.as_tensor(pts, device=dev)
-            # results are written straight into the packed gather buffer: est | delta | nevals,status
-            row = packed[si]
-            ints = row[2 * n:].view(torch.int32)
-            out = (row[:n], row[n:2 * n], ints[:n], ints[n:])
-            p_dev = torch.as_tensor(p_host, device=dev)
-            # the call is marshalled once (an Integrator owns integrand + config and is run many times)
-            plan = pipe.plan_batch(s % DEPTH, W.functor, W.a, W.b, p_dev, out=out, **kw)
-            sets.append(dict(p_host=p_host, p_dev=p_dev, kw=kw, plan=plan, out=out, group=gi, lane=s % DEPTH))
+
+    def plan_kw(p_host):
+        kw = dict(algo=algo, tol=W.tol, max_evals=W.max_evals)
+        if W.points and W.points != "param0":
+            kw["points"] = W.points
+        elif W.points == "param0":
+            from gkquad_b200.workloads import csr_points_from_param0
+            off, pts = csr_points_from_param0(p_host)
+            kw["pts_offsets"] = torch.as_tensor(off, device=dev)
+            kw["pts"] = torch.as_tensor(pts, device=dev)
+        return kw
+
+    for s in range(NSETS):
+        p_host, idx = shard_params(W, n, rank, world, offset=s * n * world)
+        kw = dict(plan_kw(p_host), n=n)
+        out = (torch.zeros(n, dtype=torch.float64, device=dev), torch.zeros(n, dtype=torch.float64, device=dev),
+               torch.zeros(n, dtype=torch.int32, device=dev), torch.zeros(n, dtype=torch.int32, device=dev))
+        p_dev = torch.as_tensor(p_host, device=dev)
+        # the call is marshalled once (an Integrator owns integrand + config and is run many times)
+        plan = pipe.plan_batch(s % DEPTH, W.functor, W.a, W.b, p_dev, out=out, **kw)
+        sets.append(dict(p_host=p_host, p_dev=p_dev, kw=kw, plan=plan, out=out, lane=s % DEPTH))
     p_host = sets[0]["p_host"]
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    n_total = n * world
+    root_out = None
+    if world > 1 and rank == 0:
+        root_out = (torch.empty(n_total, dtype=torch.float64, device=dev), torch.empty(n_total, dtype=torch.float64, device=dev),
+                    torch.empty(n_total, dtype=torch.int32, device=dev), torch.empty(n_total, dtype=torch.int32, device=dev))
+    # the last batch of the job is computed in chunks, each gathered behind the next one's kernels
+    CH = max(1, args.gather_chunks) if world > 1 else 1
+    chunk_plans = {}
 
-    def step(k, gather):
+    def chunk_plan(s, c):
+        """Plan of chunk c of set s: the same arrays, positions [lo, hi) (offsets are multiples of 4)."""
+        key = (s, c)
+        if key not in chunk_plans:
+            S = sets[s]
+            step = (n // CH + 3) // 4 * 4
+            lo, hi = c * step, min(n, (c + 1) * step)
+            kw = dict(S["kw"], n=hi - lo)
+            if "pts_offsets" in kw:
+                kw["pts_offsets"] = (kw["pts_offsets"][lo:hi + 1] - kw["pts_offsets"][lo]).contiguous()
+                kw["pts"] = kw["pts"][int(S["kw"]["pts_offsets"][lo]):int(S["kw"]["pts_offsets"][hi])].contiguous()
+            lane = c % DEPTH
+            pl = pipe.plan_batch(lane, W.functor, W.a, W.b, S["p_dev"][:, lo:hi].contiguous(),
+                                 out=tuple(t[lo:hi] for t in S["out"]), **kw)
+            chunk_plans[key] = (pl, lane, lo, hi)
+        return chunk_plans[key]
+
+    def gather_set(s, stream_obj, lo=None, hi=None):
+        """gkq_gather / gkq_gather_range of set s's results to rank 0 on `stream_obj`."""
+        kw = {} if lo is None else dict(local_offset=lo, local_count=hi - lo)
+        eng.gather(sets[s]["out"], n_total, root=0, block=SHARD_BLOCK, out=root_out, stream=stream_obj.cuda_stream, **kw)
+
+    def step(k, per_step_gather=False):
         """One pass of the hot path over one batch: the rank integrates its shard and leaves the results
-        in its own HBM.  With `gather` (N > 1) every G-th step also hands its group to the side stream:
-        finish the group's stragglers (join) and all_gather the packed results, while the next group
-        is computed."""
-        s = k % NSETS
-        S = sets[s]
-        Gp = groups[S["group"]]
-        if s % G == 0 and Gp["done"] is not None:  # the gather that last read this group must be over
-            for ls in pipe.streams:
-                ls.wait_event(Gp["done"])
-            Gp["done"] = None
+        in its own HBM.  per_step_gather (N > 1): the batch is also gathered to rank 0 on the side
+        stream while the next batches are computed."""
+        S = sets[k % NSETS]
         pipe.run(S["plan"], S["lane"])
-        if gather and s % G == G - 1:
-            for ls in pipe.streams:
-                ev = torch.cuda.Event()
-                ev.record(ls)
-                comm.wait_event(ev)
-            with torch.cuda.stream(comm):
-                for e in pipe.engines:
-                    e.join()  # the gather also waits for the deferred remainders of the group
-                dist.all_gather_into_tensor(Gp["gathered"], Gp["packed"])
-                Gp["done"] = torch.cuda.Event()
-                Gp["done"].record()
+        if per_step_gather:
+            ev = torch.cuda.Event()
+            ev.record(pipe.streams[S["lane"]])
+            comm.wait_event(ev)
+            pipe.engines[S["lane"]]._check(pipe.engines[S["lane"]].L.gkq_join(pipe.engines[S["lane"]].h, comm.cuda_stream))
+            gather_set(k % NSETS, comm)
+
+    def last_step_chunked(k):
+        """The job's last batch: CH chunks on alternating lanes; chunk c is gathered to rank 0 on the
+        side stream (gkq_gather_range) while chunk c + 1 is integrated."""
+        s = k % NSETS
+        for c in range(CH):
+            pl, lane, lo, hi = chunk_plan(s, c)
+            pipe.run(pl, lane)
+            ev = torch.cuda.Event()
+            ev.record(pipe.streams[lane])
+            comm.wait_event(ev)
+            e = pipe.engines[lane]
+            e._check(e.L.gkq_join(e.h, comm.cuda_stream))  # the chunk's stragglers, then its gather
+            gather_set(s, comm, lo, hi)
 
     def join():
         pipe.join()  # outstanding deferred remainders; the current stream waits for every lane
         if world > 1:
             torch.cuda.current_stream().wait_stream(comm)
 
-    def final_gather(k_last):
-        """north_star's 'final NCCL gather of results and status': the last batch, to every rank."""
-        S = sets[k_last % NSETS]
-        row = groups[S["group"]]["packed"][(k_last % NSETS) % G]
-        dist.all_gather_into_tensor(last_gathered, row)
-
-    # throughput pipelining of independent batches: the latency-bound remainders of several batches
-    # are finished by one launch (deferred join); every step is complete before the end event
-    last_gathered = torch.empty(world, 3 * n, dtype=torch.float64, device=dev) if world > 1 else None
-
     steps = args.steps
-    if world > 1 and steps % G:
-        steps += G - steps % G  # whole groups (the per-step-gather leg gathers group-wise)
     # nvidia-smi is started BEFORE the warm-up: while it attaches to the driver, CUDA launches of this
     # process stall for milliseconds, which must not fall into the timed region
     sampler = ClockSampler(local_rank)
@@ -328,15 +427,19 @@ def _main(args, real_stdout):
     # (at least two deferred-join cycles of 8 batches per lane: every scratch buffer has reached its
     # steady-state size before the timed region)
     for k in range(max(18 * DEPTH, 2 * NSETS, args.warmup, 3)):
-        step(k, world > 1)
+        step(k)
     join()
     if world > 1:
-        final_gather(0)
+        for s in range(NSETS):  # chunk plans are marshalled (and their scratch sized) outside the region
+            for c in range(CH):
+                chunk_plan(s, c)
+        last_step_chunked((steps - 1) % NSETS)
+        join()
     torch.cuda.synchronize()
 
     # ---- timed region: EXACTLY K steps between barrier + synchronize, device-timed -------------
     # The path shards with no data-path collective: each rank's results stay in its HBM; the job ends
-    # with the final gather of the last batch (inside the region).
+    # with the gather of the last batch to rank 0 (inside the region).
     pipe.reset_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
@@ -345,12 +448,13 @@ def _main(args, real_stdout):
     e0.record()
     pipe.fork()  # the lanes start behind the start event
     t_region0 = time.perf_counter()
-    for k in range(steps):
-        step(k, False)
-    t_enq = (time.perf_counter() - t_region0) / steps
-    join()  # ... and the end event behind every lane
+    for k in range(steps - 1 if world > 1 else steps):
+        step(k)
     if world > 1:
-        final_gather(steps - 1)
+        comm.wait_stream(torch.cuda.current_stream())
+        last_step_chunked(steps - 1)
+    t_enq = (time.perf_counter() - t_region0) / steps
+    join()  # ... and the end event behind every lane (and the side stream)
     e1.record()
     torch.cuda.synchronize()
     t_region1 = time.perf_counter()
@@ -359,27 +463,38 @@ def _main(args, real_stdout):
     launches = pipe.kernel_launches()  # our kernels only (NCCL's are not counted)
     total_ms = e0.elapsed_time(e1)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    # snapshot of what the timed region wrote (the profiling pass below re-runs set 0)
+    timed_out = tuple(x.clone() for x in sets[0]["out"])
     conv = sum(float((S["out"][3] == 0).sum().item()) for S in sets) / NSETS  # mean per step
     conv_local = torch.tensor([conv], dtype=torch.float64, device=dev)
+    gathered_ok = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(conv_local, op=dist.ReduceOp.SUM)
+        if rank == 0:  # what arrived on rank 0 is what rank 0 itself computed for its shard
+            idx0 = torch.as_tensor(D.shard_indices(n_total, 0, world, SHARD_BLOCK), device=dev)
+            mine = sets[(steps - 1) % NSETS]["out"]
+            gathered_ok = bool(torch.equal(root_out[0][idx0], mine[0]) and torch.equal(root_out[3][idx0], mine[3]))
     total_ms = float(t.item())
     converged = float(conv_local.item())
     ms_per_step = total_ms / steps
     value = converged / (ms_per_step * 1e-3)
     clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
 
-    # ---- N > 1 only: the same K steps with EVERY batch gathered to every rank (group-wise, on a side
-    # stream).  Reported next to `value`: at this per-GPU rate a full gather needs 24 B x 6e9/s x (N-1)
-    # of NVLink ingress per GPU, which passes the 900 GB/s of one GPU between N = 4 and N = 8.
+    # ---- N > 1 only: the same K steps with EVERY batch gathered to rank 0 (gkq_gather on a side
+    # stream, 20 B per integral).  Rank 0 then receives 20 B x (N - 1) x the per-GPU rate: at N = 8 that
+    # is above what one GPU's NVLink ingress carries, so this figure is link-bound, not kernel-bound.
     per_step_gather = None
     if world > 1:
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for k in range(NSETS):
+            step(k, True)
+        join()
         dist.barrier()
         torch.cuda.synchronize()
         g0.record()
         pipe.fork()
+        comm.wait_stream(torch.cuda.current_stream())
         for k in range(steps):
             step(k, True)
         join()
@@ -389,66 +504,16 @@ def _main(args, real_stdout):
         tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
         dist.all_reduce(tg, op=dist.ReduceOp.MAX)
         ms_g = float(tg.item()) / steps
+        ingress = 20.0 * n * (world - 1) / (ms_g * 1e-3) / 1e9
         per_step_gather = {"value": converged / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g,
-                           "gathered_bytes_per_step_per_gpu": int(24 * n * world),
-                           "note": "every batch all_gathered (24 B/integral) inside the timed region, group-wise on a "
-                                   "side stream; bound by NVLink ingress, not by the integration kernels"}
+                           "root_ingress_GBps": ingress, "bytes_per_integral": 20,
+                           "link_bound_ms_per_step": 20.0 * n * (world - 1) / 770e9 * 1e3}
     torch.cuda.synchronize()
     for e in pipe.engines:
         e.set_deferred_join(False)
     p_dev, kw = sets[0]["p_dev"], sets[0]["kw"]
     est, dlt, nev, st = sets[0]["out"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # L2 flush for the profiling pass
-
-    # ---- N > 1 only: the gather fused into the kernels -- every rank's kernels store their results
-    # straight into RANK 0's buffer over NVLink (peer mapping from torch's symmetric memory), so the
-    # transfer overlaps the math store by store and no collective kernel runs at all.
-    p2p_gather = None
-    if world > 1 and args.p2p_gather:
-        try:
-            import torch.distributed._symmetric_memory as symm
-            sbuf = symm.empty((NSETS, world, 3 * n), dtype=torch.float64, device=dev)
-            hdl = symm.rendezvous(sbuf, dist.group.WORLD)
-            root = hdl.get_buffer(0, (NSETS, world, 3 * n), torch.float64)
-            pplans = []
-            for s_i, S in enumerate(sets):
-                row = root[s_i, rank]
-                ints = row[2 * n:].view(torch.int32)
-                pplans.append(eng.plan_batch(W.functor, W.a, W.b, S["p_dev"],
-                                             out=(row[:n], row[n:2 * n], ints[:n], ints[n:]), **S["kw"]))
-            eng.set_deferred_join(True)
-            for k in range(2 * NSETS):
-                pplans[k % NSETS].run()
-            eng.join()
-            torch.cuda.synchronize()
-            hdl.barrier()
-            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            dist.barrier()
-            torch.cuda.synchronize()
-            q0.record()
-            for k in range(steps):
-                pplans[k % NSETS].run()
-            eng.join()
-            q1.record()
-            torch.cuda.synchronize()
-            hdl.barrier()  # every rank's stores have landed on rank 0
-            dist.barrier()
-            tq = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device=dev)
-            dist.all_reduce(tq, op=dist.ReduceOp.MAX)
-            ms_q = float(tq.item()) / steps
-            landed = None
-            if rank == 0:  # what arrived on rank 0 is what the ranks computed
-                ints0 = sbuf[0, :, 2 * n:].reshape(world, -1).view(torch.int32)
-                landed = float((ints0[:, n:2 * n] == 0).sum().item())
-            eng.set_deferred_join(False)
-            p2p_gather = {"value": converged / (ms_q * 1e-3), "unit": UNIT, "ms_per_step": ms_q,
-                          "converged_seen_on_rank0_last_batch": landed,
-                          "note": "every batch gathered to rank 0 by the integration kernels themselves: their result "
-                                  "stores go over NVLink into rank 0's HBM (symmetric-memory peer mapping), no "
-                                  "collective kernel; bound by rank 0's NVLink ingress for N > 6"}
-        except Exception as exc:  # symmetric memory not available on this box
-            p2p_gather = {"unavailable": repr(exc)[:200]}
-            eng.set_deferred_join(False)
 
     # ---- per-kernel profile (separate pass, events around every kernel on the launch stream) ----
     eng.set_profiling(True)
@@ -462,163 +527,330 @@ def _main(args, real_stdout):
     eng.set_profiling(False)
     eng.sync()
     stats = eng.stats()
-    nev_h = nev.cpu().numpy().astype(np.int64)
+    nev_h = timed_out[2].cpu().numpy().astype(np.int64)
+    fid = eng.functor(1, W.functor)[0]
     fl_eval = eng.functor(1, W.functor)[3]
     F_t = 6.0 if not (np.isfinite(W.a) and np.isfinite(W.b)) else 0.0
     w_eval = fl_eval + F_t + 8.0  # W_i = nevals_i * (F_f + F_t + 8)
-    n25 = stats["last_survivors_qk25"]
-    cl, c2 = stats["last_chain_loop"], stats["last_chain_step2"]
-    evals_by_kernel = {}
-    if W.algo == "QAGS":
-        rest = int(nev_h.sum()) - 17 * n - 25 * n25 - 50 * (cl[0] + cl[1])
-        tail_share = [c2[k] / max(1, c2[0] + c2[1]) for k in range(2)]
-        evals_by_kernel = {"k_qags_init<qk17>": 17 * n, "k_qags_init<qk25>": 25 * n25,
-                           "k_qags_first[0]": 50 * cl[0], "k_qags_first[1]": 50 * cl[1],
-                           "k_adaptive<QAGS>[0]": int(rest * tail_share[0]),
-                           "k_adaptive<QAGS>[1]": int(rest * tail_share[1])}
-    else:
-        evals_by_kernel = {"k_adaptive<QAGP>": int(nev_h.sum())}
+    evals_by_kernel = kernel_evals(W, n, nev_h, stats)
     kernels = []
     for name, v in prof_acc.items():
         ms = float(np.mean(v))
         fl = evals_by_kernel.get(name, 0) * w_eval
-        kernels.append({"kernel": name, "ms": ms, "evals": evals_by_kernel.get(name, 0),
+        kernels.append({"kernel": name, "ms": ms, "evals": int(evals_by_kernel.get(name, 0)),
                         "tflops": fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0})
     peak_flops, peak_ms = eng.measure_fp64_peak(5)
-    dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
+    dom = max(kernels, key=lambda k: k["ms"] if k["evals"] else 0.0) if kernels else None
     whole_tflops = float(nev_h.sum()) * w_eval / (ms_per_step * 1e-3) / 1e12
     roofline = None
     if dom:
+        traffic = ncu_traffic(ncu_name_regex(dom["kernel"], fid))
         roofline = {
             "bound": "fp64", "kernel": dom["kernel"], "achieved": dom["tflops"], "peak": peak_flops / 1e12,
             "unit": "TFLOP/s", "frac": dom["tflops"] / (peak_flops / 1e12),
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of that kernel, from the ncu
-            # --set full capture of this workload (profiles/ncu_S1_kernels_r01d_raw.csv: 37.9 MB read +
-            # 21.1 MB written, against 16.8 MB of parameters in and ~21 MB of results / parked state /
-            # worklists out: partial-sector result stores make L2 fetch the rest of their lines); bytes
-            "traffic": 59.0e6 if (args.workload == "S1" and n == 1 << 20 and dom["kernel"] == "k_qags_init<qk17>") else None,
-            "peak_source": "measured in this run: dependent-chain DFMA micro-kernel over all SMs "
-                           "(MEASURED_PEAKS.json carries no FP64 figure; BASELINE.md section 3)",
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of that kernel, read from the
+            # committed ncu --set full capture (profiles/ncu_*_raw.csv) by kernel name; bytes
+            "traffic": traffic["bytes"] if traffic else None,
+            "traffic_source": traffic["source"] if traffic else None,
+            "algorithmic_bytes": int(n * (8 * p_host.shape[0] + 24)),
+            "peak_source": "measured in this run: dependent-chain DFMA micro-kernel over all SMs (MEASURED_PEAKS.json has no FP64 figure)",
             "flops_per_eval": w_eval, "kernels": kernels,
             "whole_step": {"achieved": whole_tflops, "frac": whole_tflops / (peak_flops / 1e12)},
-            "hbm": {"algorithmic_bytes_per_step": int(n * (8 * p_host.shape[0] + 24)),
-                    "note": "HBM is two orders of magnitude from binding (SURVEY.md section 8d)",
-                    # north_star's "worklist compaction pass" is not a pass here: survivors are appended to
-                    # the worklists by warp-aggregated atomics inside the rule kernels (4 B written per
-                    # survivor, 4 B read back by the consumer kernel)
-                    "compaction": {"survivor_ids_bytes_per_step": int(8 * (n25 + cl[0] + cl[1])),
-                                   "survivors_qk25": int(n25), "survivors_loop": int(cl[0] + cl[1]),
-                                   "note": "fused into k_qags_init / k_qags_first (ballot + popc + one atomic per "
-                                           "warp per list); removing the appends altogether shortens "
-                                           "k_qags_init<qk17> by 4 % (profiles/S1_r01.md)"}},
         }
 
     # ---- e2e: the public host entry (gkq_integrate_batch_host) with pinned host buffers ----------
     e2e = None
     if not args.no_e2e:
-        ph = torch.as_tensor(p_host).pin_memory()
-        oe = torch.empty(n, dtype=torch.float64).pin_memory()
-        od = torch.empty(n, dtype=torch.float64).pin_memory()
-        on = torch.empty(n, dtype=torch.int32).pin_memory()
-        os_ = torch.empty(n, dtype=torch.int32).pin_memory()
-        out = (oe.numpy(), od.numpy(), on.numpy().view(np.uint32), os_.numpy().view(np.uint32))
-        kwh = dict(algo=algo, tol=W.tol, max_evals=W.max_evals, n=n, out=out)
-        if W.points and W.points != "param0":
-            kwh["points"] = W.points
-        if W.points != "param0":
-            # `--e2e-threads` host threads, each with its own handle and its own pinned result
-            # buffers, make the blocking call in turn (ctypes releases the GIL): the H2D of one call
-            # overlaps the D2H of the other.  Every call still copies its step's inputs in and its
-            # results out inside the timed region.
-            nth = max(1, min(args.e2e_threads, DEPTH))
-            hplans, houts = [], []
-            for t in range(nth):
-                if t == 0:
-                    o_t = out
-                else:
-                    bufs = (torch.empty(n, dtype=torch.float64).pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory(),
-                            torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory())
-                    houts.append(bufs)
-                    o_t = (bufs[0].numpy(), bufs[1].numpy(), bufs[2].numpy().view(np.uint32), bufs[3].numpy().view(np.uint32))
-                hplans.append(pipe.engines[t].plan_batch(W.functor, W.a, W.b, ph.numpy(), **dict(kwh, out=o_t)))
-            for hp_ in hplans:
-                for _ in range(3):
-                    hp_.run()
-            hplan = hplans[0]
-            if world > 1:
-                dist.barrier()
-            e2e_steps = args.steps - args.steps % nth if args.steps >= nth else nth
+        e2e = e2e_leg_1d(args, pipe, W, sets[0]["p_host"], n, world, dev, steps)
 
-            def host_worker(t):
-                for _ in range(e2e_steps // nth):
-                    hplans[t].run()
-            workers = [threading.Thread(target=host_worker, args=(t,)) for t in range(1, nth)]
-            t0 = time.perf_counter()
-            for w_ in workers:
-                w_.start()
-            host_worker(0)
-            for w_ in workers:
-                w_.join()
-            dt = (time.perf_counter() - t0) / e2e_steps
-            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            conv_e = float((out[3] == 0).sum())
-            ce = torch.tensor([conv_e], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(ce, op=dist.ReduceOp.SUM)
-            e2e = {"value": float(ce.item()) / float(tt.item()), "unit": UNIT,
-                   "h2d_bytes_per_step": int(p_host.nbytes), "d2h_bytes_per_step": int(24 * n),
-                   "ms_per_step": float(tt.item()) * 1e3,
-                   "api": "gkq_integrate_batch_host (pinned host buffers, chunked H2D/compute/D2H pipeline)"
-                          + (f", called from {nth} host threads with one handle each" if nth > 1 else "")}
-
-    # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------
+    # ---- CPU baseline beside it (rank 0, N=1 only) + parity of the TIMED outputs ---------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, reps, ref = cpu_leg(W, p_host, n)
-        g_est = est.cpu().numpy()
-        g_st = st.cpu().numpy().astype(np.uint32)
-        tol_abs = W.tol.to_abs(np.abs(ref["estimate"]))
-        okrows = ref["status"] == 0
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"the same {n}-integral batch, best of {reps} passes, all host threads "
-                         "(golden-vector-pinned C++ port of gkquad's CPU path; no Rust toolchain here)",
-               "parity_vs_cpu": {"status_mismatch": int((g_st != ref["status"]).sum()),
-                                 "nevals_mismatch": int((nev_h != ref["nevals"]).sum()),
-                                 "out_of_tolerance": int((np.abs(g_est - ref["estimate"])[okrows] > tol_abs[okrows]).sum())}}
+               "sample": f"the same {n}-integral batch, best of {reps} passes, all host threads (golden-vector-pinned C++ port of gkquad's CPU path)",
+               "parity_vs_cpu": dict(parity(W, timed_out[0].cpu().numpy(), nev_h, timed_out[3].cpu().numpy().astype(np.uint32), ref),
+                                     checked="outputs of set 0 as written by the timed region (snapshot before the profiling pass)")}
+
+    # ---- every other BASELINE configuration ----------------------------------------------------------
+    configs = {}
+    want = [] if args.configs == "none" else [c for c in SECONDARY if args.configs == "all" or c[0] in args.configs.split(",")]
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.configs != "none":
+        configs["cfg1_simple"] = cfg1_simple()
+    configs["cfg2_S1"] = "the top-level keys of this line"
+    sec_steps = max(3, min(steps, 10))
+    for cname, wname, cn in want:
+        try:
+            configs[cname] = run_secondary(args, eng, WORKLOADS[wname], cn, rank, world, dev, sec_steps, peak_flops, flush)
+        except Exception as exc:  # a failing secondary configuration must not take the headline down
+            configs[cname] = {"error": repr(exc)[:300]}
+    if world > 1:
+        dist.barrier()
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{W.name}: {W.description}; {W.algo}, {W.tol}, max_evals {W.max_evals}",
-                       "batch_per_gpu": n, "global_batch": n * world,
-                       "parallelism": f"shard{world}" + ("+final_nccl_all_gather" if world > 1 else ""),
-                       "l2": "8 independent batches cycled (320 MB of inputs+outputs > 126 MB L2); no flush needed",
-                       "pipeline": f"BatchPipeline depth {DEPTH}: independent batches alternate between {DEPTH} handles "
-                                   f"on {DEPTH} streams (the single-wave survivor kernels of one batch fill the "
-                                   "ramps and tails of the other); deferred join: the stragglers (integrals "
-                                   "needing > 1 bisection step) of up to 8 steps of a lane are finished by one "
-                                   "launch of the persistent kernel; all K steps complete inside the timed region",
-                       "gather": ("no data-path collective: every rank keeps its shard's results in its own HBM; "
-                                  "one final all_gather of the last batch (24 B/integral) inside the timed region; "
-                                  "`per_step_gather` is the same run with every batch gathered") if world > 1
-                       else "none (N=1)",
-                       "converged_fraction": converged / (n * world),
-                       "mean_nevals": float(nev_h.mean())},
+            "config": workload_config(W, n, world),
+            "details": {"pipeline_depth": DEPTH, "deferred_join": True,
+                        "gather": (f"final gather of the last batch to rank 0 inside the timed region: gkq_gather_range, {CH} chunks, "
+                                   "20 B/integral, NCCL send/recv in the library") if world > 1 else "none (N=1)",
+                        "gathered_matches_local": gathered_ok,
+                        "converged_fraction": converged / (n * world), "mean_nevals": float(nev_h.mean()),
+                        "host_enqueue_ms_per_step": t_enq * 1e3},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "host_enqueue_ms_per_step": t_enq * 1e3,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "configs": configs,
         }
         if per_step_gather is not None:
             line["per_step_gather"] = per_step_gather
-        if p2p_gather is not None:
-            line["p2p_gather"] = p2p_gather
         emit(real_stdout, line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def kernel_evals(W, n, nev_h, stats):
+    """Integrand evaluations attributed to each kernel of one batch call (profiling names)."""
+    n25 = stats["last_survivors_qk25"]
+    cl, c2 = stats["last_chain_loop"], stats["last_chain_step2"]
+    total = int(nev_h.sum())
+    if W.algo == "QAGS" or (W.algo == "AUTO" and not W.points):
+        rest = total - 17 * n - 25 * n25 - 50 * (cl[0] + cl[1])
+        return {"k_qags_init<qk17>": 17 * n, "k_qags_init<qk25>": 25 * n25,
+                "k_qags_first[0]": 50 * cl[0], "k_qags_first[1]": 50 * cl[1], "k_adaptive<QAGS>": rest}
+    # QAGP: the flat seeding / first-step kernels count their own share when the engine reports it
+    out = {}
+    seeded = stats.get("last_qagp_seed_evals", 0)
+    first = stats.get("last_qagp_first_evals", 0)
+    if seeded:
+        out["k_qagp_seed"] = seeded
+    if first:
+        out["k_qagp_first"] = first
+    out["k_adaptive<QAGP>"] = total - seeded - first
+    return out
+
+
+def ncu_name_regex(display, fid):
+    """ncu kernel-name pattern of a profiling display name."""
+    return {"k_qags_init<qk17>": rf"k_qags_init<F1<{fid}>, 8,", "k_qags_init<qk25>": rf"k_qags_init<F1<{fid}>, 12,",
+            "k_qags_first[0]": rf"k_qags_first<F1<{fid}>", "k_qags_first[1]": rf"k_qags_first<F1<{fid}>",
+            "k_adaptive<QAGS>": rf"k_adaptive<F1<{fid}>, 0,", "k_adaptive<QAGP>": rf"k_adaptive<F1<{fid}>, 1,",
+            "k_qagp_seed": rf"k_qagp_seed<F1<{fid}>", "k_qagp_first": rf"k_qagp_first<F1<{fid}>"}.get(display, display.split("<")[0])
+
+
+def e2e_leg_1d(args, pipe, W, p_host, n, world, dev, steps):
+    """The same metric through the public host entry (gkq_integrate_batch_host): pinned host buffers,
+    H2D of the step's inputs and D2H of its results inside the timed call; `--e2e-threads` host threads
+    with one handle each make the blocking call in turn (ctypes releases the GIL), so the H2D of one
+    call overlaps the D2H of the other."""
+    import torch
+    import torch.distributed as dist
+    algo = ALGO[W.algo]
+    ph = torch.as_tensor(p_host).pin_memory()
+    kwh = dict(algo=algo, tol=W.tol, max_evals=W.max_evals, n=n)
+    csr = W.points == "param0"
+    if W.points and not csr:
+        kwh["points"] = W.points
+    if csr:
+        kwh["pts_offsets"] = np.arange(n + 1, dtype=np.int64)
+        kwh["pts"] = ph.numpy()[0]
+    nth = max(1, min(args.e2e_threads, pipe.depth))
+    hplans, houts = [], []
+    for t in range(nth):
+        bufs = (torch.empty(n, dtype=torch.float64).pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory(),
+                torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory())
+        houts.append(bufs)
+        o_t = (bufs[0].numpy(), bufs[1].numpy(), bufs[2].numpy().view(np.uint32), bufs[3].numpy().view(np.uint32))
+        hplans.append(pipe.engines[t].plan_batch(W.functor, W.a, W.b, ph.numpy(), **dict(kwh, out=o_t)))
+    for hp_ in hplans:
+        for _ in range(3):
+            hp_.run()
+    if world > 1:
+        dist.barrier()
+    e2e_steps = steps - steps % nth if steps >= nth else nth
+
+    def host_worker(t):
+        for _ in range(e2e_steps // nth):
+            hplans[t].run()
+    workers = [threading.Thread(target=host_worker, args=(t,)) for t in range(1, nth)]
+    t0 = time.perf_counter()
+    for w_ in workers:
+        w_.start()
+    host_worker(0)
+    for w_ in workers:
+        w_.join()
+    dt = (time.perf_counter() - t0) / e2e_steps
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    ce = torch.tensor([float((houts[0][3].numpy() == 0).sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ce, op=dist.ReduceOp.SUM)
+    h2d = int(p_host.nbytes) + (8 * (n + 1) + 8 * n if csr else 0)
+    return {"value": float(ce.item()) / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": int(24 * n), "ms_per_step": float(tt.item()) * 1e3,
+            "api": "gkq_integrate_batch_host, pinned host buffers" + (f", {nth} host threads with one handle each" if nth > 1 else "")}
+
+
+def run_secondary(args, eng, W, cn, rank, world, dev, steps, peak_flops, flush):
+    """One BASELINE configuration of the `configs` block at full size on the already warm engine.
+    1-D: cn integrals per GPU (weak); 2-D: cn integrals in total, block-cyclic sharded over the ranks
+    (strong, BASELINE configs[4]) and gathered to rank 0 by gkq_gather inside every timed step."""
+    import torch
+    import torch.distributed as dist
+    two_d = W.dim == 2
+    total = cn if two_d else cn * world
+    NS = 1 if two_d else 4  # 1-D: 4 independent batches cycled (> L2); 2-D: the interval slabs alone are GBs
+    sets = []
+    for s in range(NS):
+        p_host, idx = shard_params(W, cn, rank, world, offset=s * total, total=total)
+        m = int(p_host.shape[1])
+        p_dev = torch.as_tensor(p_host, device=dev)
+        kw = dict(algo=ALGO[W.algo], tol=W.tol, max_evals=W.max_evals, n=m)
+        if not two_d:
+            if W.points == "param0":
+                kw["pts_offsets"] = torch.arange(m + 1, dtype=torch.int64, device=dev)
+                kw["pts"] = p_dev[0].contiguous()
+            elif W.points:
+                kw["points"] = W.points
+            out = (torch.zeros(m, dtype=torch.float64, device=dev), torch.zeros(m, dtype=torch.float64, device=dev),
+                   torch.zeros(m, dtype=torch.int32, device=dev), torch.zeros(m, dtype=torch.int32, device=dev))
+            plan = eng.plan_batch(W.functor, W.a, W.b, p_dev, out=out, **kw)
+            sets.append(dict(p_host=p_host, run=plan.run, out=out, m=m))
+        else:
+            if W.points == "param01":
+                kw["pts_offsets"] = torch.arange(m + 1, dtype=torch.int64, device=dev)
+                kw["pts_xy"] = p_dev.t().contiguous()
+            elif W.points:
+                kw["points"] = W.points
+            S = dict(p_host=p_host, out=None, m=m)
+
+            def run2(S=S, p_dev=p_dev, kw=kw):
+                r = eng.integrate2_batch(W.functor, W.yrange, W.a, W.b, fparams=p_dev, yparams=W.yparams, **kw)
+                S["out"] = (r.estimate, r.delta, r.nevals, r.status)
+                S["keep"] = r
+                return r
+            S["run"] = run2
+            sets.append(S)
+    g_out = None
+    if two_d and world > 1 and rank == 0:
+        g_out = (torch.empty(total, dtype=torch.float64, device=dev), torch.empty(total, dtype=torch.float64, device=dev),
+                 torch.empty(total, dtype=torch.int32, device=dev), torch.empty(total, dtype=torch.int32, device=dev))
+
+    def one(k):
+        S = sets[k % NS]
+        S["run"]()
+        if two_d and world > 1:
+            eng.gather(S["out"], total, root=0, block=SHARD_BLOCK, out=g_out)
+
+    for k in range(max(2, NS)):
+        one(k)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(steps):
+        one(k)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    S0 = sets[0]
+    g_est, g_dlt, g_nev, g_st = (x.cpu().numpy() for x in S0["out"])  # as written by the timed region
+    g_nev = g_nev.astype(np.int64)
+    g_st = g_st.astype(np.uint32)
+    acc = torch.tensor([float((g_st == 0).sum()), float(g_nev.sum()), float(len(g_st))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    conv, evals, count = (float(x) for x in acc.tolist())
+    fl_eval = eng.functor(W.dim, W.functor)[3]
+    F_t = 6.0 if not (np.isfinite(W.a) and np.isfinite(W.b)) else 0.0
+    w_eval = fl_eval + F_t + 8.0
+    tfl = evals * w_eval / (ms * 1e-3) / 1e12
+    res = {"workload": f"{W.name}: {W.description}; {W.algo}, {W.tol}, max_evals {W.max_evals}",
+           "global_batch": int(count), "scaling": "strong" if two_d else "weak",
+           "value": conv / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+           "converged_fraction": conv / count, "mean_nevals": evals / count, "evals_per_s": evals / (ms * 1e-3),
+           "roofline": {"bound": "fp64", "achieved": tfl, "peak": peak_flops / 1e12, "unit": "TFLOP/s",
+                        "frac": tfl / (peak_flops / 1e12), "flops_per_eval": w_eval, "scope": "whole batch call"}}
+    if two_d and world > 1:
+        res["gather"] = "gkq_gather to rank 0 inside every timed step (20 B/integral)"
+        if rank == 0:
+            idx0 = torch.as_tensor(np.asarray(shard_params(W, cn, 0, world, total=total)[1]), device=dev)
+            res["gathered_matches_local"] = bool(torch.equal(g_out[0][idx0], S0["out"][0]) and torch.equal(g_out[2][idx0], S0["out"][2]))
+    # per-kernel profile of one call
+    try:
+        eng.set_profiling(True)
+        flush.zero_()
+        S0["run"]()
+        res["roofline"]["kernels"] = [{"kernel": nm, "ms": ms_k} for nm, ms_k in eng.profile()]
+        eng.set_profiling(False)
+        eng.sync()
+    except Exception as exc:
+        res["roofline"]["kernels_error"] = repr(exc)[:120]
+        eng.set_profiling(False)
+    # e2e through the host entry (pinned host buffers)
+    if not args.no_e2e:
+        res["e2e"] = e2e_secondary(eng, W, S0["p_host"], S0["m"], world, dev, min(steps, 4))
+    # CPU oracle on the same batch + parity of what the timed region wrote
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        m = S0["m"]
+        v, cores, reps, ref = cpu_leg(W, S0["p_host"], m, seconds_target=2.0, min_reps=1, max_reps=3)
+        res["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"the same {m}-integral batch, best of {reps} pass(es), all host threads"}
+        res["parity_vs_cpu"] = parity(W, g_est, g_nev, g_st, ref)
+    return res
+
+
+def e2e_secondary(eng, W, p_host, m, world, dev, steps):
+    import torch
+    import torch.distributed as dist
+    ph = torch.as_tensor(p_host).pin_memory()
+    bufs = (torch.empty(m, dtype=torch.float64).pin_memory(), torch.empty(m, dtype=torch.float64).pin_memory(),
+            torch.empty(m, dtype=torch.int32).pin_memory(), torch.empty(m, dtype=torch.int32).pin_memory())
+    h2d = int(p_host.nbytes)
+    if W.dim == 1:
+        kw = dict(algo=ALGO[W.algo], tol=W.tol, max_evals=W.max_evals, n=m,
+                  out=(bufs[0].numpy(), bufs[1].numpy(), bufs[2].numpy().view(np.uint32), bufs[3].numpy().view(np.uint32)))
+        if W.points == "param0":
+            kw["pts_offsets"] = np.arange(m + 1, dtype=np.int64)
+            kw["pts"] = ph.numpy()[0]
+            h2d += 8 * (m + 1) + 8 * m
+        elif W.points:
+            kw["points"] = W.points
+        plan = eng.plan_batch(W.functor, W.a, W.b, ph.numpy(), **kw)
+        run = plan.run
+        api = "gkq_integrate_batch_host"
+        status = lambda r: kw["out"][3]
+    else:
+        kw = dict(algo=ALGO[W.algo], tol=W.tol, max_evals=W.max_evals, n=m)
+        if W.points == "param01":
+            kw["pts_offsets"] = np.arange(m + 1, dtype=np.int64)
+            kw["pts_xy"] = np.ascontiguousarray(p_host.T)
+            h2d += 8 * (m + 1) + 16 * m
+        elif W.points:
+            kw["points"] = W.points
+
+        def run():
+            return eng.integrate2_batch(W.functor, W.yrange, W.a, W.b, fparams=ph.numpy(), yparams=W.yparams, **kw)
+        api = "gkq_integrate2_batch_host"
+        status = lambda r: r.status
+    r = run()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = run()
+    dt = (time.perf_counter() - t0) / steps
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    ce = torch.tensor([float((np.asarray(status(r)) == 0).sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ce, op=dist.ReduceOp.SUM)
+    return {"value": float(ce.item()) / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": int(24 * m), "ms_per_step": float(tt.item()) * 1e3, "api": api}
 
 
 if __name__ == "__main__":

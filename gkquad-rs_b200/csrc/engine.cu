@@ -1188,7 +1188,6 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
                                 int64_t range_stride, const double* params, int64_t param_stride,
                                 const int64_t* pts_offsets, const double* pts, double* out_estimate,
                                 double* out_delta, uint32_t* out_nevals, uint32_t* out_status) {
-    (void)pts;
     if (!h) return GKQ_ERR_INVALID_ARGUMENT;
     if (!cfg) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "cfg is NULL");
     if (functor_id < 0 || functor_id >= F1_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown functor id");
@@ -1196,10 +1195,14 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
     if (n == 0) return GKQ_OK;
     if (!a || !b || !out_estimate || !out_delta || !out_nevals || !out_status)
         return fail(h, GKQ_ERR_INVALID_ARGUMENT, "NULL array argument");
-    if (pts_offsets) return fail(h, GKQ_ERR_UNSUPPORTED, "per-integral points: use the device entry");
     GKQ_CUDA(h, cudaSetDevice(h->device));
     const int np = F1_TABLE[functor_id].nparams;
     if (np > 0 && !params) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "params is NULL");
+    if (pts_offsets) {
+        if (!pts) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "pts is NULL");
+        if (host_has_nan(pts, (size_t)pts_offsets[n]))  // integrator.rs:86-90
+            return fail(h, GKQ_ERR_NAN_INPUT, "cannot include NAN value in singular points");
+    }
     const int np_batch = param_stride ? np : 0;  // per-integral parameter rows
     int rc;
     // the data is visible to the CPU here: refuse what the reference refuses to construct
@@ -1216,6 +1219,73 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
         if ((rc = gkq_join(h, h->s_compute))) return rc;
         GKQ_CUDA(h, cudaStreamSynchronize(h->s_compute));
         h->rb[0].tail_pending = h->rb[1].tail_pending = false;
+    }
+
+    if (pts_offsets) {
+        // per-integral break points (CSR): single-shot staging -- such batches are QAGP work (hundreds
+        // of samples per integral), the copies are a small share of the call
+        const size_t N = (size_t)n, npts = (size_t)pts_offsets[n];
+        const size_t nr = range_stride ? N : 1, npar = param_stride ? N : 1;
+        const int n_ov = ov_host ? (ov_host->abs_tol != nullptr) + (ov_host->rel_tol != nullptr) + (ov_host->max_evals != nullptr) : 0;
+        const size_t in_d = 2 * nr + (size_t)np * npar + (N + 1) + npts + (size_t)n_ov * N;
+        const size_t want = in_d * 8 + N * 24 + 256;
+        if (want > h->stage_bytes) {
+            if (h->stage_dev) GKQ_CUDA(h, cudaFree(h->stage_dev));
+            h->stage_dev = nullptr;
+            h->stats.scratch_bytes -= h->stage_bytes;
+            h->stage_bytes = 0;
+            GKQ_CUDA(h, cudaMalloc(&h->stage_dev, want));
+            h->stage_bytes = want;
+            h->stats.scratch_bytes += want;
+        }
+        cudaStream_t st = h->s_compute;
+        double* d = (double*)h->stage_dev;
+        double *d_a = d, *d_b = d + nr, *d_par = d + 2 * nr;
+        long long* d_off = (long long*)(d_par + (size_t)np * npar);
+        double* d_pts = (double*)(d_off + N + 1);
+        double* q = d_pts + npts;
+        gkq_overrides ov_dev = {nullptr, nullptr, nullptr};
+        if (ov_host && ov_host->abs_tol) {
+            ov_dev.abs_tol = q;
+            GKQ_CUDA(h, cudaMemcpyAsync(q, ov_host->abs_tol, N * 8, cudaMemcpyHostToDevice, st));
+            q += N;
+        }
+        if (ov_host && ov_host->rel_tol) {
+            ov_dev.rel_tol = q;
+            GKQ_CUDA(h, cudaMemcpyAsync(q, ov_host->rel_tol, N * 8, cudaMemcpyHostToDevice, st));
+            q += N;
+        }
+        if (ov_host && ov_host->max_evals) {
+            ov_dev.max_evals = (const uint64_t*)q;
+            GKQ_CUDA(h, cudaMemcpyAsync(q, ov_host->max_evals, N * 8, cudaMemcpyHostToDevice, st));
+            q += N;
+        }
+        double* d_est = q;
+        double* d_dlt = d_est + N;
+        uint32_t* d_nev = (uint32_t*)(d_dlt + N);
+        uint32_t* d_st = d_nev + N;
+        GKQ_CUDA(h, cudaMemcpyAsync(d_a, a, nr * 8, cudaMemcpyHostToDevice, st));
+        GKQ_CUDA(h, cudaMemcpyAsync(d_b, b, nr * 8, cudaMemcpyHostToDevice, st));
+        for (int k = 0; k < np; ++k)
+            GKQ_CUDA(h, cudaMemcpyAsync(d_par + (size_t)k * npar, params + (size_t)k * (param_stride ? param_stride : 1),
+                                        npar * 8, cudaMemcpyHostToDevice, st));
+        GKQ_CUDA(h, cudaMemcpyAsync(d_off, pts_offsets, (N + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (npts) GKQ_CUDA(h, cudaMemcpyAsync(d_pts, pts, npts * 8, cudaMemcpyHostToDevice, st));
+        const bool was_deferred = h->deferred;
+        h->deferred = false;  // ordered: the call's stragglers are finished on `st` before the copies out
+        h->cur = 0;
+        rc = integrate_batch_ctx(h, cfg, functor_id, n, d_a, d_b, range_stride, d_par, param_stride ? (int64_t)N : 0,
+                                 (const int64_t*)d_off, d_pts, d_est, d_dlt, d_nev, d_st, st, false, 0ull, nullptr,
+                                 n_ov ? &ov_dev : nullptr, 0);
+        h->deferred = was_deferred;
+        if (rc) return rc;
+        GKQ_CUDA(h, cudaMemcpyAsync(out_estimate, d_est, N * 8, cudaMemcpyDeviceToHost, st));
+        GKQ_CUDA(h, cudaMemcpyAsync(out_delta, d_dlt, N * 8, cudaMemcpyDeviceToHost, st));
+        GKQ_CUDA(h, cudaMemcpyAsync(out_nevals, d_nev, N * 4, cudaMemcpyDeviceToHost, st));
+        GKQ_CUDA(h, cudaMemcpyAsync(out_status, d_st, N * 4, cudaMemcpyDeviceToHost, st));
+        GKQ_CUDA(h, cudaStreamSynchronize(st));
+        h->rb[0].tail_pending = h->rb[1].tail_pending = false;
+        return GKQ_OK;
     }
 
     // chunk schedule

@@ -84,3 +84,34 @@ def test_product_does_not_reach_into_the_oracle():
         text = p.read_text()
         assert "gkq_oracle" not in text and "from oracle" not in text and "import oracle" not in text, p
         assert "libgkq_oracle" not in text, p
+
+
+def test_shard_geometry_matches_the_host_mirror():
+    """gkq_shard_size / gkq_shard_index (pure host functions of the multi-GPU ABI) describe the same
+    block-cyclic partition as the Python mirror: every integral has exactly one
+    owner, ragged last blocks included."""
+    import numpy as np
+    from gkquad_b200 import _ffi
+    from gkquad_b200.workloads import block_cyclic_shard
+    L = _ffi.lib()
+    for n, w, b in [(0, 2, 4096), (1, 3, 4), (100, 3, 8), (1 << 20, 8, 4096), (100000, 8, 4096), (100000, 2, 4096),
+                    (12345, 5, 7), (4096 * 8 + 1, 8, 4096)]:
+        seen = np.zeros(n, dtype=np.int32)
+        for r in range(w):
+            idx = block_cyclic_shard(n, r, w, b)
+            assert L.gkq_shard_size(n, w, r, b) == len(idx)
+            got = np.array([L.gkq_shard_index(n, w, r, b, j) for j in range(len(idx))] if n <= 20000 else
+                           [L.gkq_shard_index(n, w, r, b, j) for j in (0, len(idx) // 2, len(idx) - 1) if len(idx)])
+            want = idx if n <= 20000 else idx[[0, len(idx) // 2, len(idx) - 1]] if len(idx) else idx
+            assert np.array_equal(got, want)
+            seen[idx] += 1
+            assert L.gkq_shard_size(n, w, 0, b) >= len(idx)  # rank 0 owns the largest shard (gkq_gather's common range)
+        assert np.all(seen == 1)
+    assert L.gkq_shard_size(10, 0, 0, 4) < 0 and L.gkq_shard_index(10, 2, 0, 4, 99) < 0
+
+
+def test_comm_entries_refuse_misuse_without_a_device():
+    from gkquad_b200 import _ffi
+    L = _ffi.lib()
+    assert L.gkq_comm_init(None, 2, 0, None) < 0 and L.gkq_gather(None, 0, 1, 0, *([None] * 9)) < 0
+    assert L.gkq_comm_destroy(None) < 0 and L.gkq_comm_get_unique_id(None) < 0
