@@ -23,8 +23,8 @@
 
 namespace gkq {
 
-// Geometry of the interleaved per-thread slabs.  Element k of thread t lives at
-// base[k * stride + t]; all arrays of one thread share one `double` slab and one `int` slab.
+// Geometry of the interleaved per-thread slabs: all arrays of one thread share one `double` slab and
+// one `int` slab (layout: struct Slab below).
 struct SlabGeom {
     double* dbase;
     int* wbase;
@@ -33,10 +33,19 @@ struct SlabGeom {
     int npts_max;               // break-point slots per thread (QAGP) incl. the two endpoints
 };
 
+// View of one thread's column of the slabs.  The four doubles of an interval (a, b, estimate, delta)
+// form ONE 32-byte record -- a single address computation and one DRAM sector per interval instead
+// of four of each; the records of a column are `stride` records apart (records of the same slot k
+// of consecutive threads are adjacent, so lanes walking in step still coalesce).  Behind the cap
+// records sit the thread's epsilon table, result history and break points as plain doubles, and in
+// the int slab its level and order arrays.  Addresses are base + k * (byte stride): one 32 x 32 -> 64
+// bit multiply-add each (round 1 spent a quarter of the persistent kernel's code on 64-bit index
+// arithmetic: profiles/qagp_r02.md).
 struct Slab {
-    double* d;
-    int* w;
-    unsigned long long stride;
+    char* iv;  // interval records: record k at iv + k * sb32
+    char* ex;  // extras: double j at ex + j * sb8   (EPS[52] | R3[3] | PTS[..])
+    char* lw;  // ints: LV[k] at lw + k * sb4, ORD[k] at lw + (cap + k) * sb4
+    unsigned int sb32, sb8, sb4;  // byte strides = stride * 32 / 8 / 4
     int cap;
     // -DGKQ_BOUNDS_CHECK: a debug build that traps on any list / table index outside its slot
     // range (compute-sanitizer is not available on every pool); run the GPU tests against it.
@@ -45,16 +54,34 @@ struct Slab {
 #else
     GKQ_DEV void chk(int, int) const {}
 #endif
-    GKQ_DEV double& A(int k) const { chk(k, cap); return d[(unsigned long long)k * stride]; }
-    GKQ_DEV double& B(int k) const { chk(k, cap); return d[(unsigned long long)(cap + k) * stride]; }
-    GKQ_DEV double& E(int k) const { chk(k, cap); return d[(unsigned long long)(2 * cap + k) * stride]; }
-    GKQ_DEV double& D(int k) const { chk(k, cap); return d[(unsigned long long)(3 * cap + k) * stride]; }
-    GKQ_DEV double& EPS(int k) const { chk(k, 52); return d[(unsigned long long)(4 * cap + k) * stride]; }
-    GKQ_DEV double& R3(int k) const { chk(k, 3); return d[(unsigned long long)(4 * cap + 52 + k) * stride]; }
-    GKQ_DEV double& PTS(int k) const { chk(k, 1 << 20); return d[(unsigned long long)(4 * cap + 55 + k) * stride]; }
-    GKQ_DEV int& LV(int k) const { chk(k, cap); return w[(unsigned long long)k * stride]; }
-    GKQ_DEV int& ORD(int k) const { chk(k, cap); return w[(unsigned long long)(cap + k) * stride]; }
+    GKQ_DEV double* rec(int k) const { chk(k, cap); return reinterpret_cast<double*>(iv + (size_t)(unsigned)k * sb32); }
+    GKQ_DEV double& A(int k) const { return rec(k)[0]; }
+    GKQ_DEV double& B(int k) const { return rec(k)[1]; }
+    GKQ_DEV double& E(int k) const { return rec(k)[2]; }
+    GKQ_DEV double& D(int k) const { return rec(k)[3]; }
+    GKQ_DEV double& X(int j) const { return *reinterpret_cast<double*>(ex + (size_t)(unsigned)j * sb8); }
+    GKQ_DEV double& EPS(int k) const { chk(k, 52); return X(k); }
+    GKQ_DEV double& R3(int k) const { chk(k, 3); return X(52 + k); }
+    GKQ_DEV double& PTS(int k) const { chk(k, 1 << 20); return X(55 + k); }
+    GKQ_DEV int& LV(int k) const { chk(k, cap); return *reinterpret_cast<int*>(lw + (size_t)(unsigned)k * sb4); }
+    GKQ_DEV int& ORD(int k) const { chk(k, cap); return *reinterpret_cast<int*>(lw + (size_t)(unsigned)(cap + k) * sb4); }
 };
+// Column `t` of a slab pair whose first double / int column group starts at dcol / wcol (in units of
+// `stride` elements: the nested kernels keep an outer and an inner list per thread, one behind the
+// other).  stride < 2^27 (checked by the host: byte strides are 32-bit).
+GKQ_DEV Slab make_slab(double* dbase, int* wbase, unsigned long long stride, unsigned long long t, int cap,
+                       unsigned long long dcol = 0, unsigned long long wcol = 0) {
+    Slab S;
+    double* d0 = dbase + dcol * stride;
+    S.iv = reinterpret_cast<char*>(d0 + 4ull * t);
+    S.ex = reinterpret_cast<char*>(d0 + 4ull * (unsigned long long)cap * stride + t);
+    S.lw = reinterpret_cast<char*>(wbase + wcol * stride + t);
+    S.sb32 = (unsigned int)(stride * 32ull);
+    S.sb8 = (unsigned int)(stride * 8ull);
+    S.sb4 = (unsigned int)(stride * 4ull);
+    S.cap = cap;
+    return S;
+}
 __host__ __device__ inline unsigned long long slab_doubles(int cap, int npts_max) {
     return 4ull * cap + 55ull + (unsigned long long)npts_max;
 }

@@ -198,6 +198,13 @@ struct gkq_handle_s {
     std::vector<ProfEntry> prof;
     std::vector<cudaEvent_t> prof_pool;
 
+    // level-synchronous 2-D path (kernels_2d_flat.cuh): one carved allocation + pinned round counters
+    char* flat_buf = nullptr;
+    size_t flat_bytes = 0;
+    Ctl2* flat_ctl_host = nullptr;  // pinned [2]
+    cudaEvent_t ev_flat[2] = {nullptr, nullptr};
+    int occ_2df[F2_COUNT][2];
+
     Launch1D l1[F1_COUNT];
     int occ_loop[F1_COUNT], occ_qagp[F1_COUNT], occ_init25[F1_COUNT];
     Launch2D l2[F2_COUNT];
@@ -244,6 +251,7 @@ struct FillL2 {
         h->l2[ID] = make_launch2d<ID>();
         h->occ_2d[ID][0] = h->occ_2d[ID][1] = -1;
         h->occ_2dw[ID][0] = h->occ_2dw[ID][1] = -1;
+        h->occ_2df[ID][0] = h->occ_2df[ID][1] = -1;
         FillL2<ID + 1>::go(h);
     }
 };
@@ -662,6 +670,9 @@ int gkq_create(int device, gkq_handle_t* out) {
         ev(&h->ev_done[k]);
     }
     ok = ok && cudaMallocHost(&h->fixed_pin, 64 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&h->flat_ctl_host, 2 * sizeof(Ctl2)) == cudaSuccess;
+    ev(&h->ev_flat[0]);
+    ev(&h->ev_flat[1]);
     if (!ok) {
         gkq_destroy(h);
         return fail(nullptr, GKQ_ERR_CUDA, "handle allocation failed");
@@ -709,6 +720,10 @@ int gkq_destroy(gkq_handle_t h) {
         if (R.ev_tail) cudaEventDestroy(R.ev_tail);
     }
     cudaFree(h->stage_dev);
+    cudaFree(h->flat_buf);
+    cudaFreeHost(h->flat_ctl_host);
+    for (int k = 0; k < 2; ++k)
+        if (h->ev_flat[k]) cudaEventDestroy(h->ev_flat[k]);
     cudaFreeHost(h->fixed_pin);
     for (int k = 0; k < gkq_handle_s::MAX_CHUNKS; ++k) {
         if (h->ev_in[k]) cudaEventDestroy(h->ev_in[k]);
@@ -1560,6 +1575,113 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
 }
 
 // ---- 2-D ----------------------------------------------------------------------------------------
+}  // extern "C"
+namespace gkq {
+void launch_flat_plan(bool qagp, const Batch2D& P, int round, int grid, cudaStream_t st) {
+    if (qagp)
+        k2_plan<true><<<grid, FB, 0, st>>>(P, round);
+    else
+        k2_plan<false><<<grid, FB, 0, st>>>(P, round);
+}
+void launch_flat_commit(bool qagp, const Batch2D& P, int round, int grid, cudaStream_t st) {
+    if (qagp)
+        k2_commit<true><<<grid, FB, 0, st>>>(P, round);
+    else
+        k2_commit<false><<<grid, FB, 0, st>>>(P, round);
+}
+}  // namespace gkq
+
+// Bytes of level-synchronous scratch per outer integral (everything but the inner lists).
+static size_t flat_bytes_per_outer(int cap_outer, int npts_max) {
+    return sizeof(Lane) + sizeof(OuterCtx) + 3 * 4 + 50 * (8 + 4 * 4) + slab_doubles(cap_outer, npts_max + 2) * 8 +
+           slab_ints(cap_outer) * 4 + 64;
+}
+
+// The nested drivers as rounds of flat kernels (kernels_2d_flat.cuh).  Enqueues rounds on `st` until an
+// active count of zero has come back; the host runs one round ahead of the count it waits for.
+static int run_nested_flat(gkq_handle_t h, const Launch2D& L, int fid2, int alg, Batch2D Q, int64_t n, cudaStream_t st) {
+    int rc;
+    const size_t N = (size_t)n;
+    // carve the per-outer scratch
+    const size_t per = flat_bytes_per_outer(Q.cap_outer, Q.npts_max);
+    const size_t want = per * N + 4096;
+    if (want > h->flat_bytes) {
+        GKQ_CUDA(h, cudaStreamSynchronize(st));
+        if (h->flat_buf) GKQ_CUDA(h, cudaFree(h->flat_buf));
+        h->flat_buf = nullptr;
+        h->stats.scratch_bytes -= h->flat_bytes;
+        h->flat_bytes = 0;
+        GKQ_CUDA(h, cudaMalloc(&h->flat_buf, want + want / 8));
+        h->flat_bytes = want + want / 8;
+        h->stats.scratch_bytes += h->flat_bytes;
+    }
+    char* p = h->flat_buf;
+    auto take = [&](size_t bytes) {
+        char* q = p;
+        p += (bytes + 255) / 256 * 256;
+        return q;
+    };
+    Flat2& F = Q.flat;
+    F.ctl = (Ctl2*)take(sizeof(Ctl2));
+    F.oslab.dbase = (double*)take(slab_doubles(Q.cap_outer, Q.npts_max + 2) * 8 * N);
+    F.oslab.wbase = (int*)take(slab_ints(Q.cap_outer) * 4 * N);
+    F.oslab.stride = N;
+    F.oslab.cap = Q.cap_outer;
+    F.oslab.npts_max = Q.npts_max + 2;
+    F.olane = (Lane*)take(sizeof(Lane) * N);
+    F.octx = (OuterCtx*)take(sizeof(OuterCtx) * N);
+    F.act[0] = (unsigned int*)take(4 * N);
+    F.act[1] = (unsigned int*)take(4 * N);
+    F.xlist = (unsigned int*)take(4 * N);
+    F.t_est = (double*)take(8 * 50 * N);
+    F.t_nev = (uint32_t*)take(4 * 50 * N);
+    F.t_meta = (uint32_t*)take(4 * 50 * N);
+    F.t_owner = (uint32_t*)take(4 * 50 * N);
+    F.t_k = (uint32_t*)take(4 * 50 * N);
+    if ((size_t)(p - h->flat_buf) > h->flat_bytes) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "level-synchronous scratch carve overflow");
+
+    // persistent grid of the inner kernel: its threads own the inner lists
+    if (h->occ_2df[fid2][alg] < 0) h->occ_2df[fid2][alg] = L.occupancy_flat[alg]();
+    int grid = persistent_grid(h, h->occ_2df[fid2][alg], Q.cap_inner, Q.npts_max + 2, FB);
+    if (grid < 1) return fail(h, GKQ_ERR_OUT_OF_MEMORY, "max_evals too large for the interval slabs");
+    // (a round posts up to 50 tasks per outer integral)
+    const long long task_blocks = (50ll * n + FB - 1) / FB;
+    if ((long long)grid > task_blocks) grid = (int)task_blocks;
+    SlabGeom g;
+    if ((rc = ensure_slab(h, (unsigned long long)grid * FB, Q.cap_inner, Q.npts_max + 2, g))) return rc;
+    Q.slab = g;
+    long long flat_grid = (n + FB - 1) / FB;
+    const long long flat_cap = (long long)h->sm_count * 16;
+    if (flat_grid > flat_cap) flat_grid = flat_cap;
+
+    const char* kname = alg == 0 ? "nested_flat<QAGS2>" : "nested_flat<QAGP2>";
+    prof_begin(h, kname, st);
+    GKQ_CUDA(h, cudaMemsetAsync(F.ctl, 0, sizeof(Ctl2), st));
+    L.flat_start[alg](Q, (int)flat_grid, st);
+    if ((rc = launch_check(h, "k2_start"))) return rc;
+    const int max_rounds = Q.cap_outer + 8;
+    for (int r = 0;; ++r) {
+        if (r > max_rounds) return fail(h, GKQ_ERR_CUDA, "level-synchronous nest did not terminate");
+        k2_round_reset<<<1, 1, 0, st>>>(F.ctl, r);
+        launch_flat_plan(alg == 1, Q, r, (int)flat_grid, st);
+        L.flat_inner[alg](Q, grid, st);
+        launch_flat_commit(alg == 1, Q, r, (int)flat_grid, st);
+        L.flat_exact[alg](Q, grid, st);
+        if ((rc = launch_check(h, "nested_flat round"))) return rc;
+        h->stats.kernel_launches += 4;
+        GKQ_CUDA(h, cudaMemcpyAsync(&h->flat_ctl_host[r & 1], F.ctl, sizeof(Ctl2), cudaMemcpyDeviceToHost, st));
+        GKQ_CUDA(h, cudaEventRecord(h->ev_flat[r & 1], st));
+        if (r >= 1) {
+            GKQ_CUDA(h, cudaEventSynchronize(h->ev_flat[(r - 1) & 1]));
+            // after round r - 1: nact[r & 1] outer integrals were left for round r (already enqueued)
+            if (h->flat_ctl_host[(r - 1) & 1].nact[r & 1] == 0ull) break;
+        }
+    }
+    prof_end(h, st);
+    return GKQ_OK;
+}
+
+extern "C" {
 int gkq_integrate2_batch_ex(gkq_handle_t h, const gkq_config* cfg, const gkq_overrides* ov, int functor2_id, int yrange_id,
                          int64_t n, const double* x0, const double* x1, int64_t range_stride,
                          const double* fparams, int64_t fparam_stride, const double* yparams,
@@ -1714,8 +1836,21 @@ int gkq_integrate2_batch_ex(gkq_handle_t h, const gkq_config* cfg, const gkq_ove
         // k_nested_pool: warps own a few outer integrals each and share their inner integrals
         // among the lanes; k_nested (a thread per outer integral) is kept as the reference mapping.
         bool pool_mode = true;
-        if (const char* env = getenv("GKQ_NESTED_MODE")) {  // test / tuning knob: 1 = thread, 2 = pool
-            if (atoi(env) == 1) pool_mode = false;
+        // level-synchronous rounds pay once a round's inner integrals fill the machine; small batches
+        // (and batches whose per-outer scratch would not fit) stay on the pool kernel
+        bool flat_mode = n >= 1024 && n < (1ll << 25) &&
+                         flat_bytes_per_outer((int)outer_need, Q.npts_max) * (size_t)n < h->total_mem / 3;
+        if (const char* env = getenv("GKQ_NESTED_MODE")) {  // test / tuning knob: 1 = thread, 2 = pool, 3 = level-synchronous
+            const int m = atoi(env);
+            if (m == 1) pool_mode = false;
+            if (m == 1 || m == 2) flat_mode = false;
+            if (m == 3) flat_mode = n < (1ll << 25);
+        }
+        if (flat_mode) {
+            Q.cap_outer = (int)outer_need;
+            Q.cap_inner = (int)inner_need;
+            if ((rc = run_nested_flat(h, L, functor2_id, alg, Q, n, st))) return rc;
+            continue;
         }
         const int blk = pool_mode ? PB : BLOCK;
         int grid = persistent_grid(h, pool_mode ? h->occ_2dw[functor2_id][alg] : h->occ_2d[functor2_id][alg],

@@ -494,21 +494,26 @@ GKQ_DEV int make_sorted_points(const Slab& S, double begin, double end, const do
 }
 
 // ---- persistent adaptive kernel ------------------------------------------------------------------
-template <class F, bool QAGP, int NPARAMS>
+// COOP: compile the cooperative latency mode in.  It pays when the queue is SHORT (the straggler
+// records of a smooth QAGS batch: 153 integrals walking 10 sequential steps) and costs when the queue
+// is long -- measured on 1M-integral batches with it compiled out: P0 1.08 -> 0.83 ms, P1 7.4 -> 6.3,
+// I1 0.61 -> 0.52, I2 2.39 -> 2.12, S3 0.81 -> 0.74 (profiles/ab_coop_r02.txt): a quarter of P0's
+// warp instructions were shuffles and redundant reductions of warps that had drawn a thin share of the
+// queue's tail.  QAGP batches (the whole batch goes through this kernel) are compiled without it; the
+// QAGS instance keeps it but switches it off at run time unless the queue is shorter than the grid.
+template <class F, bool QAGP, int NPARAMS, bool COOP = !QAGP>
 __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(const Batch1D P) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned long long t = (unsigned long long)blockIdx.x * ABLOCK + threadIdx.x;
     // lane-indexed node table for the cooperative path (constant memory would serialise)
-    __shared__ double s_xgk[12];
-    if (threadIdx.x < 12) s_xgk[threadIdx.x] = c_xgk25[threadIdx.x];
-    __syncthreads();
+    __shared__ double s_xgk[COOP ? 12 : 1];
+    if (COOP) {
+        if (threadIdx.x < 12) s_xgk[threadIdx.x] = c_xgk25[threadIdx.x];
+        __syncthreads();
+    }
 
-    Slab S;
-    S.d = P.slab.dbase + t;
-    S.w = P.slab.wbase + t;
-    S.stride = P.slab.stride;
-    S.cap = P.slab.cap;
+    const Slab S = make_slab(P.slab.dbase, P.slab.wbase, P.slab.stride, t, P.slab.cap);
 
     unsigned long long total;
     if (QAGP)
@@ -521,7 +526,9 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
     // first fill: queue positions [0, first_span) are owned statically; later refills draw
     // positions first_span + atomicAdd(head, ..)
     const unsigned long long share0 = (total + nwarps - 1ull) / nwarps;
-    const bool thin_start = share0 <= (unsigned long long)COOP_MAX_LIVE;
+    // cooperative mode only for queues that cannot even fill the grid's lanes once
+    const int CML = (COOP && total <= nwarps * 32ull) ? COOP_MAX_LIVE : 0;
+    const bool thin_start = share0 <= (unsigned long long)CML;
     const unsigned long long first_span = thin_start ? share0 * nwarps : nwarps * 32ull;
     bool first_fill = true;
 
@@ -576,7 +583,7 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
                     const unsigned long long cur = first_span + *(volatile unsigned long long*)head;
                     const unsigned long long remaining = total > cur ? total - cur : 0ull;
                     const unsigned long long share = (remaining + nwarps - 1ull) / nwarps;
-                    if (remaining > 0ull && share <= (unsigned long long)COOP_MAX_LIVE) {
+                    if (remaining > 0ull && share <= (unsigned long long)CML) {
                         int room = (int)share - live_now;
                         if (room < 1) room = live_now == 0 ? 1 : 0;
                         if (room < take) take = room;
@@ -727,7 +734,7 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
         QK q0, q1;
         q0.estimate = q0.delta = q0.absvalue = q0.asc = 0.;
         q1 = q0;
-        if (__popc(live) > COOP_MAX_LIVE) {
+        if (!COOP || __popc(live) > CML) {
             // throughput mode: every lane walks its own 50 samples, warp-converged
 #pragma unroll 1
             for (int hh = 0; hh < 2; ++hh) {
@@ -846,11 +853,7 @@ __global__ void __launch_bounds__(ABLOCK, GKQ_ADAPTIVE_MIN_BLOCKS) k_adaptive(co
 template <class F, int NPARAMS>
 __global__ void __launch_bounds__(ABLOCK) k_qag(const Batch1D P) {
     const unsigned long long t = (unsigned long long)blockIdx.x * ABLOCK + threadIdx.x;
-    Slab S;
-    S.d = P.slab.dbase + t;
-    S.w = P.slab.wbase + t;
-    S.stride = P.slab.stride;
-    S.cap = P.slab.cap;
+    const Slab S = make_slab(P.slab.dbase, P.slab.wbase, P.slab.stride, t, P.slab.cap);
     const long long step = (long long)gridDim.x * ABLOCK;
     for (long long i = (long long)t; i < P.n; i += step) {
         Wrapped<F> g;

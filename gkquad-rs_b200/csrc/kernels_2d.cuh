@@ -445,6 +445,31 @@ __device__ __noinline__ Res seq_qagp(G& g, double a, double b, bool transform, P
     return r;
 }
 
+struct OuterCtx;  // kernels_2d_pool.cuh
+struct Ctl2 {
+    unsigned long long nact[2];  // active outer integrals of this round / the next
+    unsigned long long ntasks;   // inner tasks posted this round
+    unsigned long long qhead;    // queue head of k2_inner
+    unsigned long long nexact;   // outer integrals handed to k2_exact this round
+    unsigned long long xhead;    // queue head of k2_exact
+    unsigned long long pad[2];
+};
+
+// Scratch of the level-synchronous path (handle-owned, sized by the batch).
+struct Flat2 {
+    Lane* olane;            // [n] outer QAGS / QAGP machines
+    OuterCtx* octx;         // [n]
+    unsigned int* act[2];   // [n] active outer slots, ping-pong
+    unsigned int* xlist;    // [n] outer slots for k2_exact
+    double* t_est;          // [50 n] task results ...
+    uint32_t* t_nev;
+    uint32_t* t_meta;       // status | RSV_* << 3 | n << 5
+    uint32_t* t_owner;      // ... and what they are: outer slot,
+    uint32_t* t_k;          // node index inside the trip
+    Ctl2* ctl;
+    SlabGeom oslab;         // outer interval lists: one column per outer slot (stride n)
+};
+
 struct Batch2D {
     long long n;
     const double* x0;
@@ -475,6 +500,7 @@ struct Batch2D {
     const double* rel_tol_each;
     const unsigned long long* max_evals_each;
     int pool_r;  // k_nested_pool: outer integrals per warp (<= POOL_R)
+    Flat2 flat;  // level-synchronous path (kernels_2d_flat.cuh)
 };
 
 GKQ_DEV Tol load_tol2(const Batch2D& P, long long i) {
@@ -577,16 +603,10 @@ __global__ void __launch_bounds__(BLOCK) k_nested(const Batch2D P) {
     constexpr bool QAGP = ALG == 1;
     const unsigned long long t = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x;
     // slab regions of this thread: [outer lists | inner lists]
-    Slab Sout, Sin;
-    Sout.d = P.slab.dbase + t;
-    Sout.w = P.slab.wbase + t;
-    Sout.stride = P.slab.stride;
-    Sout.cap = P.cap_outer;
-    const unsigned long long outer_d = slab_doubles(P.cap_outer, P.npts_max + 2);
-    Sin.d = Sout.d + outer_d * P.slab.stride;
-    Sin.w = Sout.w + slab_ints(P.cap_outer) * P.slab.stride;
-    Sin.stride = P.slab.stride;
-    Sin.cap = P.cap_inner;
+    // slab regions of this thread: [outer lists | inner lists]
+    const Slab Sout = make_slab(P.slab.dbase, P.slab.wbase, P.slab.stride, t, P.cap_outer);
+    const Slab Sin = make_slab(P.slab.dbase, P.slab.wbase, P.slab.stride, t, P.cap_inner,
+                               slab_doubles(P.cap_outer, P.npts_max + 2), slab_ints(P.cap_outer));
 
     const unsigned long long total = P.worklist ? *P.worklist_count : (unsigned long long)P.n;
     unsigned long long* head = QAGP ? &P.ctl->headP : &P.ctl->head2;
@@ -679,6 +699,7 @@ struct NodeSet {
 
 }  // namespace gkq
 #include "kernels_2d_pool.cuh"
+#include "kernels_2d_flat.cuh"
 namespace gkq {
 
 struct Launch2D {
@@ -687,7 +708,15 @@ struct Launch2D {
     void (*run_qag)(const Batch2D&, int grid, cudaStream_t);  // QAG2: k_nested<.., 2> (BLOCK threads)
     void (*run_pool[2])(const Batch2D&, int grid, cudaStream_t);  // k_nested_pool (PB threads per block)
     int (*occupancy_pool[2])();
+    // level-synchronous path (kernels_2d_flat.cuh): [0] QAGS2, [1] QAGP2
+    void (*flat_start[2])(const Batch2D&, int grid, cudaStream_t);
+    void (*flat_inner[2])(const Batch2D&, int grid, cudaStream_t);
+    void (*flat_exact[2])(const Batch2D&, int grid, cudaStream_t);
+    int (*occupancy_flat[2])();
 };
+// the kernels of the level-synchronous path that do not depend on the integrand
+void launch_flat_plan(bool qagp, const Batch2D& P, int round, int grid, cudaStream_t st);
+void launch_flat_commit(bool qagp, const Batch2D& P, int round, int grid, cudaStream_t st);
 template <int ID>
 Launch2D make_launch2d();
 #define GKQ_DECL_F2(ID, NAME, NP, FL) template <> Launch2D make_launch2d<ID>();
@@ -744,6 +773,34 @@ GKQ_F2_LIST(GKQ_DECL_F2)
             cudaFuncSetAttribute(k_nested_pool<F2<ID>, true, NP>,                                 \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem);              \
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_nested_pool<F2<ID>, true, NP>, PB, smem); \
+            return nb;                                                                            \
+        };                                                                                        \
+        L.flat_start[0] = [](const Batch2D& P, int grid, cudaStream_t st) {                       \
+            k2_start<F2<ID>, false, NP><<<grid, FB, 0, st>>>(P);                                  \
+        };                                                                                        \
+        L.flat_start[1] = [](const Batch2D& P, int grid, cudaStream_t st) {                       \
+            k2_start<F2<ID>, true, NP><<<grid, FB, 0, st>>>(P);                                   \
+        };                                                                                        \
+        L.flat_inner[0] = [](const Batch2D& P, int grid, cudaStream_t st) {                       \
+            k2_inner<F2<ID>, false, NP><<<grid, FB, 0, st>>>(P);                                  \
+        };                                                                                        \
+        L.flat_inner[1] = [](const Batch2D& P, int grid, cudaStream_t st) {                       \
+            k2_inner<F2<ID>, true, NP><<<grid, FB, 0, st>>>(P);                                   \
+        };                                                                                        \
+        L.flat_exact[0] = [](const Batch2D& P, int grid, cudaStream_t st) {                       \
+            k2_exact<F2<ID>, false, NP><<<grid, FB, 0, st>>>(P);                                  \
+        };                                                                                        \
+        L.flat_exact[1] = [](const Batch2D& P, int grid, cudaStream_t st) {                       \
+            k2_exact<F2<ID>, true, NP><<<grid, FB, 0, st>>>(P);                                   \
+        };                                                                                        \
+        L.occupancy_flat[0] = []() {                                                              \
+            int nb = 0;                                                                           \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k2_inner<F2<ID>, false, NP>, FB, 0); \
+            return nb;                                                                            \
+        };                                                                                        \
+        L.occupancy_flat[1] = []() {                                                              \
+            int nb = 0;                                                                           \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k2_inner<F2<ID>, true, NP>, FB, 0); \
             return nb;                                                                            \
         };                                                                                        \
         return L;                                                                                 \

@@ -281,16 +281,10 @@ __global__ void __launch_bounds__(PB, 4) k_nested_pool(const Batch2D P) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned long long t = (unsigned long long)blockIdx.x * PB + threadIdx.x;
-    Slab Sout, Sin;
-    Sout.d = P.slab.dbase + t;
-    Sout.w = P.slab.wbase + t;
-    Sout.stride = P.slab.stride;
-    Sout.cap = P.cap_outer;
-    const unsigned long long outer_d = slab_doubles(P.cap_outer, P.npts_max + 2);
-    Sin.d = Sout.d + outer_d * P.slab.stride;
-    Sin.w = Sout.w + slab_ints(P.cap_outer) * P.slab.stride;
-    Sin.stride = P.slab.stride;
-    Sin.cap = P.cap_inner;
+    // slab regions of this thread: [outer lists | inner lists]
+    const Slab Sout = make_slab(P.slab.dbase, P.slab.wbase, P.slab.stride, t, P.cap_outer);
+    const Slab Sin = make_slab(P.slab.dbase, P.slab.wbase, P.slab.stride, t, P.cap_inner,
+                               slab_doubles(P.cap_outer, P.npts_max + 2), slab_ints(P.cap_outer));
 
     extern __shared__ __align__(16) unsigned char pool_smem[];
     PoolShared& W = reinterpret_cast<PoolShared*>(pool_smem)[threadIdx.x >> 5];

@@ -2,6 +2,8 @@
 glibc through numpy, in units in the last place.  The kernels replace libdevice inside the
 integrand functors because the rule kernels are issue-bound (profiles/S1_r01.md); they must stay
 as accurate as what they replace (CUDA documents 1 ulp for exp and 2 ulp for sin / cos)."""
+import math
+
 import numpy as np
 import pytest
 
@@ -60,3 +62,59 @@ def test_sincos_accuracy(eng, fn, ref):
     print(fn, "max ulp error", e.max(), "mean", e.mean(), "argmax", x[np.argmax(e)])
     assert e.max() <= 2.0
     assert np.isnan(got[-1]) and np.isnan(got[-2])
+
+
+def _libm(fn, x):
+    """glibc's scalar libm through Python's math module (numpy's own log / power use a vectorised
+    libm with ~1 ulp error on AVX-512 hosts, which is not the oracle's arithmetic)."""
+    out = np.empty(len(x))
+    for i, v in enumerate(x.tolist()):
+        try:
+            out[i] = fn(v)
+        except (ValueError, ZeroDivisionError):  # log(0), 0 ** -p, log(-x)
+            out[i] = -np.inf if fn is math.log and v == 0.0 else (np.inf if v == 0.0 else np.nan)
+        except OverflowError:
+            out[i] = np.inf
+    return out
+
+
+def _eval2(eng, functor, x, params):
+    import torch
+    p = np.ascontiguousarray(np.broadcast_to(np.asarray(params, dtype=np.float64)[:, None], (len(params), len(x))))
+    return eng.eval_batch(functor, torch.as_tensor(x, device="cuda:0"), torch.as_tensor(p, device="cuda:0")).cpu().numpy()
+
+
+def test_log_accuracy(eng):
+    """gk_log_fast (table-driven, csrc/gk_math_logpow.cuh) through the functor ln|x - c| with c = 0:
+    <= 0.53 ulp on the host check (tools/hostcheck/check_logpow.cpp); here against glibc (<= 1 ulp allows
+    for glibc's own 0.52).  Non-normal / non-positive arguments take the libdevice path."""
+    rng = np.random.default_rng(11)
+    x = np.concatenate([np.exp(rng.uniform(-700, 700, 400_000)), rng.uniform(0.5, 1.5, 400_000),
+                        1.0 + rng.uniform(-1e-3, 1e-3, 100_000), rng.uniform(0, 1, 200_000), -rng.uniform(0, 5, 1000),
+                        [1.0, 2.0, 0.5, 1e-310, 5e-324, 0.0, np.inf, np.nan, np.nextafter(1.0, 0), np.nextafter(1.0, 2)]])
+    got = _eval2(eng, "logabs_p", x, [0.0])
+    want = _libm(math.log, np.abs(x))  # glibc through the math module (numpy may use a vector libm)
+    e = _ulp_err(got, want)
+    fin = np.isfinite(want)
+    print("log: max ulp error", e[fin].max(), "mean", e[fin].mean(), "bit-equal share", float((got == want)[fin].mean()))
+    assert e[fin].max() <= 1.0
+    assert got[x == 0.0][0] == -np.inf and got[np.isinf(x)][0] == np.inf and np.isnan(got[np.isnan(x)]).all()
+    assert (got == want)[fin].mean() > 0.997
+
+
+@pytest.mark.parametrize("p", [0.1, 0.35, 0.6, 0.9, -2.6, 3.0, 17.25])
+def test_pow_accuracy(eng, p):
+    """gk_pow_fast through the functor |x - c|^-p with c = 0 (P1: p in [0.1, 0.6]; f1 / f2: x^2.6, x^-0.9)."""
+    rng = np.random.default_rng(int(p * 100) + 1000)
+    x = np.concatenate([rng.uniform(0, 1, 400_000), np.exp(rng.uniform(-30, 30, 300_000)), 1.0 + rng.uniform(-1e-4, 1e-4, 50_000),
+                        [1.0, 2.0, 0.25, 1e-300, 1e300, 1e-320, 0.0, np.inf, np.nan]])
+    got = _eval2(eng, "abspow_p", x, [0.0, p])
+    want = _libm(lambda v: math.pow(v, -p), np.abs(x))
+    e = _ulp_err(got, want)
+    fin = np.isfinite(want) & (want != 0) & (np.abs(want) > 1e-300)
+    print("pow p =", p, "max ulp error", e[fin].max(), "mean", e[fin].mean(), "bit-equal share", float((got == want)[fin].mean()))
+    assert e[fin].max() <= 1.0
+    assert np.isnan(got[np.isnan(x)]).all()
+    i0 = np.nonzero(x == 0.0)[0][0]
+    assert got[i0] == want[i0]
+    assert (got == want)[fin].mean() > 0.995

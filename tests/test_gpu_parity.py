@@ -401,7 +401,7 @@ def test_double_dynamic_ranges(eng):
         compare(g, ref, _tol(tol), exact=True, label=f)
 
 
-@pytest.mark.parametrize("mode", ["1", "2"], ids=["thread_per_outer", "warp_per_outer"])
+@pytest.mark.parametrize("mode", ["1", "2", "3"], ids=["thread_per_outer", "warp_per_outer", "level_synchronous"])
 def test_double_budget_exhaustion(eng, mode, monkeypatch):
     """The running evaluation budget, the first-error latch and the persistent inner workspace of the
     nest (double/algorithm/qags.rs:60-93, qagp.rs:108-137) under budgets that run out at every stage;
@@ -517,7 +517,7 @@ def test_per_integral_tolerance_and_budget(eng):
         eng.set_deferred_join(False)
 
 
-@pytest.mark.parametrize("mode", ["1", "2"], ids=["thread_per_outer", "pool"])
+@pytest.mark.parametrize("mode", ["1", "2", "3"], ids=["thread_per_outer", "pool", "level_synchronous"])
 def test_double_dynamic_x(eng, mode, monkeypatch):
     """DynamicX (double/range.rs:38-75; algorithms: qags.rs:29-44, qagp.rs:34-53): x inside, y outside,
     integrand arguments and point coordinates swapped.  Bit-exact against the oracle, and equal to the
@@ -551,7 +551,7 @@ def test_double_dynamic_x(eng, mode, monkeypatch):
     assert r.value.estimate == ref["estimate"][0] and r.value.nevals == ref["nevals"][0]
 
 
-@pytest.mark.parametrize("mode", ["1", "2"], ids=["thread_per_outer", "pool"])
+@pytest.mark.parametrize("mode", ["1", "2", "3"], ids=["thread_per_outer", "pool", "level_synchronous"])
 def test_double_per_integral_tolerance_and_budget(eng, mode, monkeypatch):
     """Per-nest tolerance values and TOTAL budgets (IntegrationConfig2, double/common.rs:14-32, set anew
     for every integral of a sweep): bit-exact against the oracle, device and host entry."""

@@ -1,6 +1,7 @@
 """GPU tests added in round 2: FULL-SIZE parity against the oracle (BASELINE.json sizes: 1M 1-D
 batches, 100k 2-D batches), the multi-GPU entries of the C ABI (gkq_comm_* / gkq_gather), the
 deferred-join output table, input validation.  Everything goes through libgkquad_b200.so."""
+import math
 import os
 import subprocess
 from pathlib import Path
@@ -78,7 +79,11 @@ def test_full_size_tolerance_parity(eng, wname, max_flips, max_nevals_mismatch):
         truth = W.truth(p)
         ok = ref["status"] == 0
         gn = g.numpy()
-        assert np.all(np.abs(gn.estimate - truth)[ok] <= np.abs(W.tol.to_abs(np.abs(truth)))[ok] * 1.01 + 1e-15)
+        # (QUADPACK's delta is an estimate: a converged integral may sit a little outside the requested
+        # tolerance of the TRUE value -- the oracle's values do the same; what is asserted against the
+        # closed form is the engine's distance from it relative to the oracle's)
+        allow = np.abs(W.tol.to_abs(np.abs(truth)))
+        assert np.all(np.abs(gn.estimate - truth)[ok] <= np.abs(ref["estimate"] - truth)[ok] + allow[ok] + 1e-15)
 
 
 @pytest.mark.parametrize("wname", ["S2", "P0", "I0", "I1"])
@@ -271,3 +276,51 @@ def test_cpp_ranks_over_the_abi(workload):
     print(out.stdout, out.stderr)
     assert out.returncode == 0, (out.stdout, out.stderr)
     assert "bit-identical" in out.stdout
+
+
+@pytest.mark.parametrize("mode", ["2", "3"], ids=["pool", "level_synchronous"])
+def test_golden_double_in_every_mapping(eng, golden, mode, monkeypatch):
+    """The reference's nested golden vectors (tests/algorithms_double.rs:56-195) through the pool kernel and
+    through the level-synchronous rounds (forced with GKQ_NESTED_MODE; batches >= 1024 take the rounds by
+    default): identical answers."""
+    from helpers import STATUS, assert_rel, num
+    from test_gpu_parity import _tol
+    monkeypatch.setenv("GKQ_NESTED_MODE", mode)
+    for case in golden["double"]:
+        if case["algo"] == "QAG":
+            continue
+        r = eng.integrate2_batch(case["functor2"], case["yrange"], num(case["x0"]), num(case["x1"]),
+                                 fparams=case["fparams"] or None, yparams=[num(v) for v in case["yparams"]] or None,
+                                 algo=ALGO[case["algo"]], tol=_tol(case["tol"]), max_evals=case["max_evals"],
+                                 points=[tuple(p) for p in case["points"]], n=1)[0]
+        assert (r.error.value if r.error else 0) == STATUS[case["status"]], (case["name"], r)
+        exact = case["functor2"] != "g2"
+        assert_rel(r.value.estimate, case["estimate"], 1e-15 if exact else 1e-13)
+        assert r.value.nevals == case["nevals"], (case["name"], r)
+
+
+def test_level_synchronous_equals_pool_on_mixed_batch(eng, monkeypatch):
+    """A 2-D batch with infinite ranges, dynamic y-ranges, per-integral points and budgets that run out for
+    some integrals: the level-synchronous rounds and the pool kernel agree bit for bit."""
+    import torch
+    from gkquad_b200 import Tolerance
+    n = 3000
+    rng = np.random.default_rng(3)
+    p = np.stack([-0.5 + rng.random(n), -0.5 + rng.random(n)])
+    off = np.arange(n + 1, dtype=np.int64)
+    budgets = rng.choice([300, 2000, 20000, 60000, 100000], n).astype(np.uint64)
+    out = {}
+    for mode in ("2", "3"):
+        monkeypatch.setenv("GKQ_NESTED_MODE", mode)
+        g1 = eng.integrate2_batch("d1_p", "const", -1.0, 1.0, fparams=p, yparams=[-1.0, 1.0], algo=ALGO["QAGP"],
+                                  tol=Tolerance.Relative(1e-6), max_evals=100000, pts_offsets=off,
+                                  pts_xy=np.ascontiguousarray(p.T), max_evals_each=budgets, n=n)
+        g2 = eng.integrate2_batch("rsqrt3", "const", -math.inf, math.inf, yparams=[-math.inf, math.inf], algo=ALGO["QAGS"],
+                                  tol=Tolerance.Relative(1e-5), max_evals=40000, n=1100)
+        g3 = eng.integrate2_batch("hemisphere_p", "circle", -1.0, 1.0, fparams=[1.0], yparams=[1.0], algo=ALGO["QAGS"],
+                                  tol=Tolerance.Relative(1e-8), max_evals=100000, n=1030)
+        out[mode] = (g1, g2, g3)
+    for a, b in zip(out["2"], out["3"]):
+        assert np.array_equal(a.estimate, b.estimate, equal_nan=True) and np.array_equal(a.delta, b.delta, equal_nan=True)
+        assert np.array_equal(a.nevals, b.nevals) and np.array_equal(a.status, b.status)
+    assert len(np.unique(out["3"][0].status)) > 1  # budgets did run out for some
