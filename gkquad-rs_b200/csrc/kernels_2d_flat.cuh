@@ -30,6 +30,9 @@
 namespace gkq {
 
 constexpr int FB = 128;  // threads per block of the flat kernels
+#ifndef GKQ_FLAT_MIN_BLOCKS
+#define GKQ_FLAT_MIN_BLOCKS 4
+#endif
 
 struct FlatBoardSink {
     double* est;
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(FB) k2_plan(const Batch2D P, int round) {
 
 // ---- inner: persistent self-refilling lanes over the round's tasks -------------------------------
 template <class F2T, bool QAGP, int NPARAMS>
-__global__ void __launch_bounds__(FB, 4) k2_inner(const Batch2D P) {
+__global__ void __launch_bounds__(FB, GKQ_FLAT_MIN_BLOCKS) k2_inner(const Batch2D P) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned long long t = (unsigned long long)blockIdx.x * FB + threadIdx.x;

@@ -441,7 +441,13 @@ __global__ void __launch_bounds__(PB, 4) k_nested_pool(const Batch2D P) {
                     }
                 }
                 const unsigned live = __ballot_sync(FULL, s.active);
-                if (live == 0u) break;
+                if (live == 0u) {
+                    // (nothing started in this pass -- the lanes drew tasks of an outer integral that is on
+                    // the exact path, or tasks that ended inside lane_start -- is not "board drained":
+                    // round 1 left the loop here and committed stale values for the tasks behind them)
+                    if (next >= T) break;
+                    continue;
+                }
 
                 TripPlan p;
                 p.ra0 = p.rb0 = p.ra1 = p.rb1 = 0.;
