@@ -47,6 +47,13 @@ __global__ void __launch_bounds__(BLOCK) k_fill_result_list(const unsigned int* 
         write_result(O, (long long)list[k], est, dlt, nev, st);
 }
 
+// Host entry: nevals and status of a chunk leave the device as ONE u32 (nevals << 3 | status):
+// 20 instead of 24 bytes per integral over a link that is the bound of the whole call.
+__global__ void __launch_bounds__(BLOCK) k_pack_nev_st(long long n, const uint32_t* nev, const uint32_t* st, uint32_t* out) {
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i < n) out[i] = (nev[i] << 3) | (st[i] & 7u);
+}
+
 // GKQ_FLAG_VALIDATE_INPUTS: any NaN among the first `n` entries of up to five optional arrays?
 __global__ void __launch_bounds__(BLOCK) k_any_nan(long long n, const double* a0, const double* a1, const double* a2,
                                                    const double* a3, unsigned int* flag) {
@@ -187,6 +194,9 @@ struct gkq_handle_s {
     double host_tail_share = 0.0;
     size_t stage_bytes = 0;
     char* stage_dev = nullptr;
+    uint32_t* pk_pin = nullptr;  // pinned landing area of the packed (nevals << 3 | status) words
+    size_t pk_cap = 0;
+    cudaEvent_t ev_out[MAX_CHUNKS] = {};
     double* fixed_pin = nullptr;  // pinned copy of the shared (stride-0) range / parameters
 
     // optional per-kernel timing (gkq_set_profiling): one CUDA event pair per launch
@@ -668,6 +678,7 @@ int gkq_create(int device, gkq_handle_t* out) {
     for (int k = 0; k < gkq_handle_s::MAX_CHUNKS; ++k) {
         ev(&h->ev_in[k]);
         ev(&h->ev_done[k]);
+        ev(&h->ev_out[k]);
     }
     ok = ok && cudaMallocHost(&h->fixed_pin, 64 * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMallocHost(&h->flat_ctl_host, 2 * sizeof(Ctl2)) == cudaSuccess;
@@ -728,7 +739,9 @@ int gkq_destroy(gkq_handle_t h) {
     for (int k = 0; k < gkq_handle_s::MAX_CHUNKS; ++k) {
         if (h->ev_in[k]) cudaEventDestroy(h->ev_in[k]);
         if (h->ev_done[k]) cudaEventDestroy(h->ev_done[k]);
+        if (h->ev_out[k]) cudaEventDestroy(h->ev_out[k]);
     }
+    cudaFreeHost(h->pk_pin);
     if (h->ev_c2) cudaEventDestroy(h->ev_c2);
     prof_clear(h);
     for (auto e : h->prof_pool) cudaEventDestroy(e);
@@ -1332,7 +1345,7 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
     const size_t fixed_bytes = 64 * 8, ctl_bytes = sizeof(Control) * MAXC;
     const size_t in_doubles = (size_t)((range_stride ? 2 : 0) + np_batch) * N;
     const int n_ov = ov_host ? (ov_host->abs_tol != nullptr) + (ov_host->rel_tol != nullptr) + (ov_host->max_evals != nullptr) : 0;
-    const size_t want = fixed_bytes + ctl_bytes + in_doubles * 8 + N * 24 + (size_t)n_ov * N * 8 + 256;
+    const size_t want = fixed_bytes + ctl_bytes + in_doubles * 8 + N * 24 + (size_t)n_ov * N * 8 + N * 4 + 256;
     if (want > h->stage_bytes) {
         if (h->stage_dev) GKQ_CUDA(h, cudaFree(h->stage_dev));
         h->stage_dev = nullptr;
@@ -1354,11 +1367,26 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
     uint32_t* d_st = d_nev + N;
     // per-integral tolerance / budget arrays (when given) behind the outputs
     gkq_overrides ov_dev = {nullptr, nullptr, nullptr};
+    uint32_t* d_pk = nullptr;
     {
         double* q = (double*)(d_st + N);
         if (ov_host && ov_host->abs_tol) { ov_dev.abs_tol = q; q += N; }
         if (ov_host && ov_host->rel_tol) { ov_dev.rel_tol = q; q += N; }
         if (ov_host && ov_host->max_evals) { ov_dev.max_evals = (const uint64_t*)q; q += N; }
+        d_pk = (uint32_t*)q;
+    }
+    // Packed result words (see k_pack_nev_st): when the bulk results of a chunk are final -- every path
+    // but the heavy-tail one, which ships the staged arrays whole at the end -- nevals and status cross
+    // the link as one word and the calling thread unpacks chunk c while chunk c + 1 is in flight.
+    const bool is_qags_call = cfg->algo == GKQ_ALGO_QAGS || (cfg->algo == GKQ_ALGO_AUTO && cfg->npoints == 0);
+    const bool heavy_tail_expected = is_qags_call && h->host_tail_fid == functor_id && h->host_tail_share > 1.0 / 16.0;
+    const bool packed = !heavy_tail_expected && cfg->max_evals < (1ull << 29) && getenv("GKQ_HOST_UNPACKED") == nullptr;
+    if (packed && N > h->pk_cap) {
+        if (h->pk_pin) GKQ_CUDA(h, cudaFreeHost(h->pk_pin));
+        h->pk_pin = nullptr;
+        h->pk_cap = 0;
+        GKQ_CUDA(h, cudaMallocHost(&h->pk_pin, (N + N / 8) * sizeof(uint32_t)));
+        h->pk_cap = N + N / 8;
     }
 
     // GKQ_HOST_TRACE=1: per-chunk timeline (timing events) printed to stderr -- tuning aid
@@ -1462,12 +1490,40 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
         mark(so);
         GKQ_CUDA(h, cudaMemcpyAsync(out_estimate + off, d_est + off, (size_t)m * 8, cudaMemcpyDeviceToHost, so));
         GKQ_CUDA(h, cudaMemcpyAsync(out_delta + off, d_dlt + off, (size_t)m * 8, cudaMemcpyDeviceToHost, so));
-        GKQ_CUDA(h, cudaMemcpyAsync(out_nevals + off, d_nev + off, (size_t)m * 4, cudaMemcpyDeviceToHost, so));
-        GKQ_CUDA(h, cudaMemcpyAsync(out_status + off, d_st + off, (size_t)m * 4, cudaMemcpyDeviceToHost, so));
+        if (packed) {
+            k_pack_nev_st<<<(unsigned)((m + BLOCK - 1) / BLOCK), BLOCK, 0, so>>>(m, d_nev + off, d_st + off, d_pk + off);
+            if ((rc = launch_check(h, "k_pack_nev_st"))) break;
+            GKQ_CUDA(h, cudaMemcpyAsync(h->pk_pin + off, d_pk + off, (size_t)m * 4, cudaMemcpyDeviceToHost, so));
+            GKQ_CUDA(h, cudaEventRecord(h->ev_out[c], so));
+        } else {
+            GKQ_CUDA(h, cudaMemcpyAsync(out_nevals + off, d_nev + off, (size_t)m * 4, cudaMemcpyDeviceToHost, so));
+            GKQ_CUDA(h, cudaMemcpyAsync(out_status + off, d_st + off, (size_t)m * 4, cudaMemcpyDeviceToHost, so));
+        }
         mark(so);
     }
     h->host_records_primed = false;
     h->cur = 0;
+
+    // Unpack chunk c (host) while the copies of the later chunks and the remainder kernel are in flight.
+    // Runs once, after everything has been ENQUEUED and before the first blocking wait of phase 3; the
+    // stragglers' patch is applied after it.
+    bool unpacked = false;
+    auto unpack_chunks = [&]() {
+        if (!packed || unpacked || rc != GKQ_OK) return;
+        unpacked = true;
+        for (int c = 0; c < nchunks; ++c) {
+            if (cudaEventSynchronize(h->ev_out[c]) != cudaSuccess) return;  // (reported by the stream checks below)
+            const uint32_t* pk = h->pk_pin + c_off[c];
+            uint32_t* nv = out_nevals + c_off[c];
+            uint32_t* sv = out_status + c_off[c];
+            const int64_t m = c_len[c];
+            for (int64_t i = 0; i < m; ++i) {
+                const uint32_t w = pk[i];
+                nv[i] = w >> 3;
+                sv[i] = w & 7u;
+            }
+        }
+    };
 
     // ---- phase 3: the stragglers of every chunk: one launch, results into the patch ---------------
     unsigned long long nrec = 0;
@@ -1485,7 +1541,7 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
         // correct for any count; which one is taken follows the share the PREVIOUS host call of this
         // functor saw (asking the device now would stall the enqueue behind the bulk: measured -5 %
         // on the smooth headline workload).
-        heavy_tail = h->host_tail_fid == functor_id && h->host_tail_share > 1.0 / 16.0;
+        heavy_tail = heavy_tail_expected;
     }
     if (have_records && heavy_tail) {
         const Outputs whole = {d_est, d_dlt, d_nev, d_st};  // record indices are batch-wide (idx_offset)
@@ -1522,6 +1578,7 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
                 return cudaMemcpyAsync(hv.st + lo, dv.st + lo, cnt * 4, cudaMemcpyDeviceToHost, h->s_compute);
             };
             GKQ_CUDA(h, fetch(0, first));
+            unpack_chunks();
             GKQ_CUDA(h, cudaStreamSynchronize(h->s_compute));
             nrec = R.rctl_host->count;
             if (nrec > first) {
@@ -1531,6 +1588,7 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
             R.tail_pending = false;
         }
     }
+    unpack_chunks();
     cudaError_t e1 = cudaStreamSynchronize(h->s_in);
     cudaError_t e2 = cudaStreamSynchronize(h->s_compute);
     cudaError_t e4 = cudaStreamSynchronize(h->s_compute2);

@@ -150,20 +150,21 @@ struct YRange {
 // tables (engine.cu), the launch tables and the explicit instantiations (inst_*.cu).
 // flops: counted from source for polynomial/rational bodies (add, sub,
 // mul, div, sqrt = 1); for transcendental bodies the DADD+DMUL+2*DFMA SASS count of one
-// evaluation (see profiles/functor_flops_r01.md for how they were obtained).
+// evaluation (see profiles/functor_flops_r01.md for how they were obtained; the pow / log functors were
+// re-measured with the engine's own pow / log: profiles/functor_flops_r02.csv).
 #define GKQ_F1_LIST(X)                       \
     X(F1_SQUARE, "square", 0, 1.0)           \
     X(F1_RECIP_P, "recip_p", 1, 1.0)         \
     X(F1_LORENTZ_P, "lorentz_p", 1, 4.0)     \
     X(F1_EXPCOS_P, "expcos_p", 2, 61.0)     \
     X(F1_GAUSS_P, "gauss_p", 1, 31.0)        \
-    X(F1_ABSPOW_P, "abspow_p", 2, 120.0)     \
-    X(F1_LOGABS_P, "logabs_p", 1, 45.0)      \
-    X(F1_F1, "f1", 0, 172.0)                 \
-    X(F1_F2, "f2", 0, 172.0)                 \
+    X(F1_ABSPOW_P, "abspow_p", 2, 68.0)     \
+    X(F1_LOGABS_P, "logabs_p", 1, 30.0)      \
+    X(F1_F1, "f1", 0, 104.0)                 \
+    X(F1_F2, "f2", 0, 104.0)                 \
     X(F1_F3, "f3", 0, 59.0)                 \
-    X(F1_F4, "f4", 0, 53.0)                  \
-    X(F1_F5, "f5", 0, 50.0)                  \
+    X(F1_F4, "f4", 0, 38.0)                  \
+    X(F1_F5, "f5", 0, 35.0)                  \
     X(F1_F6, "f6", 0, 6.0)                   \
     X(F1_EXP_P, "exp_p", 1, 30.0)            \
     X(F1_SQRT_SHIFT_P, "sqrt_shift_p", 1, 2.0)       \

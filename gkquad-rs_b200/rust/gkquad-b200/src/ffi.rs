@@ -132,4 +132,21 @@ extern "C" {
                            ms: *mut c_float) -> c_int;
     pub fn gkq_measure_fp64_peak(h: gkq_handle_t, repeats: c_int, flops_per_s: *mut c_double,
                                  ms: *mut c_double) -> c_int;
+    // multi-GPU: static block-cyclic shard + one gather of results (NCCL inside the library)
+    pub fn gkq_comm_get_unique_id(id_out: *mut c_void) -> c_int; // [GKQ_COMM_ID_BYTES]
+    pub fn gkq_comm_init(h: gkq_handle_t, nranks: c_int, rank: c_int, unique_id: *const c_void) -> c_int;
+    pub fn gkq_comm_destroy(h: gkq_handle_t) -> c_int;
+    pub fn gkq_comm_info(h: gkq_handle_t, nranks: *mut c_int, rank: *mut c_int) -> c_int;
+    pub fn gkq_shard_size(n_total: i64, nranks: c_int, rank: c_int, block: i64) -> i64;
+    pub fn gkq_shard_index(n_total: i64, nranks: c_int, rank: c_int, block: i64, j: i64) -> i64;
+    pub fn gkq_gather(h: gkq_handle_t, n_total: i64, block: i64, root: c_int, est: *const f64, dlt: *const f64,
+                      nev: *const u32, st: *const u32, g_est: *mut f64, g_dlt: *mut f64, g_nev: *mut u32,
+                      g_st: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn gkq_gather_range(h: gkq_handle_t, n_total: i64, block: i64, root: c_int, local_offset: i64,
+                            local_count: i64, est: *const f64, dlt: *const f64, nev: *const u32, st: *const u32,
+                            g_est: *mut f64, g_dlt: *mut f64, g_nev: *mut u32, g_st: *mut u32,
+                            stream: *mut c_void) -> c_int;
 }
+pub const GKQ_COMM_ID_BYTES: usize = 128;
+pub const GKQ_FLAG_SWAP_XY: i32 = 1;
+pub const GKQ_FLAG_VALIDATE_INPUTS: i32 = 2;

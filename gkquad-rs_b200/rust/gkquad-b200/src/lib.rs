@@ -151,3 +151,127 @@ algorithm!(QagsB200, ffi::GKQ_ALGO_QAGS, "replaces gkquad::single::algorithm::QA
 algorithm!(QagpB200, ffi::GKQ_ALGO_QAGP, "replaces gkquad::single::algorithm::QAGP (qagp.rs:20-64)");
 algorithm!(AutoB200, ffi::GKQ_ALGO_AUTO, "replaces gkquad::single::algorithm::AUTO (auto.rs:7-35)");
 algorithm!(QagB200, ffi::GKQ_ALGO_QAG, "replaces the deprecated gkquad::single::algorithm::QAG (qag.rs:16-60)");
+
+// ---- 2-D: the Algorithm2 seam (gkquad/src/double/algorithm/mod.rs:7-10) -----------------------------
+use gkquad::double::algorithm::Algorithm2;
+use gkquad::double::range::Rectangle;
+use gkquad::double::{Integrand2, IntegrationConfig2};
+
+/// A 2-D functor of the device registry, a y-range functor (`"const"` for a Rectangle, `"zero_to_x"`,
+/// `"circle"`: the DynamicY closures of double/range.rs:77-112 cannot cross the FFI) and SoA parameter
+/// batches for both.  `Integrand2` is implemented only to satisfy the trait bound.
+pub struct DeviceIntegrand2 {
+    pub functor: String,
+    pub fparams: Vec<Vec<f64>>,
+    pub yrange: String,
+    pub yparams: Vec<Vec<f64>>,
+    /// per-integral singular points in CSR form (offsets count (x, y) pairs); empty = config.points
+    pub pts_offsets: Vec<i64>,
+    pub pts_xy: Vec<f64>,
+}
+impl Integrand2 for DeviceIntegrand2 {
+    fn apply(&mut self, _x: (f64, f64)) -> f64 {
+        panic!("DeviceIntegrand2 is evaluated on the GPU; there is no CPU fallback")
+    }
+}
+impl DeviceIntegrand2 {
+    pub fn batch(&self) -> usize {
+        self.fparams.first().or(self.yparams.first()).map(|r| r.len()).unwrap_or(1)
+    }
+}
+
+impl EngineB200 {
+    /// `gkq_integrate2_batch_host`: every nest of the batch over the x-range `xr`; the y-range comes
+    /// from the integrand's y-range functor (a Rectangle passes its y-range as the two parameters of
+    /// `"const"`, double/algorithm/qags.rs:18-27).
+    fn run2(&mut self, f: &DeviceIntegrand2, xr: &Range, yconst: Option<&Range>, config: &IntegrationConfig2) -> IntegrationResult {
+        let n = f.batch();
+        let name = CString::new(f.functor.as_str()).unwrap();
+        let yname = CString::new(if yconst.is_some() { "const" } else { f.yrange.as_str() }).unwrap();
+        let fid = unsafe { ffi::gkq_functor_lookup(2, name.as_ptr()) };
+        let yid = unsafe { ffi::gkq_functor_lookup(0, yname.as_ptr()) };
+        assert!(fid >= 0 && yid >= 0, "unknown device functor {} / {}", f.functor, f.yrange);
+        let fflat: Vec<f64> = f.fparams.iter().flat_map(|r| r.iter().cloned()).collect();
+        let (yflat, ystride): (Vec<f64>, i64) = match yconst {
+            Some(r) => (vec![r.begin, r.end], 0),
+            None => (f.yparams.iter().flat_map(|r| r.iter().cloned()).collect(), if f.yparams.is_empty() { 0 } else { n as i64 }),
+        };
+        let pts: Vec<f64> = config.points.iter().flat_map(|p| [p.0, p.1]).collect();
+        let cfg = ffi::gkq_config {
+            algo: self.algo,
+            flags: 0,
+            tol: tol_to_ffi(&config.tolerance),
+            max_evals: config.max_evals as u64,
+            workspace_capacity: 0,
+            points: if pts.is_empty() { std::ptr::null() } else { pts.as_ptr() },
+            npoints: config.points.len() as i64,
+        };
+        self.last = BatchResult { estimate: vec![0.0; n], delta: vec![0.0; n], nevals: vec![0; n], status: vec![0; n] };
+        let csr = !f.pts_offsets.is_empty();
+        let rc = unsafe {
+            ffi::gkq_integrate2_batch_host(
+                self.h, &cfg, fid, yid, n as i64, &xr.begin, &xr.end, 0,
+                if fflat.is_empty() { std::ptr::null() } else { fflat.as_ptr() },
+                if fflat.is_empty() { 0 } else { n as i64 },
+                if yflat.is_empty() { std::ptr::null() } else { yflat.as_ptr() }, ystride,
+                if csr { f.pts_offsets.as_ptr() } else { std::ptr::null() },
+                if csr { f.pts_xy.as_ptr() } else { std::ptr::null() },
+                self.last.estimate.as_mut_ptr(), self.last.delta.as_mut_ptr(),
+                self.last.nevals.as_mut_ptr(), self.last.status.as_mut_ptr())
+        };
+        assert_eq!(rc, 0, "gkq_integrate2_batch_host failed");
+        self.last.get(0)
+    }
+}
+
+macro_rules! algorithm2 {
+    ($name:ident, $algo:expr, $doc:expr) => {
+        #[doc = $doc]
+        pub struct $name(EngineB200);
+        impl $name {
+            pub fn new(device: i32) -> Result<Self, String> {
+                Ok(Self(EngineB200::with_algo(device, $algo)?))
+            }
+            /// Every nest of the last `integrate` call (the trait returns integral 0, like the 1-D seam).
+            pub fn last_batch(&self) -> &BatchResult {
+                self.0.last_batch()
+            }
+            /// Inherent batch method: the whole batch at once, without going through `Integrator2`.
+            pub fn integrate_batch(&mut self, f: &DeviceIntegrand2, xr: &Range, yr: Option<&Range>,
+                                   config: &IntegrationConfig2) -> &BatchResult {
+                self.0.run2(f, xr, yr, config);
+                self.0.last_batch()
+            }
+        }
+        /// `Integrator2::with_algorithm(f, QagsB200_2::new(0)?)` over a Rectangle
+        /// (double/integrator.rs:80-87 -> this).
+        impl Algorithm2<DeviceIntegrand2, Rectangle> for $name {
+            fn integrate(&mut self, f: &mut DeviceIntegrand2, range: &Rectangle, config: &IntegrationConfig2) -> IntegrationResult {
+                self.0.run2(f, &range.xrange, Some(&range.yrange), config)
+            }
+        }
+    };
+}
+algorithm2!(Qags2B200, ffi::GKQ_ALGO_QAGS, "replaces gkquad::double::algorithm::QAGS2 (double/algorithm/qags.rs:18-97)");
+algorithm2!(Qagp2B200, ffi::GKQ_ALGO_QAGP, "replaces gkquad::double::algorithm::QAGP2 (double/algorithm/qagp.rs:22-139)");
+algorithm2!(Auto2B200, ffi::GKQ_ALGO_AUTO, "replaces gkquad::double::algorithm::AUTO2 (double/algorithm/auto.rs:15-36)");
+
+// ---- 1-D inherent batch methods (`integrate_batch`) -----------------------------
+impl QagsB200 {
+    pub fn integrate_batch(&mut self, f: &DeviceIntegrand, range: &Range, config: &IntegrationConfig) -> &BatchResult {
+        self.0.run(f, range, config);
+        self.0.last_batch()
+    }
+}
+impl QagpB200 {
+    pub fn integrate_batch(&mut self, f: &DeviceIntegrand, range: &Range, config: &IntegrationConfig) -> &BatchResult {
+        self.0.run(f, range, config);
+        self.0.last_batch()
+    }
+}
+impl AutoB200 {
+    pub fn integrate_batch(&mut self, f: &DeviceIntegrand, range: &Range, config: &IntegrationConfig) -> &BatchResult {
+        self.0.run(f, range, config);
+        self.0.last_batch()
+    }
+}
