@@ -61,7 +61,7 @@ def parse():
                     help="host threads (one handle each) that make the blocking host-entry calls of the e2e leg")
     ap.add_argument("--pipeline-depth", type=int, default=3,
                     help="handles / streams the independent batches alternate between (1 = one handle, one stream)")
-    ap.add_argument("--gather-chunks", type=int, default=4,
+    ap.add_argument("--gather-chunks", type=int, default=1,
                     help="N > 1: the last batch is computed and gathered in this many chunks (only the last chunk's transfer is exposed)")
     return ap.parse_args()
 
@@ -299,7 +299,8 @@ def _main(args, real_stdout):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world, real_stdout)
+        # (torchrun pins OMP_NUM_THREADS = 1; the oracle sizes its own std::thread pool from the hardware)
+        run_reference(args, rank, max(world, args.gpus), real_stdout)
         return
 
     import torch
@@ -392,10 +393,13 @@ def _main(args, real_stdout):
         S = sets[k % NSETS]
         pipe.run(S["plan"], S["lane"])
         if per_step_gather:
+            # the batch's stragglers are finished on its OWN lane (the lanes' latency-bound remainder
+            # launches overlap one another), then the side stream gathers it
+            e = pipe.engines[S["lane"]]
+            e._check(e.L.gkq_join(e.h, pipe._raw[S["lane"]]))
             ev = torch.cuda.Event()
             ev.record(pipe.streams[S["lane"]])
             comm.wait_event(ev)
-            pipe.engines[S["lane"]]._check(pipe.engines[S["lane"]].L.gkq_join(pipe.engines[S["lane"]].h, comm.cuda_stream))
             gather_set(k % NSETS, comm)
 
     def last_step_chunked(k):
@@ -405,12 +409,12 @@ def _main(args, real_stdout):
         for c in range(CH):
             pl, lane, lo, hi = chunk_plan(s, c)
             pipe.run(pl, lane)
+            e = pipe.engines[lane]
+            e._check(e.L.gkq_join(e.h, pipe._raw[lane]))  # the chunk's stragglers on its own lane ...
             ev = torch.cuda.Event()
             ev.record(pipe.streams[lane])
             comm.wait_event(ev)
-            e = pipe.engines[lane]
-            e._check(e.L.gkq_join(e.h, comm.cuda_stream))  # the chunk's stragglers, then its gather
-            gather_set(s, comm, lo, hi)
+            gather_set(s, comm, lo, hi)  # ... then its gather on the side stream, behind the next chunk's kernels
 
     def join():
         pipe.join()  # outstanding deferred remainders; the current stream waits for every lane
@@ -768,13 +772,13 @@ def run_secondary(args, eng, W, cn, rank, world, dev, steps, peak_flops, flush):
     fl_eval = eng.functor(W.dim, W.functor)[3]
     F_t = 6.0 if not (np.isfinite(W.a) and np.isfinite(W.b)) else 0.0
     w_eval = fl_eval + F_t + 8.0
-    tfl = evals * w_eval / (ms * 1e-3) / 1e12
+    tfl = evals * w_eval / (ms * 1e-3) / 1e12 / world  # per GPU
     res = {"workload": f"{W.name}: {W.description}; {W.algo}, {W.tol}, max_evals {W.max_evals}",
            "global_batch": int(count), "scaling": "strong" if two_d else "weak",
            "value": conv / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
            "converged_fraction": conv / count, "mean_nevals": evals / count, "evals_per_s": evals / (ms * 1e-3),
            "roofline": {"bound": "fp64", "achieved": tfl, "peak": peak_flops / 1e12, "unit": "TFLOP/s",
-                        "frac": tfl / (peak_flops / 1e12), "flops_per_eval": w_eval, "scope": "whole batch call"}}
+                        "frac": tfl / (peak_flops / 1e12), "flops_per_eval": w_eval, "scope": "whole batch call, per GPU"}}
     if two_d and world > 1:
         res["gather"] = "gkq_gather to rank 0 inside every timed step (20 B/integral)"
         if rank == 0:

@@ -164,16 +164,19 @@ def test_batch_bit_exact(eng, wname):
                                                         ("P1", 0.10), ("P2", 0.10)])
 def test_batch_tolerance_parity(eng, wname, max_nevals_mismatch):
     """Transcendental integrands: within tolerance of the oracle, identical status -- except for
-    noise-level flips (see gpu_common.compare): at most 1 per 10^4 integrals (measured: 2-4 per
-    10^6 on S1; the oracle flips 7 per 10^6 against itself when its cos moves by one ulp,
-    tools/libm_sensitivity.py), every one of them with both values agreeing within the tolerance."""
+    noise-level flips (see gpu_common.compare): at most 1 in these 20 000-integral samples, 2 for the
+    stress family S3 (measured: 4 per 2^20 on S1, 33 on S3; the oracle flips 7 per 10^6 against itself
+    when its cos moves by one ulp, tools/libm_sensitivity.py), every one of them with both values
+    agreeing within the tolerance."""
     from gpu_common import compare
     n = 20000 if wname.startswith("S") else 4000
     W, p, g, ref = _run_both(eng, wname, n)
     s = compare(g, ref, W.tol, label=wname)
     print(s)
     assert s["out_of_tol"] == 0, s
-    assert s["status_mismatch"] == s["noise_level_flips"] <= max(1, n // 10000), s
+    # (measured floor: 4 flips per 2^20 on S1, 33 on S3 -> expect 0.08 resp. 0.6 in 20 000; the full-size
+    # bound is asserted by test_gpu_round2.py::test_full_size_tolerance_parity)
+    assert s["status_mismatch"] == s["noise_level_flips"] <= (2 if wname == "S3" else 1), s
     assert s["nevals_mismatch"] <= max_nevals_mismatch * n, s
 
 
