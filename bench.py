@@ -61,6 +61,12 @@ def parse():
                     help="host threads (one handle each) that make the blocking host-entry calls of the e2e leg")
     ap.add_argument("--pipeline-depth", type=int, default=3,
                     help="handles / streams the independent batches alternate between (1 = one handle, one stream)")
+    ap.add_argument("--final-lane", default="express", choices=["express", "regular"],
+                    help="N > 1: the job's last batch (the one that is gathered) runs on a high-priority lane of the "
+                         "pipeline, so its transfer overlaps what the other lanes still compute; 'regular' = a normal lane")
+    ap.add_argument("--start-barrier", default="device", choices=["device", "host"],
+                    help="N > 1: after barrier + synchronize the ranks also meet in a one-element all-reduce on the "
+                         "stream right before the start event (their clocks start together); 'host' = host barrier only")
     ap.add_argument("--gather-chunks", type=int, default=1,
                     help="N > 1: the last batch is computed and gathered in this many chunks (only the last chunk's transfer is exposed)")
     return ap.parse_args()
@@ -322,7 +328,8 @@ def _main(args, real_stdout):
     algo = ALGO[W.algo]
     # throughput mode: `depth` handles on `depth` streams, batch k on lane k % depth (BatchPipeline);
     # lane 0's handle also serves the per-kernel profiling pass, the host entry (e2e) and the gathers
-    pipe = gk.BatchPipeline(local_rank, depth=args.pipeline_depth)
+    EXPRESS = world > 1 and args.final_lane == "express"
+    pipe = gk.BatchPipeline(local_rank, depth=args.pipeline_depth, express=EXPRESS)
     DEPTH = pipe.depth
     eng = pipe.engines[0]
     D.init_comm(eng)  # gkq_comm_init: the library's own NCCL communicator (torch only carries the id)
@@ -354,7 +361,7 @@ def _main(args, real_stdout):
         plan = pipe.plan_batch(s % DEPTH, W.functor, W.a, W.b, p_dev, out=out, **kw)
         sets.append(dict(p_host=p_host, p_dev=p_dev, kw=kw, plan=plan, out=out, lane=s % DEPTH))
     p_host = sets[0]["p_host"]
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    comm = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
     n_total = n * world
     root_out = None
     if world > 1 and rank == 0:
@@ -375,7 +382,7 @@ def _main(args, real_stdout):
             if "pts_offsets" in kw:
                 kw["pts_offsets"] = (kw["pts_offsets"][lo:hi + 1] - kw["pts_offsets"][lo]).contiguous()
                 kw["pts"] = kw["pts"][int(S["kw"]["pts_offsets"][lo]):int(S["kw"]["pts_offsets"][hi])].contiguous()
-            lane = c % DEPTH
+            lane = pipe.express_lane if EXPRESS else c % DEPTH
             pl = pipe.plan_batch(lane, W.functor, W.a, W.b, S["p_dev"][:, lo:hi].contiguous(),
                                  out=tuple(t[lo:hi] for t in S["out"]), **kw)
             chunk_plans[key] = (pl, lane, lo, hi)
@@ -422,6 +429,9 @@ def _main(args, real_stdout):
             torch.cuda.current_stream().wait_stream(comm)
 
     steps = args.steps
+    start_token = torch.zeros(1, device=dev)
+    if world > 1:
+        dist.all_reduce(start_token)  # (NCCL's lazy connection set-up happens here, not in the region)
     # nvidia-smi is started BEFORE the warm-up: while it attaches to the driver, CUDA launches of this
     # process stall for milliseconds, which must not fall into the timed region
     sampler = ClockSampler(local_rank)
@@ -449,6 +459,11 @@ def _main(args, real_stdout):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    if world > 1 and args.start_barrier == "device":
+        # the ranks leave the host barrier tens of microseconds apart; a one-element all-reduce on the
+        # stream lines their start events up on the device (rank 0's clock would otherwise also count how
+        # much later the slowest rank started, because the job ends with rank 0 receiving from everybody)
+        dist.all_reduce(start_token)
     e0.record()
     pipe.fork()  # the lanes start behind the start event
     t_region0 = time.perf_counter()
@@ -599,7 +614,9 @@ def _main(args, real_stdout):
             "config": workload_config(W, n, world),
             "details": {"pipeline_depth": DEPTH, "deferred_join": True,
                         "gather": (f"final gather of the last batch to rank 0 inside the timed region: gkq_gather_range, {CH} chunks, "
-                                   "20 B/integral, NCCL send/recv in the library") if world > 1 else "none (N=1)",
+                                   "20 B/integral, NCCL send/recv in the library; the last batch runs on "
+                                   + ("the pipeline's high-priority lane (its transfer overlaps the other lanes' kernels)" if EXPRESS else "a regular lane")
+                                   + f"; start barrier: {args.start_barrier}") if world > 1 else "none (N=1)",
                         "gathered_matches_local": gathered_ok,
                         "converged_fraction": converged / (n * world), "mean_nevals": float(nev_h.mean()),
                         "host_enqueue_ms_per_step": t_enq * 1e3},

@@ -125,10 +125,7 @@ struct gkq_handle_s {
         Control* ctl_host = nullptr;  // pinned mirror (profiling read-back, CSR split)
         bool ctl_pending = false;
         size_t cap_n = 0;
-        double* abs0 = nullptr;
-        double* park_est = nullptr;   // result0 of loop entrants, parked between the bulk kernels
-        double* park_dlt = nullptr;
-        unsigned int* park_nev = nullptr;
+        ParkRec* park = nullptr;      // result0 of loop entrants, parked between the bulk kernels
         unsigned int *list25 = nullptr, *listS = nullptr, *listP = nullptr;
         unsigned int* listLoop[2] = {nullptr, nullptr};
         cudaStream_t side = nullptr;  // chain 1 of the QAGS bulk
@@ -292,10 +289,7 @@ int ensure_batch_scratch(gkq_handle_t h, size_t n) {
     const size_t w = n + n / 8 + 1024;
     int rc;
     size_t have;
-    have = S.cap_n; if ((rc = grow(h, S.abs0, have, w))) return rc;
-    have = S.cap_n; if ((rc = grow(h, S.park_est, have, w))) return rc;
-    have = S.cap_n; if ((rc = grow(h, S.park_dlt, have, w))) return rc;
-    have = S.cap_n; if ((rc = grow(h, S.park_nev, have, w))) return rc;
+    have = S.cap_n; if ((rc = grow(h, S.park, have, w))) return rc;
     have = S.cap_n; if ((rc = grow(h, S.list25, have, w))) return rc;
     have = S.cap_n; if ((rc = grow(h, S.listS, have, w))) return rc;
     have = S.cap_n; if ((rc = grow(h, S.listP, have, w))) return rc;
@@ -618,7 +612,9 @@ int gkq_config_default(int dim, gkq_config* cfg) {
     return GKQ_OK;
 }
 
-int gkq_create(int device, gkq_handle_t* out) {
+int gkq_create(int device, gkq_handle_t* out) { return gkq_create_prio(device, 0, out); }
+
+int gkq_create_prio(int device, int stream_priority, gkq_handle_t* out) {
     if (!out) return fail(nullptr, GKQ_ERR_INVALID_ARGUMENT, "out is NULL");
     *out = nullptr;
     int ndev = 0;
@@ -650,7 +646,14 @@ int gkq_create(int device, gkq_handle_t* out) {
     FillL2<0>::go(h);
     bool ok = true;
     auto ev = [&](cudaEvent_t* e_) { ok = ok && cudaEventCreateWithFlags(e_, cudaEventDisableTiming) == cudaSuccess; };
-    auto strm = [&](cudaStream_t* s_) { ok = ok && cudaStreamCreateWithFlags(s_, cudaStreamNonBlocking) == cudaSuccess; };
+    // the handle's own streams (second chain, tail, host-entry pipeline) take the priority the caller
+    // gives its lane; CUDA clamps the value to the device's range (lower number = runs first)
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    const int prio = stream_priority < prio_hi ? prio_hi : (stream_priority > prio_lo ? prio_lo : stream_priority);
+    auto strm = [&](cudaStream_t* s_) {
+        ok = ok && cudaStreamCreateWithPriority(s_, cudaStreamNonBlocking, prio) == cudaSuccess;
+    };
     for (int c = 0; c < 2; ++c) {
         gkq_handle_s::Scratch& S = h->sc[c];
         ok = ok && cudaMalloc(&S.ctl, sizeof(Control)) == cudaSuccess &&
@@ -701,10 +704,7 @@ int gkq_destroy(gkq_handle_t h) {
         gkq_handle_s::Scratch& s = h->sc[c];
         cudaFree(s.ctl);
         cudaFreeHost(s.ctl_host);
-        cudaFree(s.abs0);
-        cudaFree(s.park_est);
-        cudaFree(s.park_dlt);
-        cudaFree(s.park_nev);
+        cudaFree(s.park);
         cudaFree(s.list25);
         cudaFree(s.listS);
         cudaFree(s.listP);
@@ -1056,10 +1056,7 @@ static int integrate_batch_ctx(gkq_handle_t h, const gkq_config* cfg, int functo
     P.out.nevals = out_nevals;
     P.out.status = out_status;
     P.ctl = ctl_zeroed ? ctl_zeroed : S.ctl;
-    P.abs0 = S.abs0;
-    P.park_est = S.park_est;
-    P.park_dlt = S.park_dlt;
-    P.park_nev = S.park_nev;
+    P.park = S.park;
     P.list25 = S.list25;
     P.listLoop[0] = S.listLoop[0];
     P.listLoop[1] = S.listLoop[1];

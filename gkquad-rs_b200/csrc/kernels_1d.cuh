@@ -28,10 +28,24 @@ constexpr int ABLOCK = 128;
 #endif
 constexpr int COOP_MAX_LIVE = GKQ_COOP_MAX_LIVE;
 // Resident 128-thread blocks per SM the adaptive kernels are compiled for (register cap
-// 65536 / (128 * N)): 6 -> 80 registers, 24 warps per SM (tuned with ncu, profiles/).
+// 65536 / (128 * N)).  Round 1 ran 6 (80 registers, 24 warps per SM); round 2 measured 5 and 4
+// (profiles/ab_adaptive_blocks_r02.txt, 1 M-integral batches): 4 blocks = 128 registers, 16 warps per SM
+// wins everywhere -- P0 0.787 -> 0.694 ms, P1 6.03 -> 4.72, S3 0.694 -> 0.621, the S1 straggler launch
+// 63 -> 53 us -- because (a) the list / epsilon-table code no longer spills and (b) the 2 x 12 samples
+// a transcendental body parks in local memory (192 B per thread) then fit L1 next to the lanes' shared
+// memory: 512 threads x 192 B = 98 KB against 137 KB of L1, where 768 threads needed 147 KB of 78 KB.
 #ifndef GKQ_ADAPTIVE_MIN_BLOCKS
-#define GKQ_ADAPTIVE_MIN_BLOCKS 6
+#define GKQ_ADAPTIVE_MIN_BLOCKS 4
 #endif
+// result0 of an integral that enters the main loop, parked by the initial pass that found it
+// unfinished until k_qags_first picks it up: ONE 32-byte record = one DRAM sector, written whole by its
+// thread and read back with two 16-byte loads (round 1 kept four SoA arrays: four partly written sectors
+// per entrant, each filled from DRAM first).  Handle-owned scratch: the caller's output arrays are never
+// read back -- they may be shared by several deferred calls in flight, or live in a peer GPU's memory.
+struct alignas(32) ParkRec {
+    double est, dlt, absv;  // estimate, delta, absvalue of the initial rule (qags.rs:315-376 returns them)
+    unsigned int nev, pad;
+};
 
 // Device-side control block of one batch call (zeroed by a memset node before the kernels).
 // The QAGS pipeline runs as two independent chains after the qk17 pass:
@@ -129,12 +143,7 @@ struct Batch1D {
     Outputs out;
     // scratch owned by the handle
     Control* ctl;
-    double* abs0;               // [n] absvalue of the initial rule (qags.rs:315-376 returns it)
-    // [n] result0 of the loop entrants, parked in handle-owned scratch: the caller's output arrays
-    // are written exactly once per integral (they may live in a peer GPU's memory)
-    double* park_est;
-    double* park_dlt;
-    unsigned int* park_nev;
+    ParkRec* park;              // [n] result0 of the loop entrants
     unsigned int* list25;       // [n]
     unsigned int* listLoop[2];  // [n] per chain: integrals entering the main loop
     int chain;                  // which chain this launch serves (k_qags_first)
@@ -306,14 +315,22 @@ __global__ void __launch_bounds__(IBLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : GKQ
                 else
                     toLoop = true;  // qags.rs:370-372 (`break`) or end of the 2-pass loop
             }
-            // finished integrals get their final answer; loop entrants park result0 in scratch
-            // (estimate, delta, nevals, absvalue) until k_qags_first picks them up
-            if (done) write_result(P.out, i, q.estimate, q.delta, nevals, status);
+            // EVERY integral of the pass writes its 24 output bytes -- finished integrals their final
+            // answer, the others result0 of this pass as a placeholder that the later kernels overwrite --
+            // so whole 32-byte sectors leave the SM and L2 never fills a partly written sector from DRAM
+            // (ncu, qk17 pass over 1 M integrals: dram read 37.9 -> 16.8 MB = the parameters, with the
+            // 27 % unfinished integrals no longer left as holes; profiles/S1_r02.md).
+            write_result(P.out, i, q.estimate, q.delta, nevals, status);
             if (toLoop) {
-                P.park_est[i] = q.estimate;
-                P.park_dlt[i] = q.delta;
-                P.park_nev[i] = nevals;
-                P.abs0[i] = q.absvalue;
+                ParkRec r;
+                r.est = q.estimate;
+                r.dlt = q.delta;
+                r.absv = q.absvalue;
+                r.nev = nevals;
+                r.pad = 0u;
+                double2* dst = reinterpret_cast<double2*>(P.park + i);
+                dst[0] = make_double2(r.est, r.dlt);
+                dst[1] = make_double2(r.absv, __hiloint2double((int)r.pad, (int)r.nev));
             }
             }
         }
@@ -358,8 +375,10 @@ __global__ void __launch_bounds__(FBLOCK, GKQ_FIRST_MIN_BLOCKS) k_qags_first(con
             double a, b;
             load_range(P, i, a, b, g.transform);
             load_functor(g.f, P, i, NPARAMS);
-            const double est0 = P.park_est[i], delta0 = P.park_dlt[i];
-            uint32_t nevals = P.park_nev[i];
+            const double2* src = reinterpret_cast<const double2*>(P.park + i);
+            const double2 pk0 = src[0], pk1 = src[1];
+            const double est0 = pk0.x, delta0 = pk0.y;
+            uint32_t nevals = (uint32_t)__double2loint(pk1.y);
             const Tol tol = load_tol(P, i);
             const unsigned long long max_evals = load_max_evals(P, i);
             const unsigned long long max_iters = (max_evals - nevals) / 50;
@@ -413,7 +432,7 @@ __global__ void __launch_bounds__(FBLOCK, GKQ_FIRST_MIN_BLOCKS) k_qags_first(con
                         for (int q = 0; q < MAX_PARAMS; ++q) rec.p[q] = g.f.p[q];
                         rec.est0 = est0;
                         rec.delta0 = delta0;
-                        rec.abs0 = P.abs0[i];
+                        rec.abs0 = pk1.x;
                         rec.e1 = q1.estimate;
                         rec.d1 = q1.delta;
                         rec.e2 = q2.estimate;

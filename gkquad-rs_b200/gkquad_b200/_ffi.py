@@ -49,7 +49,7 @@ class gkq_stats(C.Structure):
 
 # every symbol include/gkquad_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = [
-    "gkq_abi_version", "gkq_config_default", "gkq_create", "gkq_destroy", "gkq_last_error",
+    "gkq_abi_version", "gkq_config_default", "gkq_create", "gkq_create_prio", "gkq_destroy", "gkq_last_error",
     "gkq_functor_count", "gkq_functor_info", "gkq_functor_lookup", "gkq_integrate_batch",
     "gkq_integrate_batch_host", "gkq_integrate_batch_ex", "gkq_integrate_batch_host_ex", "gkq_integrate2_batch_ex", "gkq_integrate2_batch_host_ex", "gkq_integrate2_batch", "gkq_integrate2_batch_host", "gkq_qk_batch",
     "gkq_functor_eval_batch",
@@ -77,6 +77,7 @@ def lib():
     L.gkq_abi_version.restype = C.c_int
     L.gkq_config_default.argtypes = [C.c_int, C.POINTER(gkq_config)]
     L.gkq_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.gkq_create_prio.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
     L.gkq_destroy.argtypes = [vp]
     L.gkq_last_error.argtypes = [vp]
     L.gkq_last_error.restype = C.c_char_p

@@ -47,11 +47,12 @@ class Engine:
     """Owns a gkq_handle_t (device scratch, worklists, slabs).  Not thread-safe; calls are
     ordered on the CUDA stream that is current when they are made."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, stream_priority: int = 0):
         self.L = _ffi.lib()
         self.device = int(device)
         h = C.c_void_p()
-        rc = self.L.gkq_create(self.device, C.byref(h))
+        # stream_priority: CUDA priority of the streams the handle owns (gkq_create_prio)
+        rc = self.L.gkq_create_prio(self.device, int(stream_priority), C.byref(h))
         if rc != 0:
             raise _ffi.GkqError(rc, self.L.gkq_last_error(None).decode())
         self.h = h

@@ -19,19 +19,30 @@ from .engine import Engine
 
 
 class BatchPipeline:
-    def __init__(self, device: int = 0, depth: int = 2):
+    def __init__(self, device: int = 0, depth: int = 2, express: bool = False):
+        """`express`: one more lane (index `express_lane`) whose stream and handle-owned streams have
+        CUDA's high priority (gkq_create_prio): a batch run there leaves the GPU first although the
+        other lanes are busy -- for the batch whose results have to travel (a gather to another GPU)
+        while the rest of the pipeline still computes."""
         import torch
         assert depth >= 1
         self.device = int(device)
+        self._depth = depth
         self.engines = [Engine(device) for _ in range(depth)]
         self.streams = [torch.cuda.Stream(device=device) for _ in range(depth)]
+        self.express_lane = None
+        if express:
+            self.express_lane = depth
+            self.engines.append(Engine(device, stream_priority=-1))
+            self.streams.append(torch.cuda.Stream(device=device, priority=-1))
         self._raw = [s.cuda_stream for s in self.streams]  # cudaStream_t handles for the C ABI
         for e in self.engines:
             e.set_deferred_join(True)
 
     @property
     def depth(self):
-        return len(self.engines)
+        """Number of regular lanes (the express lane is not counted)."""
+        return self._depth
 
     def plan_batch(self, lane: int, *args, **kw):
         """Marshal a batch call on lane `lane` (see Engine.plan_batch); run it with run()."""

@@ -66,6 +66,7 @@ extern "C" {
     pub fn gkq_abi_version() -> c_int;
     pub fn gkq_config_default(dim: c_int, cfg: *mut gkq_config) -> c_int;
     pub fn gkq_create(device: c_int, out: *mut gkq_handle_t) -> c_int;
+    pub fn gkq_create_prio(device: c_int, stream_priority: c_int, out: *mut gkq_handle_t) -> c_int;
     pub fn gkq_destroy(h: gkq_handle_t) -> c_int;
     pub fn gkq_last_error(h: gkq_handle_t) -> *const c_char;
     pub fn gkq_functor_count(dim: c_int) -> c_int;

@@ -123,6 +123,11 @@ int gkq_config_default(int dim, gkq_config* cfg);
  * (survivor worklists, per-thread interval slabs, staging buffers), grown on demand and
  * reused, so a warm call allocates nothing. */
 int gkq_create(int device, gkq_handle_t* out);
+/* The same, with a CUDA stream priority for the streams the handle owns (0 = default, negative =
+ * scheduled first, clamped to the device's range).  For a caller that runs several handles on several
+ * streams and wants one lane's batches out first -- e.g. the batch whose results are gathered to another
+ * GPU while the other lanes still compute; pass the same priority to the stream of the calls. */
+int gkq_create_prio(int device, int stream_priority, gkq_handle_t* out);
 int gkq_destroy(gkq_handle_t h);
 /* Message of the last failure on this handle (or of the last failed gkq_create when h is
  * NULL).  Never NULL. */
