@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <atomic>
 #include <vector>
 
 #include "../../include/gkquad_b200.h"
@@ -1199,6 +1200,18 @@ int gkq_functor_eval_batch(gkq_handle_t h, int functor_id, int64_t n, const doub
 //     the bulk results of a chunk leave as soon as its bulk kernels end;
 //   * the stragglers of ALL chunks are finished by ONE launch of the persistent kernel at the end;
 //     their results reach the host as a compact patch that the CPU applies.
+// Host-entry calls in flight per device (several host threads, one handle each, overlap one call's
+// copies in with another's copies out): the chunk schedule follows it -- see the chunk schedule below.
+namespace {
+std::atomic<int> g_host_inflight[64];
+struct HostInflight {
+    int dev;
+    int seen;
+    explicit HostInflight(int d) : dev(d >= 0 && d < 64 ? d : 0) { seen = g_host_inflight[dev].fetch_add(1) + 1; }
+    ~HostInflight() { g_host_inflight[dev].fetch_sub(1); }
+};
+}  // namespace
+
 int gkq_integrate_batch_host(gkq_handle_t h, const gkq_config* cfg, int functor_id, int64_t n,
                              const double* a, const double* b, int64_t range_stride,
                              const double* params, int64_t param_stride,
@@ -1313,9 +1326,16 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
         return GKQ_OK;
     }
 
-    // chunk schedule
+    // chunk schedule.  A chunk's arrays cross the link as separate copies of 8 B x chunk: 2 MB copies
+    // (256 k integrals) reach 75 GB/s with both directions busy, 4 MB copies 89 GB/s
+    // (tools/pcie_aggregate_probe.py --sizes), but a bigger first chunk delays the call's first results.
+    // One call alone is latency-bound (its copies out trail its copies in): 256 k chunks.  With three or
+    // more host calls in flight on the device the link is what counts: 512 k chunks (S1, 1 M integrals,
+    // 4 host threads: 0.585 -> 0.541 ms per call; 1 thread: 0.94 -> 1.09; tools/e2e_sweep.py,
+    // profiles/e2e_sweep_r02.txt).
     constexpr int MAXC = gkq_handle_s::MAX_CHUNKS;
-    int64_t CH = 1 << 18, C0 = 1 << 16;
+    const HostInflight inflight(h->device);
+    int64_t CH = inflight.seen >= 3 ? (1 << 19) : (1 << 18), C0 = CH;
     if (const char* env = getenv("GKQ_HOST_CHUNK")) {  // tuning knobs (integrals per chunk)
         long long v = atoll(env);
         if (v >= 1024) CH = v;
@@ -1438,7 +1458,6 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
         GKQ_CUDA(h, cudaEventRecord(h->ev_in[c], h->s_in));
         mark(h->s_in);
     }
-
     // ---- phase 2: bulk kernels + result copies, chunk by chunk ------------------------------------
     rc = GKQ_OK;
     // Whatever way this function is left (every GKQ_CUDA below may return early), the handle must not

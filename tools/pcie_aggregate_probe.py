@@ -72,5 +72,25 @@ for mode in ("h2d", "d2h", "both"):
         if mode == "both":
             line += f"  => host-entry ceiling {sum(v) * 1e9 / 36.0:.3g} integrals/s at 36 B per integral"
         print(line, flush=True)
+if "--sizes" in sys.argv and rank == 0 and world == 1:
+    # link efficiency against copy size: both directions at once, copies of `mb` MB back to back on one
+    # stream per direction (the host entry moves a chunk's arrays as copies of 0.5 - 8 MB)
+    for mb in (0.5, 1, 2, 4, 8, 16):
+        nb = int(mb * (1 << 20))
+        per = max(1, (16 << 20) // nb)
+        torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(3):
+            t0 = time.perf_counter()
+            for r in range(20):
+                for c in range(per):
+                    with torch.cuda.stream(s_in):
+                        d_in[r % NBUF][c * nb:(c + 1) * nb].copy_(h_in[r % NBUF][c * nb:(c + 1) * nb], non_blocking=True)
+                    with torch.cuda.stream(s_out):
+                        h_out[r % NBUF][c * nb:(c + 1) * nb].copy_(d_out[r % NBUF][c * nb:(c + 1) * nb], non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = max(best, 2 * 20 * per * nb / dt / 1e9)
+        print(f"both directions, copies of {mb:4} MB: {best:5.1f} GB/s", flush=True)
 if world > 1:
     dist.destroy_process_group()
