@@ -67,6 +67,7 @@ def parse():
     ap.add_argument("--start-barrier", default="device", choices=["device", "host"],
                     help="N > 1: after barrier + synchronize the ranks also meet in a one-element all-reduce on the "
                          "stream right before the start event (their clocks start together); 'host' = host barrier only")
+    ap.add_argument("--no-pin", action="store_true", help="N > 1: do not bind each rank to its own slice of the host cores")
     ap.add_argument("--gather-chunks", type=int, default=1,
                     help="N > 1: the last batch is computed and gathered in this many chunks (only the last chunk's transfer is exposed)")
     return ap.parse_args()
@@ -313,6 +314,19 @@ def _main(args, real_stdout):
     import torch.distributed as dist
 
     assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device: there is no CPU fallback"
+    pinned_cores = None
+    if world > 1 and not args.no_pin:
+        # One slice of the host cores per rank (the boxes of this pool report ONE NUMA node, so there is no
+        # node to choose): a rank whose enqueueing thread is descheduled for a millisecond starves its GPU
+        # inside a 2.5 ms region and rank 0 then waits for its results (details.per_rank shows it).
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+            os.sched_setaffinity(0, set(mine))
+            pinned_cores = [mine[0], mine[-1]]
+        except Exception:
+            pinned_cores = None
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
     if world > 1:
@@ -423,8 +437,12 @@ def _main(args, real_stdout):
             comm.wait_event(ev)
             gather_set(s, comm, lo, hi)  # ... then its gather on the side stream, behind the next chunk's kernels
 
-    def join():
+    ev_compute = torch.cuda.Event(enable_timing=True)
+
+    def join(mark=False):
         pipe.join()  # outstanding deferred remainders; the current stream waits for every lane
+        if mark:
+            ev_compute.record()  # every lane's kernels are done; what follows is the gather's exposed part
         if world > 1:
             torch.cuda.current_stream().wait_stream(comm)
 
@@ -455,6 +473,9 @@ def _main(args, real_stdout):
     # The path shards with no data-path collective: each rank's results stay in its HBM; the job ends
     # with the gather of the last batch to rank 0 (inside the region).
     pipe.reset_stats()
+    import gc
+    gc.collect()
+    gc.disable()  # (no collector pause between two launches of the region)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
@@ -473,15 +494,26 @@ def _main(args, real_stdout):
         comm.wait_stream(torch.cuda.current_stream())
         last_step_chunked(steps - 1)
     t_enq = (time.perf_counter() - t_region0) / steps
-    join()  # ... and the end event behind every lane (and the side stream)
+    join(mark=True)  # ... and the end event behind every lane (and the side stream)
     e1.record()
     torch.cuda.synchronize()
     t_region1 = time.perf_counter()
+    gc.enable()
     if world > 1:
         dist.barrier()
     launches = pipe.kernel_launches()  # our kernels only (NCCL's are not counted)
     total_ms = e0.elapsed_time(e1)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    # diagnosis of the multi-GPU tail: per rank, the whole region, the part up to the last kernel of any
+    # lane, and how long the host took to enqueue the region
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([total_ms, e0.elapsed_time(ev_compute), (t_region1 - t_region0) * 1e3, t_enq * steps * 1e3],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"region_ms": [round(float(x[0]), 4) for x in allr], "kernels_done_ms": [round(float(x[1]), 4) for x in allr],
+                    "host_wall_ms": [round(float(x[2]), 4) for x in allr], "host_enqueue_ms": [round(float(x[3]), 4) for x in allr]}
     # snapshot of what the timed region wrote (the profiling pass below re-runs set 0)
     timed_out = tuple(x.clone() for x in sets[0]["out"])
     conv = sum(float((S["out"][3] == 0).sum().item()) for S in sets) / NSETS  # mean per step
@@ -619,7 +651,8 @@ def _main(args, real_stdout):
                                    + f"; start barrier: {args.start_barrier}") if world > 1 else "none (N=1)",
                         "gathered_matches_local": gathered_ok,
                         "converged_fraction": converged / (n * world), "mean_nevals": float(nev_h.mean()),
-                        "host_enqueue_ms_per_step": t_enq * 1e3},
+                        "host_enqueue_ms_per_step": t_enq * 1e3, "per_rank": per_rank,
+                        "host_cores_of_rank0": pinned_cores},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "configs": configs,
         }
