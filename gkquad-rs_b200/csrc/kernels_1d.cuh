@@ -351,10 +351,13 @@ __global__ void __launch_bounds__(IBLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : GKQ
 #ifndef GKQ_FIRST_BLOCK
 #define GKQ_FIRST_BLOCK 128
 #endif
-// 6 blocks per SM (80 registers): with batches pipelined (BatchPipeline) the single wave that 7 blocks
-// at 72 registers bought matters less than their spills (step 0.1185 -> 0.1172 ms, profiles/S1_r01.md)
+// 5 blocks per SM (96 registers).  Round 1 went from 7 blocks (72 registers, one wave) to 6 (80): with
+// batches pipelined (BatchPipeline) a single wave matters less than the spills (step 0.1185 -> 0.1172 ms,
+// profiles/S1_r01.md).  Round 2 measured 6 / 5 / 4 (profiles/ab_adaptive_blocks_r02.txt, last block): the
+// kernel alone 37.8 / 35.8 / 34.0 us, the pipelined S1 step 0.1170 / 0.1163 / 0.1177 ms, I1 0.521 / 0.513 /
+// 0.507 ms -- all within 3 %; 5 is never worse than 6.
 #ifndef GKQ_FIRST_MIN_BLOCKS
-#define GKQ_FIRST_MIN_BLOCKS 6
+#define GKQ_FIRST_MIN_BLOCKS 5
 #endif
 constexpr int FBLOCK = GKQ_FIRST_BLOCK;
 template <class F, int NPARAMS>

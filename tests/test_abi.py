@@ -68,6 +68,9 @@ def test_no_device_means_no_compute():
     with pytest.raises(GkqError) as e:
         Engine(0)
     assert e.value.code == -3 and "no CPU fallback" in str(e.value)
+    with pytest.raises(GkqError) as e:  # the priority variant (gkq_create_prio) refuses the same way
+        Engine(0, stream_priority=-1)
+    assert e.value.code == -3
     L = __import__("gkquad_b200")._ffi.lib()
     assert L.gkq_last_error(None)  # message of the failed create is retrievable
     # NULL handle is rejected, not dereferenced

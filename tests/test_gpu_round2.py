@@ -324,3 +324,69 @@ def test_level_synchronous_equals_pool_on_mixed_batch(eng, monkeypatch):
         assert np.array_equal(a.estimate, b.estimate, equal_nan=True) and np.array_equal(a.delta, b.delta, equal_nan=True)
         assert np.array_equal(a.nevals, b.nevals) and np.array_equal(a.status, b.status)
     assert len(np.unique(out["3"][0].status)) > 1  # budgets did run out for some
+
+
+# ---- round 2, second half: express lane, host calls in flight --------------------------------------
+def test_express_lane_matches_regular_lanes(eng):
+    """BatchPipeline(express=True): the extra lane's handle and streams carry CUDA's high priority
+    (gkq_create_prio).  Priority changes the order kernels are scheduled in, never a result: the same
+    batch on the express lane, on a regular lane and on a plain engine is bit-identical, also while the
+    regular lanes are busy with other batches."""
+    import torch
+    import gkquad_b200 as gk
+    from gkquad_b200.workloads import WORKLOADS
+    W = WORKLOADS["S3"]
+    n = 50_000
+    ps = [torch.as_tensor(W.make_params(k * n, n), device="cuda:0") for k in range(3)]
+    want = [eng.integrate_batch(W.functor, W.a, W.b, p, algo=ALGO[W.algo], tol=W.tol, n=n).numpy() for p in ps]
+    pipe = gk.BatchPipeline(0, depth=2, express=True)
+    try:
+        assert pipe.depth == 2 and pipe.express_lane == 2 and len(pipe.engines) == 3
+        lanes = [0, 1, pipe.express_lane]
+        plans = [pipe.plan_batch(lanes[k], W.functor, W.a, W.b, ps[k], algo=ALGO[W.algo], tol=W.tol, n=n) for k in range(3)]
+        pipe.fork()
+        for _ in range(4):
+            for k in range(3):
+                pipe.run(plans[k], lanes[k])
+        pipe.join()
+        torch.cuda.synchronize()
+        for k in range(3):
+            g = plans[k].result.numpy()
+            assert np.array_equal(g.estimate, want[k].estimate) and np.array_equal(g.delta, want[k].delta), k
+            assert np.array_equal(g.nevals, want[k].nevals) and np.array_equal(g.status, want[k].status), k
+    finally:
+        pipe.close()
+
+
+def test_host_entry_calls_in_flight_are_bit_identical(eng):
+    """Four host threads with one handle each make the blocking host-entry call at the same time: from three
+    calls in flight on, the library moves the batch in 512 k chunks instead of 256 k (engine.cu, chunk
+    schedule).  The chunking and the concurrency change the timeline only: every thread's outputs are
+    bit-identical to the same batch integrated alone."""
+    import threading
+    import gkquad_b200 as gk
+    from gkquad_b200.workloads import WORKLOADS
+    W = WORKLOADS["S1"]
+    n = (1 << 20) + 12345  # > 2 chunks of 512 k, ragged end
+    nt = 4
+    params = [W.make_params(t * n, n) for t in range(nt)]
+    want = [eng.integrate_batch(W.functor, W.a, W.b, p, algo=ALGO[W.algo], tol=W.tol, n=n).numpy() for p in params]
+    engines = [gk.Engine(0) for _ in range(nt)]
+    got = [[None] * 3 for _ in range(nt)]
+
+    def work(t):
+        for r in range(3):
+            got[t][r] = engines[t].integrate_batch(W.functor, W.a, W.b, params[t], algo=ALGO[W.algo], tol=W.tol, n=n).numpy()
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(nt)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    for t in range(nt):
+        for r in range(3):
+            g = got[t][r]
+            assert g is not None, (t, r)
+            assert np.array_equal(g.estimate, want[t].estimate) and np.array_equal(g.delta, want[t].delta), (t, r)
+            assert np.array_equal(g.nevals, want[t].nevals) and np.array_equal(g.status, want[t].status), (t, r)
+    for e in engines:
+        e.close()
