@@ -67,6 +67,8 @@ def parse():
     ap.add_argument("--start-barrier", default="device", choices=["device", "host"],
                     help="N > 1: after barrier + synchronize the ranks also meet in a one-element all-reduce on the "
                          "stream right before the start event (their clocks start together); 'host' = host barrier only")
+    ap.add_argument("--force-express", action="store_true",
+                    help="diagnostics at N = 1: run the last batch on the express lane as the N > 1 path does (no gather)")
     ap.add_argument("--no-pin", action="store_true", help="N > 1: do not bind each rank to its own slice of the host cores")
     ap.add_argument("--gather-chunks", type=int, default=1,
                     help="N > 1: the last batch is computed and gathered in this many chunks (only the last chunk's transfer is exposed)")
@@ -342,7 +344,7 @@ def _main(args, real_stdout):
     algo = ALGO[W.algo]
     # throughput mode: `depth` handles on `depth` streams, batch k on lane k % depth (BatchPipeline);
     # lane 0's handle also serves the per-kernel profiling pass, the host entry (e2e) and the gathers
-    EXPRESS = world > 1 and args.final_lane == "express"
+    EXPRESS = (world > 1 or args.force_express) and args.final_lane == "express"
     pipe = gk.BatchPipeline(local_rank, depth=args.pipeline_depth, express=EXPRESS)
     DEPTH = pipe.depth
     eng = pipe.engines[0]
@@ -437,6 +439,12 @@ def _main(args, real_stdout):
             comm.wait_event(ev)
             gather_set(s, comm, lo, hi)  # ... then its gather on the side stream, behind the next chunk's kernels
 
+    def last_step_express_only(k):
+        pl, lane, lo, hi = chunk_plan(k % NSETS, 0)
+        pipe.run(pl, lane)
+        e = pipe.engines[lane]
+        e._check(e.L.gkq_join(e.h, pipe._raw[lane]))
+
     ev_compute = torch.cuda.Event(enable_timing=True)
 
     def join(mark=False):
@@ -461,11 +469,14 @@ def _main(args, real_stdout):
     for k in range(max(18 * DEPTH, 2 * NSETS, args.warmup, 3)):
         step(k)
     join()
-    if world > 1:
+    if world > 1 or EXPRESS:
         for s in range(NSETS):  # chunk plans are marshalled (and their scratch sized) outside the region
             for c in range(CH):
                 chunk_plan(s, c)
-        last_step_chunked((steps - 1) % NSETS)
+        if world > 1:
+            last_step_chunked((steps - 1) % NSETS)
+        else:
+            last_step_express_only((steps - 1) % NSETS)
         join()
     torch.cuda.synchronize()
 
@@ -488,11 +499,13 @@ def _main(args, real_stdout):
     e0.record()
     pipe.fork()  # the lanes start behind the start event
     t_region0 = time.perf_counter()
-    for k in range(steps - 1 if world > 1 else steps):
+    for k in range(steps - 1 if (world > 1 or EXPRESS) else steps):
         step(k)
     if world > 1:
         comm.wait_stream(torch.cuda.current_stream())
         last_step_chunked(steps - 1)
+    elif EXPRESS:
+        last_step_express_only(steps - 1)
     t_enq = (time.perf_counter() - t_region0) / steps
     join(mark=True)  # ... and the end event behind every lane (and the side stream)
     e1.record()
