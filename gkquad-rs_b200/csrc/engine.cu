@@ -1176,7 +1176,13 @@ int gkq_qk_batch(gkq_handle_t h, int rule, int functor_id, int64_t n, const doub
 
 int gkq_functor_eval_batch(gkq_handle_t h, int functor_id, int64_t n, const double* x,
                            const double* params, int64_t param_stride, double* y, void* stream) {
+    return gkq_functor_eval_batch_ex(h, functor_id, n, x, params, param_stride, y, 0, stream);
+}
+
+int gkq_functor_eval_batch_ex(gkq_handle_t h, int functor_id, int64_t n, const double* x,
+                              const double* params, int64_t param_stride, double* y, int mode, void* stream) {
     if (!h) return GKQ_ERR_INVALID_ARGUMENT;
+    if (mode != 0 && mode != 1) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "mode must be 0 or 1");
     if (functor_id < 0 || functor_id >= F1_COUNT) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "unknown functor id");
     if (n < 0 || !x || !y) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "bad argument");
     if (F1_TABLE[functor_id].nparams > 0 && !params) return fail(h, GKQ_ERR_INVALID_ARGUMENT, "params is NULL");
@@ -1188,7 +1194,7 @@ int gkq_functor_eval_batch(gkq_handle_t h, int functor_id, int64_t n, const doub
     P.params = params;
     P.param_stride = param_stride;
     const int grid = (int)((n + BLOCK - 1) / BLOCK);
-    h->l1[functor_id].eval(P, x, y, grid, (cudaStream_t)stream);
+    h->l1[functor_id].eval(P, x, y, mode, grid, (cudaStream_t)stream);
     return launch_check(h, "k_eval");
 }
 

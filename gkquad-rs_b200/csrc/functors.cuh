@@ -39,6 +39,7 @@ enum F1Id : int {
 template <int ID> struct F1;
 // BODY computes f(x) with the math policy `m` (m.exp, m.cos, m.sin, m.log, m.pow):
 //   eval(x, FastMath&)  branch-free sample; clears m.ok when an argument leaves the fast range
+//                       (m.div / m.sqrt: IEEE division / square root without nvcc's slow-path branch)
 //   operator()(x)       always-valid sample (SafeMath)
 //   GKQ_F1P: the body only uses + - * / and m.exp / m.cos / m.sin, so it also instantiates on the
 //   two-lane type D2 and a node pair is evaluated with interleaved chains (PAIRWISE).
@@ -63,30 +64,30 @@ template <int ID> struct F1;
 #define GKQ_F1P(ID, HEAVY_, BODY) GKQ_F1_IMPL(ID, HEAVY_, true, BODY)
 #endif
 GKQ_F1(F1_SQUARE, false, return x * x;)                                   // benches/single.rs:11
-GKQ_F1(F1_RECIP_P, false, return p[0] / x;)                               // benches/single.rs:20
-GKQ_F1(F1_LORENTZ_P, false, return 1.0 / (1.0 + p[0] * (x * x));)         // benches/single.rs:32
+GKQ_F1(F1_RECIP_P, false, return m.div(p[0], x);)                               // benches/single.rs:20
+GKQ_F1(F1_LORENTZ_P, false, return m.div(1.0, 1.0 + p[0] * (x * x));)         // benches/single.rs:32
 GKQ_F1P(F1_EXPCOS_P, true, return m.exp(-p[0] * x) * m.cos(p[1] * x);)         // S1 / S3
 GKQ_F1P(F1_GAUSS_P, true, return m.exp(-p[0] * (x * x));)                    // I2
 GKQ_F1(F1_ABSPOW_P, true, return m.pow(fabs(x - p[0]), -p[1]);)             // P1
 GKQ_F1(F1_LOGABS_P, true, return m.log(fabs(x - p[0]));)                    // P2
-GKQ_F1(F1_F1, true, return m.pow(x, 2.6) * m.log(1. / x);)                    // functions.rs:3-5
-GKQ_F1(F1_F2, true, return m.pow(x, -0.9) * m.log(1. / x);)                   // functions.rs:8-10
+GKQ_F1(F1_F1, true, return m.pow(x, 2.6) * m.log(m.div(1., x));)                    // functions.rs:3-5
+GKQ_F1(F1_F2, true, return m.pow(x, -0.9) * m.log(m.div(1., x));)                   // functions.rs:8-10
 GKQ_F1P(F1_F3, true, return m.cos(2.4622888266898326 * m.sin(x));)             // functions.rs:13-15 (2^1.3)
-GKQ_F1(F1_F4, true, return m.log(1. / x);)                                  // functions.rs:17-19
+GKQ_F1(F1_F4, true, return m.log(m.div(1., x));)                                  // functions.rs:17-19
 GKQ_F1(F1_F5, true, double x2 = x * x;
        return x2 * x * m.log(fabs((x2 - 1.) * (x2 - 2.)));)                 // functions.rs:22-25
 GKQ_F1(F1_F6, false, double x2 = x * x; double x3 = x2 * x;
-       return 1.0 / (x3 - x2 + x - 1.);)                                  // functions.rs:27-31
+       return m.div(1.0, x3 - x2 + x - 1.);)                                  // functions.rs:27-31
 GKQ_F1P(F1_EXP_P, true, return m.exp(p[0] * x);)
-GKQ_F1(F1_SQRT_SHIFT_P, false, return sqrt(x - p[0]);)
-GKQ_F1(F1_INV_ABS_SHIFT_P, false, return 1.0 / fabs(x - p[0]);)
+GKQ_F1(F1_SQRT_SHIFT_P, false, return m.sqrt(x - p[0]);)
+GKQ_F1(F1_INV_ABS_SHIFT_P, false, return m.div(1.0, fabs(x - p[0]));)
 GKQ_F1P(F1_COS_P, true, return m.cos(p[0] * x);)
 GKQ_F1P(F1_SIN_P, true, return m.sin(p[0] * x);)
-GKQ_F1(F1_SEMICIRCLE_P, false, return sqrt(p[0] - x * x);)                  // examples/sphere.rs:11 (p0 = 1)
+GKQ_F1(F1_SEMICIRCLE_P, false, return m.sqrt(p[0] - x * x);)                  // examples/sphere.rs:11 (p0 = 1)
 // examples/wallis_integral.rs:13: (x * PI).sin().powi(m), m = p0; powi = compiler-rt __powidf2
 GKQ_F1(F1_SINPOW_P, true, double s = m.sin(x * 3.141592653589793); int n = (int)p[0];
        double r = 1.0; for (int k = n < 0 ? -n : n;;) { if (k & 1) r *= s; k >>= 1; if (k == 0) break; s *= s; }
-       return n < 0 ? 1.0 / r : r;)
+       return n < 0 ? m.div(1.0, r) : r;)
 #undef GKQ_F1
 #undef GKQ_F1P
 #undef GKQ_F1_IMPL
@@ -112,18 +113,18 @@ template <int ID> struct F2;
         }                                                                             \
     };
 GKQ_F2(F2_XY, false, return x * y;)                                       // benches/double.rs:10
-GKQ_F2(F2_RECIP_XY_P, false, return p[0] / (x * y);)                      // benches/double.rs:19
+GKQ_F2(F2_RECIP_XY_P, false, return m.div(p[0], x * y);)                      // benches/double.rs:19
 GKQ_F2(F2_RSQRT3, false, double denom = 1.0 + x * x + y * y;
-       return 1.0 / (denom * sqrt(denom));)                               // benches/double.rs:31-33
+       return m.div(1.0, denom * m.sqrt(denom));)                               // benches/double.rs:31-33
 GKQ_F2(F2_G1, false, return 1.0 - x * y;)                                 // functions.rs:37-39
-GKQ_F2(F2_G2, true, return m.exp(y / x);)                                   // functions.rs:41-43
-GKQ_F2(F2_G3, false, return sqrt(0.25 - x * x - y * y);)                  // functions.rs:45-47
-GKQ_F2(F2_G4, false, double a = 1.0 + x + y; return 1.0 / (a * (a * a));) // functions.rs:49-51 powi(3)
-GKQ_F2(F2_GP1, false, return 1.0 / sqrt(fabs(x) + fabs(y));)              // functions.rs:54-56
-GKQ_F2(F2_GP2, false, return x / (x * x + y * y);)                        // functions.rs:58-60
-GKQ_F2(F2_GP3, false, return 0.5 / sqrt(x * x + y * y);)                  // functions.rs:62-64
-GKQ_F2(F2_D1_P, false, return 1.0 / sqrt(fabs(x - p[0]) + fabs(y - p[1]));)  // D1
-GKQ_F2(F2_HEMISPHERE_P, false, return sqrt(p[0] - x * x - y * y);)        // examples/sphere.rs:23 (p0 = 1)
+GKQ_F2(F2_G2, true, return m.exp(m.div(y, x));)                                   // functions.rs:41-43
+GKQ_F2(F2_G3, false, return m.sqrt(0.25 - x * x - y * y);)                  // functions.rs:45-47
+GKQ_F2(F2_G4, false, double a = 1.0 + x + y; return m.div(1.0, a * (a * a));) // functions.rs:49-51 powi(3)
+GKQ_F2(F2_GP1, false, return m.div(1.0, m.sqrt(fabs(x) + fabs(y)));)              // functions.rs:54-56
+GKQ_F2(F2_GP2, false, return m.div(x, x * x + y * y);)                        // functions.rs:58-60
+GKQ_F2(F2_GP3, false, return m.div(0.5, m.sqrt(x * x + y * y));)                  // functions.rs:62-64
+GKQ_F2(F2_D1_P, false, return m.div(1.0, m.sqrt(fabs(x - p[0]) + fabs(y - p[1])));)  // D1
+GKQ_F2(F2_HEMISPHERE_P, false, return m.sqrt(p[0] - x * x - y * y);)        // examples/sphere.rs:23 (p0 = 1)
 #undef GKQ_F2
 
 // ---- y-range functors: run-time switch (evaluated once per inner integral) -------------

@@ -140,6 +140,34 @@ template <class F>
 struct Wrapped {
     F f;
     bool transform;
+    static constexpr bool HEAVY = F::HEAVY;
+    // Branch-free forms for a caller that keeps ONE FastMath for a whole rule (qk_rule_light): no
+    // re-evaluation here, the caller redoes the rule when m.ok went false.
+    template <bool TR>
+    GKQ_DEV void pair_fast(double x1, double x2, double& f1, double& f2, FastMath& m) const {
+        double c1 = 1., c2 = 1.;
+        if (TR) {
+            c1 = m.div(1., 1. - fabs(x1));
+            c2 = m.div(1., 1. - fabs(x2));
+            x1 = x1 * c1;
+            x2 = x2 * c2;
+        }
+        f1 = f.eval(x1, m);
+        f2 = f.eval(x2, m);
+        if (TR) {
+            f1 = f1 * c1 * c1;
+            f2 = f2 * c2 * c2;
+        }
+    }
+    template <bool TR>
+    GKQ_DEV double at_fast(double x, FastMath& m) const {
+        if (TR) {
+            const double coef = m.div(1., 1. - fabs(x));
+            const double x2 = x * coef;
+            return f.eval(x2, m) * coef * coef;
+        }
+        return f.eval(x, m);
+    }
     // TR = whether the infinite-range map is on, as a compile-time constant (kernels that hoist
     // the test out of the node loop); the run-time forms below dispatch on `transform`.
     template <bool TR>
@@ -164,7 +192,7 @@ struct Wrapped {
             x1 = x1 * c1;
             x2 = x2 * c2;
         }
-        FastMath m;
+        PairMath m;
         if constexpr (F::PAIRWISE) {
             const D2 r = f.eval(D2{x1, x2}, m);  // both samples through the same statements (ILP 2)
             f1 = r.a;
@@ -288,6 +316,43 @@ GKQ_DEV QK qk_rule_smem(const G& g, double a, double b, double* fv, int stride) 
     return qk_rule_smem_fixed<N, false>(g, a, b, fv, stride);
 }
 
+// The rule for a body WITHOUT transcendental calls, fully unrolled: all 2N+1 samples run through the
+// branch-free math (m.div / m.sqrt, gk_math.cuh) in ONE basic block, so ptxas overlaps the dependent
+// chains of as many samples as the registers hold; if any operand left the fast range (denormal-range
+// quotients, huge divisors, negative or tiny radicands) the whole rule is redone by the out-of-line
+// always-valid version.  Same operations, same order, same results.
+template <int N, bool TR, class G>
+__device__ __noinline__ QK qk_rule_slow(const G& g, double a, double b) {
+    using R = Rule<N>;
+    double fv1[N], fv2[N];
+    const double center = 0.5 * (a + b);
+    const double half_length = 0.5 * (b - a);
+#pragma unroll 1
+    for (int j = 0; j < N; ++j) {
+        double abscissa = half_length * R::xgk(j);
+        fv1[j] = g.template at<TR>(center - abscissa);
+        fv2[j] = g.template at<TR>(center + abscissa);
+    }
+    const double f_center = g.template at<TR>(center);
+    return qk_reduce<N>(fv1, fv2, f_center, a, b);
+}
+template <int N, bool TR, class G>
+GKQ_DEV QK qk_rule_light(const G& g, double a, double b) {
+    using R = Rule<N>;
+    double fv1[N], fv2[N];
+    const double center = 0.5 * (a + b);
+    const double half_length = 0.5 * (b - a);
+    FastMath m;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double abscissa = half_length * R::xgk(j);
+        g.template pair_fast<TR>(center - abscissa, center + abscissa, fv1[j], fv2[j], m);
+    }
+    const double f_center = g.template at_fast<TR>(center, m);
+    if (!m.ok) return qk_rule_slow<N, TR>(g, a, b);
+    return qk_reduce<N>(fv1, fv2, f_center, a, b);
+}
+
 // The Gauss-Kronrod rule of single/qk/naive.rs:32-106 for ONE thread: the thread evaluates
 // all 2N+1 nodes itself and accumulates the Kronrod / Gauss / |f| sums and the asc pass in
 // the reference's order (j = 0..N-1 from the centre outwards), so results are bit-equal
@@ -297,6 +362,12 @@ GKQ_DEV QK qk_rule_smem(const G& g, double a, double b, double* fv, int stride) 
 template <int N, int UNROLL, class G>
 GKQ_DEV QK qk_rule(const G& g, double a, double b) {
     using R = Rule<N>;
+#ifndef GKQ_NO_RULE_LIGHT
+    if constexpr (UNROLL >= N && !G::HEAVY) {
+        if (g.transform) return qk_rule_light<N, true>(g, a, b);
+        return qk_rule_light<N, false>(g, a, b);
+    }
+#endif
     double fv1[N], fv2[N];
     const double center = 0.5 * (a + b);
     const double half_length = 0.5 * (b - a);
@@ -313,6 +384,9 @@ GKQ_DEV QK qk_rule(const G& g, double a, double b) {
 template <int N, int UNROLL, bool TR, class G>
 GKQ_DEV QK qk_rule_fixed(const G& g, double a, double b) {
     using R = Rule<N>;
+#ifndef GKQ_NO_RULE_LIGHT
+    if constexpr (UNROLL >= N && !G::HEAVY) return qk_rule_light<N, TR>(g, a, b);
+#endif
     double fv1[N], fv2[N];
     const double center = 0.5 * (a + b);
     const double half_length = 0.5 * (b - a);

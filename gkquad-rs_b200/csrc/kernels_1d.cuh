@@ -993,12 +993,22 @@ __global__ void __launch_bounds__(BLOCK) k_qk_batch(const Batch1D P, double* out
 // ---- plain integrand evaluation y[i] = f(x[i]; p_i): the Integrand::apply_to_slice of the
 // reference (single/common.rs:135-137).  Also the micro-kernel on which the per-functor FP64
 // flop counts of the registry are measured with ncu (DADD + DMUL + 2*DFMA per evaluation).
+// mode 1: the sample as the rule kernels take it -- branch-free math first (FastMath: own exp / sin / cos /
+// log / pow, IEEE division and square root without the slow-path branch), re-evaluated through the
+// always-valid path when an operand left the fast range.  Must equal mode 0 bit for bit.
 template <class F, int NPARAMS>
-__global__ void __launch_bounds__(BLOCK) k_eval(const Batch1D P, const double* x, double* y) {
+__global__ void __launch_bounds__(BLOCK) k_eval(const Batch1D P, const double* x, double* y, int mode) {
     const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= P.n) return;
     F f;
     load_functor(f, P, i, NPARAMS);
+    if (mode == 1) {
+        FastMath m;
+        double v = f.eval(x[i], m);
+        if (!m.ok) v = f(x[i]);
+        y[i] = v;
+        return;
+    }
     y[i] = f(x[i]);
 }
 
@@ -1011,7 +1021,7 @@ struct Launch1D {
     void (*qagp)(const Batch1D&, int grid, cudaStream_t);
     void (*qag)(const Batch1D&, int grid, cudaStream_t);
     void (*qk[6])(const Batch1D&, double* out4, int grid, cudaStream_t);  // 17, 25, 33, 41, 49, 57 points
-    void (*eval)(const Batch1D&, const double* x, double* y, int grid, cudaStream_t);
+    void (*eval)(const Batch1D&, const double* x, double* y, int mode, int grid, cudaStream_t);
     int (*occupancy_loop)();   // resident blocks per SM of the persistent kernels
     int (*occupancy_qagp)();
     int (*occupancy_init25)();
@@ -1062,8 +1072,8 @@ GKQ_F1_LIST(GKQ_DECL_F1)
         L.qag = [](const Batch1D& P, int grid, cudaStream_t st) {                                    \
             k_qag<F1<ID>, NP><<<grid, ABLOCK, 0, st>>>(P);                                           \
         };                                                                                           \
-        L.eval = [](const Batch1D& P, const double* x, double* y, int grid, cudaStream_t st) {       \
-            k_eval<F1<ID>, NP><<<grid, BLOCK, 0, st>>>(P, x, y);                                     \
+        L.eval = [](const Batch1D& P, const double* x, double* y, int mode, int grid, cudaStream_t st) { \
+            k_eval<F1<ID>, NP><<<grid, BLOCK, 0, st>>>(P, x, y, mode);                                     \
         };                                                                                           \
         L.occupancy_loop = []() {                                                                    \
             int nb = 0;                                                                              \

@@ -522,6 +522,7 @@ struct InnerF {
     double x;
     bool swap;  // GKQ_FLAG_SWAP_XY: the integrand takes (inner, outer) -- DynamicX, qags.rs:37
     static constexpr bool PAIRWISE = false;
+    static constexpr bool HEAVY = F2T::HEAVY;
     GKQ_DEV double operator()(double y) const { return swap ? f(y, x) : f(x, y); }
     template <class M> GKQ_DEV double eval(double y, M& m) const {
         return swap ? f.eval(y, x, m) : f.eval(x, y, m);

@@ -30,6 +30,9 @@
 namespace gkq {
 
 constexpr int FB = 128;  // threads per block of the flat kernels
+#ifndef GKQ_FLAT_UNROLL
+#define GKQ_FLAT_UNROLL NESTED_UNROLL
+#endif
 #ifndef GKQ_FLAT_MIN_BLOCKS
 #define GKQ_FLAT_MIN_BLOCKS 4
 #endif
@@ -246,13 +249,13 @@ __global__ void __launch_bounds__(FB, GKQ_FLAT_MIN_BLOCKS) k2_inner(const Batch2
         q0.estimate = q0.delta = q0.absvalue = q0.asc = 0.;
         q1 = q0;
         if (!QAGP && __any_sync(FULL, p.has17)) {
-            if (p.has17) q0 = qk_rule<8, NESTED_UNROLL>(g, p.ra0, p.rb0);
+            if (p.has17) q0 = qk_rule<8, GKQ_FLAT_UNROLL>(g, p.ra0, p.rb0);
         }
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
             const bool on = hh ? p.has1 : p.has0;
             if (on) {
-                const QK q = qk_rule<12, NESTED_UNROLL>(g, hh ? p.ra1 : p.ra0, hh ? p.rb1 : p.rb0);
+                const QK q = qk_rule<12, GKQ_FLAT_UNROLL>(g, hh ? p.ra1 : p.ra0, hh ? p.rb1 : p.rb0);
                 if (hh) q1 = q; else q0 = q;
             }
         }

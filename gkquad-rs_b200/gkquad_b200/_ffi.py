@@ -52,7 +52,7 @@ SYMBOLS = [
     "gkq_abi_version", "gkq_config_default", "gkq_create", "gkq_create_prio", "gkq_destroy", "gkq_last_error",
     "gkq_functor_count", "gkq_functor_info", "gkq_functor_lookup", "gkq_integrate_batch",
     "gkq_integrate_batch_host", "gkq_integrate_batch_ex", "gkq_integrate_batch_host_ex", "gkq_integrate2_batch_ex", "gkq_integrate2_batch_host_ex", "gkq_integrate2_batch", "gkq_integrate2_batch_host", "gkq_qk_batch",
-    "gkq_functor_eval_batch",
+    "gkq_functor_eval_batch", "gkq_functor_eval_batch_ex",
     "gkq_set_deferred_join", "gkq_join", "gkq_sync", "gkq_get_stats", "gkq_reset_stats", "gkq_set_profiling", "gkq_get_profile",
     "gkq_measure_fp64_peak",
     "gkq_comm_get_unique_id", "gkq_comm_init", "gkq_comm_destroy", "gkq_comm_info", "gkq_shard_size",
@@ -101,6 +101,7 @@ def lib():
     L.gkq_integrate2_batch_host_ex.argtypes = batch2x
     L.gkq_qk_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int64, dp, dp, C.c_int64, dp, C.c_int64, dp, vp]
     L.gkq_functor_eval_batch.argtypes = [vp, C.c_int, C.c_int64, dp, dp, C.c_int64, dp, vp]
+    L.gkq_functor_eval_batch_ex.argtypes = [vp, C.c_int, C.c_int64, dp, dp, C.c_int64, dp, C.c_int, vp]
     L.gkq_set_deferred_join.argtypes = [vp, C.c_int]
     L.gkq_join.argtypes = [vp, vp]
     L.gkq_sync.argtypes = [vp, vp]

@@ -256,8 +256,9 @@ class Engine:
                                         self._ptr(pp), ps, out.data_ptr(), self._stream()))
         return out
 
-    def eval_batch(self, functor, x, params=None):
-        """y[i] = f(x[i]; params[:, i]) on the device (Integrand::apply_to_slice)."""
+    def eval_batch(self, functor, x, params=None, mode=0):
+        """y[i] = f(x[i]; params[:, i]) on the device (Integrand::apply_to_slice).  mode 1 = the sample as
+        the rule kernels take it (branch-free math first; gkq_functor_eval_batch_ex)."""
         import torch
         fid, fname, npar, _ = self.functor(1, functor)
         dev = f"cuda:{self.device}"
@@ -269,8 +270,8 @@ class Engine:
                 np.ascontiguousarray(np.asarray(params, dtype=np.float64)), device=dev)
             ps = n if pp.ndim == 2 else 0
         y = torch.empty(n, dtype=torch.float64, device=dev)
-        self._check(self.L.gkq_functor_eval_batch(self.h, fid, n, xx.data_ptr(), self._ptr(pp), ps,
-                                                  y.data_ptr(), self._stream()))
+        self._check(self.L.gkq_functor_eval_batch_ex(self.h, fid, n, xx.data_ptr(), self._ptr(pp), ps,
+                                                     y.data_ptr(), int(mode), self._stream()))
         return y
 
     # ---- 2-D ------------------------------------------------------------------------------

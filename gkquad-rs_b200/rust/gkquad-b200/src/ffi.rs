@@ -123,6 +123,9 @@ extern "C" {
     pub fn gkq_functor_eval_batch(h: gkq_handle_t, functor_id: c_int, n: i64, x: *const c_double,
                                   params: *const c_double, param_stride: i64, y: *mut c_double,
                                   stream: *mut c_void) -> c_int;
+    pub fn gkq_functor_eval_batch_ex(h: gkq_handle_t, functor_id: c_int, n: i64, x: *const c_double,
+                                     params: *const c_double, param_stride: i64, y: *mut c_double,
+                                     mode: c_int, stream: *mut c_void) -> c_int;
     pub fn gkq_set_deferred_join(h: gkq_handle_t, enable: c_int) -> c_int;
     pub fn gkq_join(h: gkq_handle_t, stream: *mut c_void) -> c_int;
     pub fn gkq_sync(h: gkq_handle_t, stream: *mut c_void) -> c_int;

@@ -255,6 +255,13 @@ int gkq_qk_batch(gkq_handle_t h, int rule, int functor_id, int64_t n, const doub
  * measured (ncu: DADD + DMUL + 2*DFMA thread instructions / n). */
 int gkq_functor_eval_batch(gkq_handle_t h, int functor_id, int64_t n, const double* x,
                            const double* params, int64_t param_stride, double* y, void* stream);
+/* The same with the evaluation path chosen: mode 0 = the always-valid path (what gkq_functor_eval_batch
+ * runs), mode 1 = the sample exactly as the rule kernels take it: branch-free math first (the engine's own
+ * exp / sin / cos / log / pow; IEEE division and square root without the compiler's slow-path branch), then
+ * re-evaluated through mode 0's path when an operand left the fast range.  Both modes must agree bit for
+ * bit on every input; the parity tests use this entry to check that against the CPU. */
+int gkq_functor_eval_batch_ex(gkq_handle_t h, int functor_id, int64_t n, const double* x,
+                              const double* params, int64_t param_stride, double* y, int mode, void* stream);
 
 /* Deferred-join mode (throughput pipelining of independent batches).  By default a batch call is
  * fully ordered on `stream`.  With deferred join enabled, gkq_integrate_batch still enqueues every

@@ -118,3 +118,64 @@ def test_pow_accuracy(eng, p):
     i0 = np.nonzero(x == 0.0)[0][0]
     assert got[i0] == want[i0]
     assert (got == want)[fin].mean() > 0.995
+
+
+def _edge_values():
+    """Operands around every threshold of the fast paths: zeros, denormals, the ends of the exponent
+    range, infinities, NaN, and values whose quotients / roots land in the denormal range."""
+    tiny = np.array([0.0, -0.0, 5e-324, 1e-310, 2.2250738585072014e-308, 4.4501477170144023e-308, 1e-300, 1e-292, 1e-290,
+                     6e-293, 7e-293, 1e-200, 1e-154, 1e-153, 1e-100])
+    mid = np.array([1e-10, 0.1, 1.0 / 3.0, 0.5, 1.0, 1.5, 2.0, 3.0, 10.0, 1e10])
+    huge = np.array([1e100, 1e153, 1e154, 1e200, 1e290, 1e300, 8.98846567431158e307, 1.7976931348623157e308, np.inf, np.nan])
+    v = np.concatenate([tiny, mid, huge])
+    return np.concatenate([v, -v])
+
+
+def test_branch_free_div_sqrt(eng):
+    """gk_div_fast / gk_sqrt_fast (csrc/gk_math.cuh) are nvcc's own fast paths of `/` and `sqrt` with the
+    slow-path branch turned into a flag: the sample path of the rule kernels (gkq_functor_eval_batch_ex,
+    mode 1) must return exactly IEEE's correctly rounded quotient / root -- what numpy computes on the host --
+    for random operands over the whole exponent range AND for every edge operand (where the flag sends the
+    sample through the compiler's own `/` and `sqrt`)."""
+    rng = np.random.default_rng(7)
+    n = 1 << 21
+    with np.errstate(all="ignore"):
+        # p / x : random magnitudes over the whole exponent range, then the cross product of the edge values
+        num = np.ldexp(rng.uniform(1.0, 2.0, n), rng.integers(-1060, 1020, n)) * rng.choice([-1.0, 1.0], n)
+        den = np.ldexp(rng.uniform(1.0, 2.0, n), rng.integers(-1060, 1020, n)) * rng.choice([-1.0, 1.0], n)
+        ev = _edge_values()
+        en, ed = np.meshgrid(ev, ev)
+        num = np.concatenate([num, en.ravel(), rng.uniform(0.5, 2.0, n)])
+        den = np.concatenate([den, ed.ravel(), rng.uniform(-1.0, 1.0, n)])
+        want = num / den
+        for mode in (0, 1):
+            got = eng.eval_batch("recip_p", den, params=num[None, :], mode=mode).cpu().numpy()
+            same = (got.view(np.uint64) == want.view(np.uint64)) | (np.isnan(got) & np.isnan(want))
+            assert same.all(), (mode, int((~same).sum()), num[~same][:4], den[~same][:4], got[~same][:4], want[~same][:4])
+        # sqrt(x - p): radicands over the whole range, negative ones, zeros, denormals, inf, nan
+        x = np.concatenate([np.ldexp(rng.uniform(1.0, 2.0, n), rng.integers(-1074, 1023, n)), np.abs(ev), -np.abs(ev),
+                            rng.uniform(-1.0, 4.0, n)])
+        want = np.sqrt(x)
+        for mode in (0, 1):
+            got = eng.eval_batch("sqrt_shift_p", x, params=np.zeros((1, x.size)), mode=mode).cpu().numpy()
+            same = (got.view(np.uint64) == want.view(np.uint64)) | (np.isnan(got) & np.isnan(want))
+            assert same.all(), (mode, int((~same).sum()), x[~same][:4], got[~same][:4], want[~same][:4])
+        # a body with both: 1 / (1 + p x^2) and the 2-D bodies run through the full-size parity tests
+
+
+def test_sample_path_equals_always_valid_path(eng):
+    """mode 1 (branch-free first) == mode 0 (always valid) bit for bit for every registered 1-D functor, on
+    arguments inside and far outside the fast ranges."""
+    rng = np.random.default_rng(11)
+    n = 1 << 18
+    x = np.concatenate([rng.uniform(-3.0, 3.0, n), rng.uniform(-1e6, 1e6, n // 4), np.ldexp(rng.uniform(1, 2, n // 4), rng.integers(-1070, 1020, n // 4)),
+                        _edge_values()])
+    for fid in range(eng.L.gkq_functor_count(1)):
+        _, name, npar, _ = eng.functor(1, fid)
+        p = rng.uniform(0.25, 3.0, (max(npar, 1), x.size))
+        if name == "sinpow_p":
+            p[0] = rng.integers(-6, 7, x.size)
+        a = eng.eval_batch(name, x, params=p if npar else None, mode=0).cpu().numpy()
+        b = eng.eval_batch(name, x, params=p if npar else None, mode=1).cpu().numpy()
+        same = (a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))
+        assert same.all(), (name, int((~same).sum()), x[~same][:4], a[~same][:4], b[~same][:4])
