@@ -214,7 +214,7 @@ struct gkq_handle_s {
     int occ_2df[F2_COUNT][2];
 
     Launch1D l1[F1_COUNT];
-    int occ_loop[F1_COUNT], occ_qagp[F1_COUNT], occ_init25[F1_COUNT];
+    int occ_loop[F1_COUNT], occ_qagp[F1_COUNT], occ_init25[F1_COUNT], occ_first[F1_COUNT];
     Launch2D l2[F2_COUNT];
     int occ_2d[F2_COUNT][2];
     int occ_2dw[F2_COUNT][2];
@@ -245,7 +245,7 @@ template <int ID>
 struct FillL1 {
     static void go(gkq_handle_s* h) {
         h->l1[ID] = make_launch1d<ID>();
-        h->occ_loop[ID] = h->occ_qagp[ID] = h->occ_init25[ID] = -1;
+        h->occ_loop[ID] = h->occ_qagp[ID] = h->occ_init25[ID] = h->occ_first[ID] = -1;
         FillL1<ID + 1>::go(h);
     }
 };
@@ -928,7 +928,8 @@ static int run_qags_bulk(gkq_handle_t h, const Launch1D& L, int fid, Batch1D P, 
     // the first-step kernel has its own shape: a persistent grid of 128-thread blocks that holds
     // (nearly) all loop entrants of a typical batch at once; the few threads that take a second
     // grid-stride trip overlap the other kernels in flight
-    long long gfirst = (long long)h->sm_count * GKQ_FIRST_MIN_BLOCKS;
+    if (h->occ_first[fid] < 0) h->occ_first[fid] = L.occupancy_first();
+    long long gfirst = (long long)h->sm_count * (h->occ_first[fid] > 0 ? h->occ_first[fid] : 1);
     const long long nb_first = (P.n + FBLOCK - 1) / FBLOCK;
     if (gfirst > nb_first) gfirst = nb_first;
 

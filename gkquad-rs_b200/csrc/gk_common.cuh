@@ -320,7 +320,11 @@ GKQ_DEV QK qk_rule_smem(const G& g, double a, double b, double* fv, int stride) 
 // branch-free math (m.div / m.sqrt, gk_math.cuh) in ONE basic block, so ptxas overlaps the dependent
 // chains of as many samples as the registers hold; if any operand left the fast range (denormal-range
 // quotients, huge divisors, negative or tiny radicands) the whole rule is redone by the out-of-line
-// always-valid version.  Same operations, same order, same results.
+// always-valid version.  Same operations, same order, same results.  (In between -- 2 or 4 node pairs per
+// loop trip with one flag per group, for the 2-D nest whose instruction footprint rules the full unrolling
+// out -- measured SLOWER than the pair-at-a-time loop with the compiler's division: D0 4.33 -> 5.19 / 5.48 ms,
+// D1 73.0 -> 81.2 / 90.5 ms, profiles/ab_branch_free_div_r02.txt; the fully unrolled rule in the nest's inner
+// kernel: D1 96 ms.  The nest keeps one pair per trip.)
 template <int N, bool TR, class G>
 __device__ __noinline__ QK qk_rule_slow(const G& g, double a, double b) {
     using R = Rule<N>;

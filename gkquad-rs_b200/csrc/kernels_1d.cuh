@@ -240,6 +240,14 @@ constexpr int IBLOCK = GKQ_INIT_BLOCK;
 #ifndef GKQ_INIT25_MIN_BLOCKS
 #define GKQ_INIT25_MIN_BLOCKS 6
 #endif
+// bodies without transcendental calls: their rules are fully unrolled and run branch-free (qk_rule_light),
+// so registers buy overlap of the samples' dependent chains
+#ifndef GKQ_LIGHT_MIN_BLOCKS
+#define GKQ_LIGHT_MIN_BLOCKS 6
+#endif
+#ifndef GKQ_LIGHT_FIRST_MIN_BLOCKS
+#define GKQ_LIGHT_FIRST_MIN_BLOCKS 5
+#endif
 // the persistent kernel: its loop also holds the list / epsilon-table code, so the rule is unrolled
 // less than in the flat kernels (instruction cache; profiles/)
 #ifndef GKQ_ADAPT_UNROLL_LIGHT
@@ -257,7 +265,8 @@ struct InitUnroll {
 // ---- QAGS initial passes -------------------------------------------------------------------
 // PASS 0: N = 8 (qk17) over the whole batch (or `worklist`); PASS 1: N = 12 (qk25) over list25.
 template <class F, int N, int NPARAMS>
-__global__ void __launch_bounds__(IBLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : GKQ_INIT25_MIN_BLOCKS) k_qags_init(const Batch1D P) {
+__global__ void __launch_bounds__(IBLOCK, F::HEAVY ? ((N == 8) ? GKQ_INIT17_MIN_BLOCKS : GKQ_INIT25_MIN_BLOCKS) : GKQ_LIGHT_MIN_BLOCKS)
+k_qags_init(const Batch1D P) {
     constexpr int PASS = (N == 8) ? 0 : 1;
 #ifndef GKQ_FV_LOCAL
     // transcendental bodies: the 2N samples of the rule live in the thread's shared-memory column
@@ -361,7 +370,7 @@ __global__ void __launch_bounds__(IBLOCK, (N == 8) ? GKQ_INIT17_MIN_BLOCKS : GKQ
 #endif
 constexpr int FBLOCK = GKQ_FIRST_BLOCK;
 template <class F, int NPARAMS>
-__global__ void __launch_bounds__(FBLOCK, GKQ_FIRST_MIN_BLOCKS) k_qags_first(const Batch1D P) {
+__global__ void __launch_bounds__(FBLOCK, F::HEAVY ? GKQ_FIRST_MIN_BLOCKS : GKQ_LIGHT_FIRST_MIN_BLOCKS) k_qags_first(const Batch1D P) {
 #ifndef GKQ_FV_LOCAL
     __shared__ double s_fv[F::HEAVY ? 24 * FBLOCK : 1];
 #endif
@@ -1025,6 +1034,7 @@ struct Launch1D {
     int (*occupancy_loop)();   // resident blocks per SM of the persistent kernels
     int (*occupancy_qagp)();
     int (*occupancy_init25)();
+    int (*occupancy_first)();
 };
 
 template <int ID>
@@ -1088,6 +1098,11 @@ GKQ_F1_LIST(GKQ_DECL_F1)
         L.occupancy_init25 = []() {                                                                  \
             int nb = 0;                                                                              \
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_qags_init<F1<ID>, 12, NP>, IBLOCK, 0); \
+            return nb;                                                                               \
+        };                                                                                           \
+        L.occupancy_first = []() {                                                                  \
+            int nb = 0;                                                                              \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_qags_first<F1<ID>, NP>, FBLOCK, 0); \
             return nb;                                                                               \
         };                                                                                           \
         return L;                                                                                    \
