@@ -464,6 +464,12 @@ def _main(args, real_stdout):
     if rank == 0:
         sampler.start()
         sampler.wait_first()
+    # No collector pause between two launches of the region: collected and switched off BEFORE the warm-up
+    # (a gc.collect() between warm-up and region idles the GPU for tens of milliseconds, its clocks drop,
+    # and the first timed steps run while they ramp up again: 0.119 -> 0.124 ms per step at K = 20).
+    import gc
+    gc.collect()
+    gc.disable()
     # (at least two deferred-join cycles of 8 batches per lane: every scratch buffer has reached its
     # steady-state size before the timed region)
     for k in range(max(18 * DEPTH, 2 * NSETS, args.warmup, 3)):
@@ -484,9 +490,6 @@ def _main(args, real_stdout):
     # The path shards with no data-path collective: each rank's results stay in its HBM; the job ends
     # with the gather of the last batch to rank 0 (inside the region).
     pipe.reset_stats()
-    import gc
-    gc.collect()
-    gc.disable()  # (no collector pause between two launches of the region)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
