@@ -295,6 +295,15 @@ def ncu_traffic(kernel_regex):
                 if re.search(kernel_regex, row[ik]):
                     best = {"bytes": float(row[ir]) * scale.get(units[ir], 1.0) + float(row[iw]) * scale.get(units[iw], 1.0),
                             "read_bytes": float(row[ir]) * scale.get(units[ir], 1.0), "source": f"profiles/{f.name}"}
+                    for key, col in (("registers_per_thread", "launch__registers_per_thread"),
+                                     ("warps_active_pct_of_peak", "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                                     ("fp64_pipe_busy_pct", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                                     ("inst_per_cycle_per_sm", "sm__inst_executed.avg.per_cycle_elapsed")):
+                        if col in h:
+                            try:
+                                best[key] = float(row[h.index(col)])
+                            except ValueError:
+                                pass
                     break
         except Exception:
             continue
@@ -623,6 +632,24 @@ def _main(args, real_stdout):
             "peak_source": "measured in this run: dependent-chain DFMA micro-kernel over all SMs (MEASURED_PEAKS.json has no FP64 figure)",
             "flops_per_eval": w_eval, "kernels": kernels,
             "whole_step": {"achieved": whole_tflops, "frac": whole_tflops / (peak_flops / 1e12)},
+            # SM occupancy / pipe utilisation of that kernel, from the same committed capture
+            "occupancy": ({k: traffic[k] for k in ("registers_per_thread", "warps_active_pct_of_peak", "fp64_pipe_busy_pct",
+                                                   "inst_per_cycle_per_sm") if k in traffic} if traffic else None),
+            # north_star's worklist compaction is not a pass of its own: survivors are appended to the next
+            # kernel's worklist inside the rule kernels (ballot + popc + one atomic per warp per list)
+            "compaction": {
+                "fused_into": "k_qags_init<qk17> / <qk25> (u32 worklists) and k_qags_first (176-byte straggler records)",
+                "survivors_per_step": {"to_qk25": int(stats["last_survivors_qk25"]),
+                                       "loop_entrants": int(sum(stats["last_chain_loop"])),
+                                       "straggler_records": int(sum(stats["last_chain_step2"]))},
+                "bytes_per_step": int(8 * (stats["last_survivors_qk25"] + sum(stats["last_chain_loop"]))
+                                      + 32 * 2 * sum(stats["last_chain_loop"]) + 176 * 2 * sum(stats["last_chain_step2"])),
+                "GBps_at_step_rate": (8 * (stats["last_survivors_qk25"] + sum(stats["last_chain_loop"]))
+                                      + 64 * sum(stats["last_chain_loop"]) + 352 * sum(stats["last_chain_step2"])) / (ms_per_step * 1e-3) / 1e9,
+                "hbm_peak_GBps": 6563.2,
+                "note": "4 B written + 4 B read per worklist entry, 32 B + 32 B per parked loop entrant, 176 B + 176 B per "
+                        "straggler record; cost of the appends measured by compiling them out: 4 % of k_qags_init<qk17> "
+                        "(profiles/S1_r01.md)"},
         }
 
     # ---- e2e: the public host entry (gkq_integrate_batch_host) with pinned host buffers ----------

@@ -103,8 +103,10 @@ public:
 // One engine (gkq_handle_t) per device; the counterpart of the state an Integrator owns.
 class Engine {
 public:
-    explicit Engine(int device = 0) {
-        int rc = gkq_create(device, &h_);
+    // stream_priority: CUDA priority of the streams the handle owns (0 = default, negative = scheduled
+    // first; gkq_create_prio) -- for the lane of a pipeline whose batches have to leave the GPU first
+    explicit Engine(int device = 0, int stream_priority = 0) {
+        int rc = gkq_create_prio(device, stream_priority, &h_);
         if (rc != GKQ_OK) throw GkqError(rc, gkq_last_error(nullptr));
     }
     ~Engine() { gkq_destroy(h_); }

@@ -81,8 +81,13 @@ pub struct EngineB200 {
 }
 impl EngineB200 {
     fn with_algo(device: i32, algo: i32) -> Result<Self, String> {
+        Self::with_algo_prio(device, algo, 0)
+    }
+    /// `stream_priority`: CUDA priority of the streams the handle owns (0 = default, negative = scheduled
+    /// first; `gkq_create_prio`) -- the express lane of a pipeline of engines.
+    fn with_algo_prio(device: i32, algo: i32, stream_priority: i32) -> Result<Self, String> {
         let mut h: ffi::gkq_handle_t = std::ptr::null_mut();
-        let rc = unsafe { ffi::gkq_create(device, &mut h) };
+        let rc = unsafe { ffi::gkq_create_prio(device, stream_priority, &mut h) };
         if rc != 0 {
             let msg = unsafe { std::ffi::CStr::from_ptr(ffi::gkq_last_error(std::ptr::null_mut())) };
             return Err(msg.to_string_lossy().into_owned());
