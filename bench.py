@@ -641,11 +641,11 @@ def _main(args, real_stdout):
                 "fused_into": "k_qags_init<qk17> / <qk25> (u32 worklists) and k_qags_first (176-byte straggler records)",
                 "survivors_per_step": {"to_qk25": int(stats["last_survivors_qk25"]),
                                        "loop_entrants": int(sum(stats["last_chain_loop"])),
-                                       "straggler_records": int(sum(stats["last_chain_step2"]))},
+                                       "straggler_records": int(stats["last_survivors_step2"])},
                 "bytes_per_step": int(8 * (stats["last_survivors_qk25"] + sum(stats["last_chain_loop"]))
-                                      + 32 * 2 * sum(stats["last_chain_loop"]) + 176 * 2 * sum(stats["last_chain_step2"])),
+                                      + 32 * 2 * sum(stats["last_chain_loop"]) + 176 * 2 * stats["last_survivors_step2"]),
                 "GBps_at_step_rate": (8 * (stats["last_survivors_qk25"] + sum(stats["last_chain_loop"]))
-                                      + 64 * sum(stats["last_chain_loop"]) + 352 * sum(stats["last_chain_step2"])) / (ms_per_step * 1e-3) / 1e9,
+                                      + 64 * sum(stats["last_chain_loop"]) + 352 * stats["last_survivors_step2"]) / (ms_per_step * 1e-3) / 1e9,
                 "hbm_peak_GBps": 6563.2,
                 "note": "4 B written + 4 B read per worklist entry, 32 B + 32 B per parked loop entrant, 176 B + 176 B per "
                         "straggler record; cost of the appends measured by compiling them out: 4 % of k_qags_init<qk17> "
