@@ -1404,7 +1404,14 @@ int gkq_integrate_batch_host_ex(gkq_handle_t h, const gkq_config* cfg, const gkq
     // the link as one word and the calling thread unpacks chunk c while chunk c + 1 is in flight.
     const bool is_qags_call = cfg->algo == GKQ_ALGO_QAGS || (cfg->algo == GKQ_ALGO_AUTO && cfg->npoints == 0);
     const bool heavy_tail_expected = is_qags_call && h->host_tail_fid == functor_id && h->host_tail_share > 1.0 / 16.0;
-    const bool packed = !heavy_tail_expected && cfg->max_evals < (1ull << 29) && getenv("GKQ_HOST_UNPACKED") == nullptr;
+    // ... when at least two host calls are in flight on the device: then the link is the bound and 4 fewer
+    // bytes per integral win (S1, 1 M integrals, 2 / 4 host threads: 0.679 -> 0.612 / 0.631 -> 0.576 ms per
+    // call).  A call that is alone is a serial chain with the calling thread's unpack pass at its end
+    // (0.2 ms for 1 M integrals at one core's memory bandwidth): four plain copies are faster there
+    // (1.02 -> 0.80 ms; profiles/e2e_sweep_r02.txt, second block).
+    const char* pk_env = getenv("GKQ_HOST_UNPACKED");
+    const bool pk_wanted = pk_env ? pk_env[0] == '0' : inflight.seen >= 2;
+    const bool packed = !heavy_tail_expected && cfg->max_evals < (1ull << 29) && pk_wanted;
     if (packed && N > h->pk_cap) {
         if (h->pk_pin) GKQ_CUDA(h, cudaFreeHost(h->pk_pin));
         h->pk_pin = nullptr;
