@@ -488,11 +488,12 @@ def _main(args, real_stdout):
         for s in range(NSETS):  # chunk plans are marshalled (and their scratch sized) outside the region
             for c in range(CH):
                 chunk_plan(s, c)
-        if world > 1:
-            last_step_chunked((steps - 1) % NSETS)
-        else:
-            last_step_express_only((steps - 1) % NSETS)
-        join()
+        for _ in range(3):  # (the express handle's remainder-grid estimate needs a flush or two behind it)
+            if world > 1:
+                last_step_chunked((steps - 1) % NSETS)
+            else:
+                last_step_express_only((steps - 1) % NSETS)
+            join()
     torch.cuda.synchronize()
 
     # ---- timed region: EXACTLY K steps between barrier + synchronize, device-timed -------------
